@@ -1,0 +1,170 @@
+/* sphb.h — C ABI of the B200-native SPH hot path (libsphb.so).
+ *
+ * This is the drop-in boundary for ONE path of lucien-vallois/sph-particle-simulator: the body of
+ * sph::SPHEngine::step(dt) (reference src/sph_engine.cpp:93-144) and the state accessors around it.
+ * The reference has no FFI seam of its own — callers link the concrete C++ class — so the seam is
+ * introduced here: a host-side SPHEngine shell (sph-particle-simulator_b200/host/) keeps the
+ * reference's public class surface and forwards the hot path through these entry points.
+ * Every function cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; all pointers are caller-owned HOST memory unless named d_*
+ *     (pinned host memory makes the copies asynchronous DMA, pageable memory works too)
+ *   - return 0 on success, a negative SPHB_E_* code on failure; never throws, never aborts;
+ *     sphb_last_error() gives the message of the last failure on that context
+ *   - a context is single-threaded (like the reference engine) and bound to one CUDA device
+ *   - particle order at this interface is ALWAYS the caller's insertion order (reference id = index,
+ *     src/particle.cpp:26-33); the device keeps particles cell-sorted internally
+ *   - there is NO CPU fallback: without a usable CUDA device sphb_create fails with SPHB_E_CUDA
+ */
+#ifndef SPHB_H_
+#define SPHB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPHB_VERSION 100
+
+typedef struct sphb_ctx sphb_ctx;
+
+enum {
+    SPHB_OK = 0,
+    SPHB_E_INVALID = -1,   /* bad argument / call order */
+    SPHB_E_CUDA = -2,      /* CUDA runtime failure (message has the CUDA error string) */
+    SPHB_E_CAPACITY = -3,  /* more particles than the context capacity */
+    SPHB_E_GRID = -4,      /* cell grid implied by bounds / positions exceeds the supported size */
+    SPHB_E_NOMEM = -5
+};
+
+/* POD mirror of sph::SPHParameters (reference src/sph_engine.h:14-34), same field order and
+ * defaults; 16 floats.  neighbor_search_radius is also the hash cell size (sph_engine.cpp:22). */
+typedef struct sphb_params {
+    float rest_density;           /* 1000   */
+    float gas_constant;           /* 2000   */
+    float viscosity;              /* 0.001  */
+    float smoothing_length;       /* 0.02   */
+    float particle_mass;          /* 0.001  */
+    float timestep;               /* 0.001  */
+    float gravity;                /* -9.81  */
+    float damping;                /* 0.99   */
+    float CFL_factor;             /* 0.4    */
+    float xmin, xmax, ymin, ymax, zmin, zmax; /* -1..1 each */
+    float neighbor_search_radius; /* 0.04   */
+} sphb_params;
+
+/* Mirror of SPHEngine::PerformanceStats (reference src/sph_engine.h:51-59).  Stage times are GPU
+ * times from CUDA events and are only accumulated while SPHB_OPT_STAGE_TIMING is 1;
+ * max_neighbors is the running maximum list length including self (sph_engine.cpp:351),
+ * total_neighbor_queries grows by N per step (the race-free value of sph_engine.cpp:350). */
+typedef struct sphb_stats {
+    double total_time;
+    double neighbor_search_time;
+    double density_computation_time;
+    double force_computation_time;
+    double integration_time;
+    uint64_t max_neighbors;
+    uint64_t total_neighbor_queries;
+    uint64_t steps;
+    uint64_t kernel_launches;      /* kernels of this library launched since the last reset */
+} sphb_stats;
+
+enum {
+    /* 0 = strict: every fp32 operation of density/force/integration is issued in the reference's
+     *     association order with IEEE round-to-nearest and no FMA contraction (bit-exact against
+     *     the reference compiled without -ffast-math);
+     * 1 = fast (default): FMA contraction, reciprocal/rsqrt forms — same neighbour sets, results
+     *     within the tolerances stated in DESIGN.md (the reference itself ships with -ffast-math). */
+    SPHB_OPT_MATH_MODE = 1,
+    /* neighbour-cell walk radius: 1 = 27 cells (default), 2 = 125 cells like SpatialHash::query_squared
+     * (reference src/spatial_hash.cpp:35) */
+    SPHB_OPT_WALK_RADIUS = 2,
+    /* 1 = record per-stage CUDA-event times into sphb_stats (adds event records; default 0) */
+    SPHB_OPT_STAGE_TIMING = 3,
+    /* 1 = keep per-particle cell keys and neighbour counts of every step for sphb_debug_dump (default 0) */
+    SPHB_OPT_DEBUG_CAPTURE = 4,
+    /* pair kernel variant: 0 = per-thread walk (baseline), 1 = warp-cooperative tiled walk (default) */
+    SPHB_OPT_PAIR_KERNEL = 5
+};
+
+/* ---- lifetime ---------------------------------------------------------------------------------
+ * replaces SPHEngine::SPHEngine(size_t max_particles) / ~SPHEngine (reference sph_engine.h:91-92,
+ * sph_engine.cpp:13-18).  device = CUDA ordinal. */
+int sphb_create(sphb_ctx** out, size_t capacity, int device);
+void sphb_destroy(sphb_ctx* ctx);
+const char* sphb_last_error(const sphb_ctx* ctx); /* ctx may be NULL: error of the last failed sphb_create */
+int sphb_version(void);
+
+int sphb_set_option(sphb_ctx* ctx, int option, int64_t value);
+int sphb_get_option(const sphb_ctx* ctx, int option, int64_t* value);
+/* Run all work of this context on the given cudaStream_t (0/NULL = the legacy default stream). */
+int sphb_set_stream(sphb_ctx* ctx, void* cuda_stream);
+int sphb_synchronize(sphb_ctx* ctx);
+
+/* ---- configuration ----------------------------------------------------------------------------
+ * replaces the parameter state that SPHEngine::initialize / set_parameters / set_gravity /
+ * set_viscosity / set_smoothing_length / set_boundaries establish (reference sph_engine.cpp:20-33,
+ * 152-172).  The Q1 quirk (cell size = neighbor_search_radius, not 2h) is the caller's to preserve:
+ * this call takes the final values verbatim. */
+int sphb_set_params(sphb_ctx* ctx, const sphb_params* p);
+int sphb_get_params(const sphb_ctx* ctx, sphb_params* p);
+
+/* ---- particle state ---------------------------------------------------------------------------
+ * sphb_upload replaces ParticleSystem::clear + add_particles as seen by the hot path (reference
+ * particle.cpp:22-39): the device state becomes exactly these n particles, id = index.
+ * vel3 == NULL → zero velocities; mass == NULL → params.particle_mass for every particle. */
+int sphb_upload(sphb_ctx* ctx, size_t n, const float* pos3, const float* vel3, const float* mass);
+/* Strided variant for an array-of-structs such as the reference's 76-byte sph::Particle
+ * (particle.h:17-49): byte offsets of position[3], velocity[3], mass inside each record. */
+int sphb_upload_strided(sphb_ctx* ctx, size_t n, const void* base, size_t stride,
+                        size_t off_pos, size_t off_vel, size_t off_mass);
+/* replaces the getters SPHEngine::get_positions/get_velocities/get_densities/get_pressures
+ * (sph_engine.h:133-136) and the engine's accelerations_ buffer (sph_engine.h:64).  Each output is
+ * in insertion order, n entries (n*3 for vectors); any pointer may be NULL. */
+int sphb_download(sphb_ctx* ctx, float* pos3, float* vel3, float* rho, float* pressure, float* acc3);
+/* Write position/velocity/density/pressure back into an array-of-structs (byte offsets; pass
+ * (size_t)-1 for a field to skip). */
+int sphb_download_strided(sphb_ctx* ctx, void* base, size_t stride, size_t off_pos, size_t off_vel,
+                          size_t off_density, size_t off_pressure);
+int sphb_size(const sphb_ctx* ctx, size_t* n);
+
+/* ---- the hot path -----------------------------------------------------------------------------
+ * replaces SPHEngine::step(float dt) (reference sph_engine.cpp:93-144): neighbour build, density +
+ * EOS, pressure + viscosity force, leapfrog, AABB clamp, time += dt.  dt <= 0 selects the adaptive
+ * CFL timestep of SPHEngine::compute_cfl_timestep (sph_engine.cpp:312-333), evaluated on the device
+ * including its "particle 0 only" force criterion.  Asynchronous: returns after enqueueing. */
+int sphb_step(sphb_ctx* ctx, float dt);
+/* replaces SPHEngine::run_steps (sph_engine.cpp:146-150): n steps with fixed dt, or adaptive if dt <= 0 */
+int sphb_run_steps(sphb_ctx* ctx, size_t n, float dt);
+
+/* replaces get_current_time / get_step_count (sph_engine.h:111-112); synchronises. */
+int sphb_get_time(sphb_ctx* ctx, float* current_time, uint64_t* step_count);
+/* clear_particles resets time and step count, initialize_* do not (sph_engine.cpp:47,87-91) */
+int sphb_set_time(sphb_ctx* ctx, float current_time, uint64_t step_count);
+/* the dt the NEXT adaptive step would use (compute_cfl_timestep, sph_engine.cpp:312-333); synchronises */
+int sphb_cfl_timestep(sphb_ctx* ctx, float* dt);
+
+/* ---- diagnostics ------------------------------------------------------------------------------
+ * replaces get_performance_stats / reset_performance_stats (sph_engine.h:124-125) */
+int sphb_get_stats(sphb_ctx* ctx, sphb_stats* out);
+int sphb_reset_stats(sphb_ctx* ctx);
+/* Device reductions behind get_total_mass / get_total_energy / compute_conservation_errors
+ * (sph_engine.cpp:178-200), accumulated in fp64: sum_density = Σ rho_i (caller multiplies by h^3),
+ * kinetic = Σ 0.5 m_i |v_i|^2, max_speed = max |v_i|.  Any pointer may be NULL. */
+int sphb_diagnostics(sphb_ctx* ctx, double* sum_density, double* kinetic, float* max_speed);
+
+/* Parity hooks (need SPHB_OPT_DEBUG_CAPTURE = 1 before the step), all for the LAST step, i.e. for
+ * the positions that step's neighbour build saw:
+ *   keys[i]      63-bit cell key of particle i — SpatialHash::hash_position (spatial_hash.h:20-36)
+ *   perm[s]      id of the particle in sorted slot s == std::stable_sort of ids by keys[]
+ *   nbr_count[i] neighbour-list length of particle i, self included (spatial_hash.cpp:31-57)
+ * Any pointer may be NULL. */
+int sphb_debug_dump(sphb_ctx* ctx, uint64_t* keys, uint32_t* perm, uint32_t* nbr_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPHB_H_ */

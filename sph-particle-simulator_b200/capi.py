@@ -1,0 +1,251 @@
+"""ctypes binding of the C ABI in include/sphb.h (libsphb.so).
+
+Thin by design: one Python method per C entry point, numpy arrays in and out, every non-zero
+return code raised as :class:`SphbError` with the library's own message.  There is no fallback of
+any kind — if the shared library is missing or no CUDA device is usable this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+LIB_PATH = HERE / "libsphb.so"
+
+PARAM_FIELDS = (
+    "rest_density", "gas_constant", "viscosity", "smoothing_length", "particle_mass",
+    "timestep", "gravity", "damping", "CFL_factor",
+    "xmin", "xmax", "ymin", "ymax", "zmin", "zmax", "neighbor_search_radius",
+)
+
+# reference defaults, src/sph_engine.h:14-34
+DEFAULT_PARAMS = dict(
+    rest_density=1000.0, gas_constant=2000.0, viscosity=0.001, smoothing_length=0.02,
+    particle_mass=0.001, timestep=0.001, gravity=-9.81, damping=0.99, CFL_factor=0.4,
+    xmin=-1.0, xmax=1.0, ymin=-1.0, ymax=1.0, zmin=-1.0, zmax=1.0, neighbor_search_radius=0.04,
+)
+
+OPT_MATH_MODE = 1
+OPT_WALK_RADIUS = 2
+OPT_STAGE_TIMING = 3
+OPT_DEBUG_CAPTURE = 4
+OPT_PAIR_KERNEL = 5
+MATH_STRICT = 0
+MATH_FAST = 1
+
+# every symbol include/sphb.h declares (tests/test_abi.py checks the library exports all of them)
+ABI_SYMBOLS = (
+    "sphb_create", "sphb_destroy", "sphb_last_error", "sphb_version", "sphb_set_option", "sphb_get_option",
+    "sphb_set_stream", "sphb_synchronize", "sphb_set_params", "sphb_get_params", "sphb_upload",
+    "sphb_upload_strided", "sphb_download", "sphb_download_strided", "sphb_size", "sphb_step", "sphb_run_steps",
+    "sphb_get_time", "sphb_set_time", "sphb_cfl_timestep", "sphb_get_stats", "sphb_reset_stats",
+    "sphb_diagnostics", "sphb_debug_dump",
+)
+
+
+class SphbParams(C.Structure):
+    _fields_ = [(k, C.c_float) for k in PARAM_FIELDS]
+
+
+class SphbStats(C.Structure):
+    _fields_ = [
+        ("total_time", C.c_double), ("neighbor_search_time", C.c_double),
+        ("density_computation_time", C.c_double), ("force_computation_time", C.c_double),
+        ("integration_time", C.c_double), ("max_neighbors", C.c_uint64),
+        ("total_neighbor_queries", C.c_uint64), ("steps", C.c_uint64), ("kernel_launches", C.c_uint64),
+    ]
+
+
+class SphbError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"sphb error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load libsphb.so (built in-tree by csrc/build.sh); raises if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise FileNotFoundError(f"{LIB_PATH} not built — run __graft_entry__.build() (sph-particle-simulator_b200/csrc/build.sh)")
+    L = C.CDLL(str(LIB_PATH))
+    vp, sz, fp = C.c_void_p, C.c_size_t, C.POINTER(C.c_float)
+    L.sphb_version.restype = C.c_int
+    L.sphb_last_error.restype = C.c_char_p
+    L.sphb_last_error.argtypes = [vp]
+    L.sphb_create.argtypes = [C.POINTER(vp), sz, C.c_int]
+    L.sphb_destroy.argtypes = [vp]
+    L.sphb_destroy.restype = None
+    L.sphb_set_option.argtypes = [vp, C.c_int, C.c_int64]
+    L.sphb_get_option.argtypes = [vp, C.c_int, C.POINTER(C.c_int64)]
+    L.sphb_set_stream.argtypes = [vp, vp]
+    L.sphb_synchronize.argtypes = [vp]
+    L.sphb_set_params.argtypes = [vp, C.POINTER(SphbParams)]
+    L.sphb_get_params.argtypes = [vp, C.POINTER(SphbParams)]
+    L.sphb_upload.argtypes = [vp, sz, vp, vp, vp]
+    L.sphb_upload_strided.argtypes = [vp, sz, vp, sz, sz, sz, sz]
+    L.sphb_download.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.sphb_download_strided.argtypes = [vp, vp, sz, sz, sz, sz, sz]
+    L.sphb_size.argtypes = [vp, C.POINTER(sz)]
+    L.sphb_step.argtypes = [vp, C.c_float]
+    L.sphb_run_steps.argtypes = [vp, sz, C.c_float]
+    L.sphb_get_time.argtypes = [vp, fp, C.POINTER(C.c_uint64)]
+    L.sphb_set_time.argtypes = [vp, C.c_float, C.c_uint64]
+    L.sphb_cfl_timestep.argtypes = [vp, fp]
+    L.sphb_get_stats.argtypes = [vp, C.POINTER(SphbStats)]
+    L.sphb_reset_stats.argtypes = [vp]
+    L.sphb_diagnostics.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), fp]
+    L.sphb_debug_dump.argtypes = [vp, vp, vp, vp]
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return C.c_void_p(a.ctypes.data)
+
+
+class Context:
+    """One sphb_ctx: the device-side state of one engine on one GPU."""
+
+    def __init__(self, capacity: int, device: int = 0):
+        self.L = load_library()
+        self.capacity = int(capacity)
+        h = C.c_void_p()
+        rc = self.L.sphb_create(C.byref(h), self.capacity, int(device))
+        if rc != 0:
+            raise SphbError(rc, (self.L.sphb_last_error(None) or b"").decode())
+        self.h = h
+
+    def _ck(self, rc: int):
+        if rc != 0:
+            raise SphbError(rc, (self.L.sphb_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.sphb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- options / configuration ----------------------------------------------------------------
+    def set_option(self, opt: int, value: int):
+        self._ck(self.L.sphb_set_option(self.h, opt, int(value)))
+
+    def get_option(self, opt: int) -> int:
+        v = C.c_int64()
+        self._ck(self.L.sphb_get_option(self.h, opt, C.byref(v)))
+        return v.value
+
+    def set_stream(self, cuda_stream: int):
+        self._ck(self.L.sphb_set_stream(self.h, C.c_void_p(int(cuda_stream))))
+
+    def synchronize(self):
+        self._ck(self.L.sphb_synchronize(self.h))
+
+    def set_params(self, params: dict):
+        p = SphbParams(**{k: float(params[k]) for k in PARAM_FIELDS})
+        self._ck(self.L.sphb_set_params(self.h, C.byref(p)))
+
+    def get_params(self) -> dict:
+        p = SphbParams()
+        self._ck(self.L.sphb_get_params(self.h, C.byref(p)))
+        return {k: np.float32(getattr(p, k)) for k in PARAM_FIELDS}
+
+    # ---- state ------------------------------------------------------------------------------------
+    def upload(self, pos, vel=None, mass=None):
+        """pos (n,3), vel (n,3) or None, mass (n,) or None — numpy float32 (copied if not contiguous)."""
+        pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+        n = pos.shape[0]
+        vel = None if vel is None else np.ascontiguousarray(vel, np.float32).reshape(n, 3)
+        mass = None if mass is None else np.ascontiguousarray(np.broadcast_to(np.asarray(mass, np.float32), (n,)))
+        self._ck(self.L.sphb_upload(self.h, n, _ptr(pos), _ptr(vel), _ptr(mass)))
+
+    def upload_raw(self, n: int, pos_ptr: int, vel_ptr: int | None, mass_ptr: int | None):
+        """Upload from raw host pointers (e.g. pinned torch tensors' data_ptr())."""
+        self._ck(self.L.sphb_upload(self.h, int(n), _ptr(pos_ptr), _ptr(vel_ptr), _ptr(mass_ptr)))
+
+    def upload_strided(self, n: int, base_ptr: int, stride: int, off_pos: int, off_vel: int, off_mass: int):
+        self._ck(self.L.sphb_upload_strided(self.h, int(n), C.c_void_p(base_ptr), stride, off_pos, off_vel, off_mass))
+
+    @property
+    def size(self) -> int:
+        n = C.c_size_t()
+        self._ck(self.L.sphb_size(self.h, C.byref(n)))
+        return n.value
+
+    def download(self, pos=True, vel=True, rho=True, pressure=True, acc=True) -> dict:
+        n = self.size
+        out = {}
+        if pos: out["pos"] = np.zeros((n, 3), np.float32)
+        if vel: out["vel"] = np.zeros((n, 3), np.float32)
+        if rho: out["rho"] = np.zeros(n, np.float32)
+        if pressure: out["P"] = np.zeros(n, np.float32)
+        if acc: out["acc"] = np.zeros((n, 3), np.float32)
+        self._ck(self.L.sphb_download(self.h, _ptr(out.get("pos")), _ptr(out.get("vel")), _ptr(out.get("rho")),
+                                      _ptr(out.get("P")), _ptr(out.get("acc"))))
+        return out
+
+    def download_raw(self, pos_ptr=None, vel_ptr=None, rho_ptr=None, p_ptr=None, acc_ptr=None):
+        self._ck(self.L.sphb_download(self.h, _ptr(pos_ptr), _ptr(vel_ptr), _ptr(rho_ptr), _ptr(p_ptr), _ptr(acc_ptr)))
+
+    def download_strided(self, base_ptr: int, stride: int, off_pos, off_vel, off_density, off_pressure):
+        none = (1 << 64) - 1
+        f = lambda o: none if o is None else int(o)
+        self._ck(self.L.sphb_download_strided(self.h, C.c_void_p(base_ptr), stride, f(off_pos), f(off_vel), f(off_density),
+                                              f(off_pressure)))
+
+    # ---- stepping -----------------------------------------------------------------------------------
+    def step(self, dt: float = 0.0):
+        self._ck(self.L.sphb_step(self.h, float(dt)))
+
+    def run_steps(self, n: int, dt: float = 0.0):
+        self._ck(self.L.sphb_run_steps(self.h, int(n), float(dt)))
+
+    def get_time(self):
+        t, s = C.c_float(), C.c_uint64()
+        self._ck(self.L.sphb_get_time(self.h, C.byref(t), C.byref(s)))
+        return t.value, s.value
+
+    def set_time(self, t: float, step_count: int):
+        self._ck(self.L.sphb_set_time(self.h, float(t), int(step_count)))
+
+    def cfl_timestep(self) -> float:
+        dt = C.c_float()
+        self._ck(self.L.sphb_cfl_timestep(self.h, C.byref(dt)))
+        return dt.value
+
+    # ---- diagnostics ----------------------------------------------------------------------------
+    def stats(self) -> dict:
+        s = SphbStats()
+        self._ck(self.L.sphb_get_stats(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in SphbStats._fields_}
+
+    def reset_stats(self):
+        self._ck(self.L.sphb_reset_stats(self.h))
+
+    def diagnostics(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_float()
+        self._ck(self.L.sphb_diagnostics(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def debug_dump(self) -> dict:
+        n = self.size
+        keys = np.zeros(n, np.uint64)
+        perm = np.zeros(n, np.uint32)
+        cnt = np.zeros(n, np.uint32)
+        self._ck(self.L.sphb_debug_dump(self.h, _ptr(keys), _ptr(perm), _ptr(cnt)))
+        return {"keys": keys, "perm": perm, "nbr_count": cnt}

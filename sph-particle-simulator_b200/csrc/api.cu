@@ -1,0 +1,700 @@
+// C ABI of libsphb.so (include/sphb.h): context, buffers, step orchestration.
+// Host-side C++ only touches plain pointers and CUDA runtime calls; there is no CPU compute path.
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "sphb_internal.cuh"
+
+namespace sphb {
+int launch_cfl_probe(DeviceScalars* sc, IntegrateConsts ic, cudaStream_t st);
+int launch_unpack_strided(size_t n, const unsigned char* d_base, size_t stride, size_t off_pos, size_t off_vel, size_t off_mass,
+                          float4* posm, float4* velid, DeviceScalars* sc, cudaStream_t st);
+}
+
+using namespace sphb;
+
+namespace {
+thread_local char g_create_error[512] = "";
+constexpr uint64_t kMaxCells = 1ull << 28;
+constexpr int kMaxCoord = 1 << 20;  // |cell coordinate| limit for an injective reference key
+}  // namespace
+
+struct sphb_ctx {
+    int device = 0;
+    size_t capacity = 0;
+    size_t n = 0;
+    cudaStream_t stream = nullptr;
+
+    sphb_params prm{};
+    bool have_params = false;
+
+    int math_mode = 1;
+    int walk_radius = 1;
+    int stage_timing = 0;
+    int debug_capture = 0;
+    int pair_kernel = 1;
+
+    float4* posm[2] = {nullptr, nullptr};
+    float4* velid[2] = {nullptr, nullptr};
+    int cur = 0;
+    float2* rho_p = nullptr;
+    float4* fa = nullptr;
+    float4* fb = nullptr;
+    float4* acc = nullptr;
+    uint32_t* nbr_count = nullptr;
+    uint64_t* refkeys[2] = {nullptr, nullptr};
+    SortBuffers sb{};
+    uint32_t* cell_start = nullptr;
+    size_t cell_cap = 0;
+    DeviceScalars* sc = nullptr;
+    DeviceScalars* h_sc = nullptr;  // pinned mirror for read-back
+    unsigned char* d_stage = nullptr;
+    size_t stage_bytes = 0;
+    unsigned char* h_bounce = nullptr;  // pinned bounce buffer for the strided download
+    size_t bounce_bytes = 0;
+
+    // float bounding box of the positions currently on the device (valid when n > 0)
+    float box_min[3] = {0, 0, 0}, box_max[3] = {0, 0, 0};
+    bool box_pending = false;  // box must be read back from the device (after an upload)
+    int* d_box = nullptr;      // 6 ordered-int encoded floats
+    bool stepped_since_upload = false;
+
+    uint64_t step_count = 0;
+    sphb_stats stats{};
+    cudaEvent_t ev[6] = {};
+
+    char err[512] = "";
+};
+
+namespace {
+
+int fail(sphb_ctx* c, int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    if (c) vsnprintf(c->err, sizeof(c->err), fmt, ap);
+    else vsnprintf(g_create_error, sizeof(g_create_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(c, call)                                                                                   \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) return fail((c), SPHB_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+int bits_for(uint64_t count) {  // bits needed to represent values 0..count-1
+    int b = 1;
+    while (b < 63 && (1ull << b) < count) ++b;
+    return b;
+}
+
+int ensure_stage(sphb_ctx* c, size_t bytes) {
+    if (bytes <= c->stage_bytes) return SPHB_OK;
+    if (c->d_stage) cudaFree(c->d_stage);
+    c->d_stage = nullptr;
+    c->stage_bytes = 0;
+    CU(c, cudaMalloc(&c->d_stage, bytes));
+    c->stage_bytes = bytes;
+    return SPHB_OK;
+}
+
+int ensure_bounce(sphb_ctx* c, size_t bytes) {
+    if (bytes <= c->bounce_bytes) return SPHB_OK;
+    if (c->h_bounce) cudaFreeHost(c->h_bounce);
+    c->h_bounce = nullptr;
+    c->bounce_bytes = 0;
+    CU(c, cudaMallocHost(&c->h_bounce, bytes));
+    c->bounce_bytes = bytes;
+    return SPHB_OK;
+}
+
+int ensure_debug(sphb_ctx* c) {
+    if (c->refkeys[0]) return SPHB_OK;
+    const size_t cap = c->capacity ? c->capacity : 1;
+    CU(c, cudaMalloc(&c->refkeys[0], cap * sizeof(uint64_t)));
+    CU(c, cudaMalloc(&c->refkeys[1], cap * sizeof(uint64_t)));
+    CU(c, cudaMalloc(&c->nbr_count, cap * sizeof(uint32_t)));
+    CU(c, cudaMemset(c->refkeys[0], 0, cap * sizeof(uint64_t)));
+    CU(c, cudaMemset(c->refkeys[1], 0, cap * sizeof(uint64_t)));
+    CU(c, cudaMemset(c->nbr_count, 0, cap * sizeof(uint32_t)));
+    return SPHB_OK;
+}
+
+// ordered-int decoding of the device bounding box (see k_pack_upload's encode)
+float decode_ordered(int v) {
+    int s = v >= 0 ? v : v ^ 0x7FFFFFFF;
+    float f;
+    memcpy(&f, &s, 4);
+    return f;
+}
+
+int fetch_box(sphb_ctx* c) {
+    if (!c->box_pending) return SPHB_OK;
+    int h[6];
+    CU(c, cudaMemcpyAsync(h, c->d_box, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    for (int a = 0; a < 3; ++a) {
+        c->box_min[a] = decode_ordered(h[a]);
+        c->box_max[a] = decode_ordered(h[3 + a]);
+    }
+    c->box_pending = false;
+    return SPHB_OK;
+}
+
+int host_cell(float p, float inv_cell) {
+    float f = floorf(p * inv_cell);
+    if (!(f == f)) return 0;
+    if (f < -2147483000.0f) return -2147483647;
+    if (f > 2147483000.0f) return 2147483647;
+    return (int)f;
+}
+
+int make_grid(sphb_ctx* c, GridDesc* g) {
+    const float cell = c->prm.neighbor_search_radius;
+    if (!(cell > 0.0f)) return fail(c, SPHB_E_INVALID, "neighbor_search_radius must be > 0 (got %g)", (double)cell);
+    g->inv_cell = 1.0f / cell;  // SpatialHash::set_cell_size, reference spatial_hash.h:63-66
+    uint64_t ncells = 1;
+    for (int a = 0; a < 3; ++a) {
+        int lo = host_cell(c->box_min[a], g->inv_cell), hi = host_cell(c->box_max[a], g->inv_cell);
+        if (hi < lo) { int t = lo; lo = hi; hi = t; }
+        if (lo < -kMaxCoord || hi >= kMaxCoord)
+            return fail(c, SPHB_E_GRID, "cell coordinates [%d, %d] on axis %d exceed the 21-bit key range", lo, hi, a);
+        g->lo[a] = lo;
+        g->hi[a] = hi;
+        g->ext[a] = hi - lo + 1;
+        g->pos_lo[a] = lo > 0 ? lo : 0;
+        g->npos[a] = hi >= g->pos_lo[a] ? hi - g->pos_lo[a] + 1 : 0;
+        ncells *= (uint64_t)g->ext[a];
+        if (ncells > kMaxCells)
+            return fail(c, SPHB_E_GRID, "dense cell table would need more than %llu cells (box / neighbor_search_radius too large)",
+                        (unsigned long long)kMaxCells);
+    }
+    g->ncells = (uint32_t)ncells;
+    g->id_bits = bits_for(c->capacity > 1 ? c->capacity : 2);
+    g->cell_bits = bits_for(ncells > 1 ? ncells : 2);
+    if (g->id_bits + g->cell_bits > 64) return fail(c, SPHB_E_GRID, "composite sort key exceeds 64 bits");
+    return SPHB_OK;
+}
+
+int ensure_cell_table(sphb_ctx* c, const GridDesc& g) {
+    const size_t need = (size_t)g.ncells + 1;
+    const size_t need_bs = need / kScanTile + 2;
+    if (need > c->cell_cap) {
+        if (c->cell_start) cudaFree(c->cell_start);
+        c->cell_start = nullptr;
+        c->cell_cap = 0;
+        CU(c, cudaMalloc(&c->cell_start, need * sizeof(uint32_t)));
+        c->cell_cap = need;
+    }
+    if (need_bs > c->sb.block_sums_cap) {
+        if (c->sb.block_sums) cudaFree(c->sb.block_sums);
+        c->sb.block_sums = nullptr;
+        c->sb.block_sums_cap = 0;
+        CU(c, cudaMalloc(&c->sb.block_sums, need_bs * sizeof(uint32_t)));
+        c->sb.block_sums_cap = need_bs;
+    }
+    return SPHB_OK;
+}
+
+PairConsts make_pair_consts(const sphb_params& p) {
+    PairConsts k;
+    const float h = p.smoothing_length;
+    k.h = h;
+    k.h_sq = h * h;                                   // kernels.cpp:13
+    k.sigma = 1.0f / (static_cast<float>(M_PI) * h * h * h);  // kernels.cpp:27
+    k.r2 = p.neighbor_search_radius * p.neighbor_search_radius;  // sph_engine.cpp:347
+    k.w0 = k.sigma * (2.0f / 3.0f);                   // W(0): sigma * (2/3 - 0*0 + 0.5*0*0*0)
+    k.rest_density = p.rest_density;
+    k.gas_constant = p.gas_constant;
+    k.viscosity = p.viscosity;
+    k.gravity = p.gravity;
+    k.inv_h = 1.0f / h;
+    k.sig_h = k.sigma / h;
+    k.sig_h2 = k.sigma / k.h_sq;
+    return k;
+}
+
+IntegrateConsts make_integrate_consts(const sphb_params& p) {
+    IntegrateConsts ic;
+    ic.damping = p.damping;
+    ic.xmin = p.xmin; ic.xmax = p.xmax; ic.ymin = p.ymin; ic.ymax = p.ymax; ic.zmin = p.zmin; ic.zmax = p.zmax;
+    ic.cfl = p.CFL_factor;
+    ic.h = p.smoothing_length;
+    ic.timestep = p.timestep;
+    return ic;
+}
+
+void free_all(sphb_ctx* c) {
+    cudaSetDevice(c->device);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->posm[i]); cudaFree(c->velid[i]); cudaFree(c->refkeys[i]);
+        cudaFree(c->sb.keys[i]); cudaFree(c->sb.vals[i]);
+    }
+    cudaFree(c->rho_p); cudaFree(c->fa); cudaFree(c->fb); cudaFree(c->acc); cudaFree(c->nbr_count);
+    cudaFree(c->sb.counts); cudaFree(c->sb.block_sums); cudaFree(c->cell_start);
+    cudaFree(c->sc); cudaFree(c->d_stage); cudaFree(c->d_box);
+    if (c->h_sc) cudaFreeHost(c->h_sc);
+    if (c->h_bounce) cudaFreeHost(c->h_bounce);
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+}
+
+int read_scalars(sphb_ctx* c) {
+    CU(c, cudaMemcpyAsync(c->h_sc, c->sc, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return SPHB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sphb_version(void) { return SPHB_VERSION; }
+
+const char* sphb_last_error(const sphb_ctx* ctx) { return ctx ? ctx->err : g_create_error; }
+
+int sphb_create(sphb_ctx** out, size_t capacity, int device) {
+    if (!out) return fail(nullptr, SPHB_E_INVALID, "sphb_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, SPHB_E_CUDA, "no usable CUDA device (%s); libsphb has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= ndev) return fail(nullptr, SPHB_E_INVALID, "device %d out of range [0, %d)", device, ndev);
+    if (capacity >= (1ull << 32) - 1) return fail(nullptr, SPHB_E_CAPACITY, "capacity must be below 2^32 - 1");
+    sphb_ctx* c = new (std::nothrow) sphb_ctx();
+    if (!c) return fail(nullptr, SPHB_E_NOMEM, "out of host memory");
+    c->device = device;
+    c->capacity = capacity;
+    const size_t cap = capacity ? capacity : 1;
+    const size_t ntiles = (cap + kSortTile - 1) / kSortTile;
+#define CUC(call)                                                                                         \
+    do {                                                                                                  \
+        cudaError_t e2_ = (call);                                                                         \
+        if (e2_ != cudaSuccess) {                                                                         \
+            fail(nullptr, SPHB_E_CUDA, "%s: %s", #call, cudaGetErrorString(e2_));                         \
+            free_all(c);                                                                                  \
+            delete c;                                                                                     \
+            return SPHB_E_CUDA;                                                                           \
+        }                                                                                                 \
+    } while (0)
+    CUC(cudaSetDevice(device));
+    for (int i = 0; i < 2; ++i) {
+        CUC(cudaMalloc(&c->posm[i], cap * sizeof(float4)));
+        CUC(cudaMalloc(&c->velid[i], cap * sizeof(float4)));
+        CUC(cudaMalloc(&c->sb.keys[i], cap * sizeof(uint64_t)));
+        CUC(cudaMalloc(&c->sb.vals[i], cap * sizeof(uint32_t)));
+    }
+    CUC(cudaMalloc(&c->rho_p, cap * sizeof(float2)));
+    CUC(cudaMalloc(&c->fa, cap * sizeof(float4)));
+    CUC(cudaMalloc(&c->fb, cap * sizeof(float4)));
+    CUC(cudaMalloc(&c->acc, cap * sizeof(float4)));
+    // densities_/pressures_/accelerations_ are value-initialised by initialize() (sph_engine.cpp:26-28)
+    CUC(cudaMemset(c->rho_p, 0, cap * sizeof(float2)));
+    CUC(cudaMemset(c->acc, 0, cap * sizeof(float4)));
+    c->sb.counts_cap = 256 * ntiles;
+    CUC(cudaMalloc(&c->sb.counts, c->sb.counts_cap * sizeof(uint32_t)));
+    c->sb.block_sums_cap = c->sb.counts_cap / kScanTile + 2;
+    CUC(cudaMalloc(&c->sb.block_sums, c->sb.block_sums_cap * sizeof(uint32_t)));
+    CUC(cudaMalloc(&c->sc, sizeof(DeviceScalars)));
+    CUC(cudaMemset(c->sc, 0, sizeof(DeviceScalars)));
+    CUC(cudaMallocHost(&c->h_sc, sizeof(DeviceScalars)));
+    memset(c->h_sc, 0, sizeof(DeviceScalars));
+    CUC(cudaMalloc(&c->d_box, 6 * sizeof(int)));
+    for (auto& ev : c->ev) CUC(cudaEventCreate(&ev));
+#undef CUC
+    *out = c;
+    return SPHB_OK;
+}
+
+void sphb_destroy(sphb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_all(ctx);
+    delete ctx;
+}
+
+int sphb_set_option(sphb_ctx* c, int option, int64_t value) {
+    if (!c) return SPHB_E_INVALID;
+    switch (option) {
+        case SPHB_OPT_MATH_MODE:
+            if (value != 0 && value != 1) return fail(c, SPHB_E_INVALID, "math mode must be 0 (strict) or 1 (fast)");
+            c->math_mode = (int)value;
+            return SPHB_OK;
+        case SPHB_OPT_WALK_RADIUS:
+            if (value < 1 || value > 3) return fail(c, SPHB_E_INVALID, "walk radius must be 1..3");
+            c->walk_radius = (int)value;
+            return SPHB_OK;
+        case SPHB_OPT_STAGE_TIMING:
+            c->stage_timing = value ? 1 : 0;
+            return SPHB_OK;
+        case SPHB_OPT_DEBUG_CAPTURE:
+            c->debug_capture = value ? 1 : 0;
+            if (c->debug_capture) { cudaSetDevice(c->device); return ensure_debug(c); }
+            return SPHB_OK;
+        case SPHB_OPT_PAIR_KERNEL:
+            if (value < 0 || value > 1) return fail(c, SPHB_E_INVALID, "pair kernel variant must be 0 or 1");
+            c->pair_kernel = (int)value;
+            return SPHB_OK;
+        default:
+            return fail(c, SPHB_E_INVALID, "unknown option %d", option);
+    }
+}
+
+int sphb_get_option(const sphb_ctx* c, int option, int64_t* value) {
+    if (!c || !value) return SPHB_E_INVALID;
+    switch (option) {
+        case SPHB_OPT_MATH_MODE: *value = c->math_mode; return SPHB_OK;
+        case SPHB_OPT_WALK_RADIUS: *value = c->walk_radius; return SPHB_OK;
+        case SPHB_OPT_STAGE_TIMING: *value = c->stage_timing; return SPHB_OK;
+        case SPHB_OPT_DEBUG_CAPTURE: *value = c->debug_capture; return SPHB_OK;
+        case SPHB_OPT_PAIR_KERNEL: *value = c->pair_kernel; return SPHB_OK;
+        default: return SPHB_E_INVALID;
+    }
+}
+
+int sphb_set_stream(sphb_ctx* c, void* cuda_stream) {
+    if (!c) return SPHB_E_INVALID;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->stream = static_cast<cudaStream_t>(cuda_stream);
+    return SPHB_OK;
+}
+
+int sphb_synchronize(sphb_ctx* c) {
+    if (!c) return SPHB_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return SPHB_OK;
+}
+
+int sphb_set_params(sphb_ctx* c, const sphb_params* p) {
+    if (!c || !p) return SPHB_E_INVALID;
+    c->prm = *p;
+    c->have_params = true;
+    return SPHB_OK;
+}
+
+int sphb_get_params(const sphb_ctx* c, sphb_params* p) {
+    if (!c || !p) return SPHB_E_INVALID;
+    *p = c->prm;
+    return SPHB_OK;
+}
+
+int sphb_size(const sphb_ctx* c, size_t* n) {
+    if (!c || !n) return SPHB_E_INVALID;
+    *n = c->n;
+    return SPHB_OK;
+}
+
+static int after_upload(sphb_ctx* c, size_t n) {
+    c->n = n;
+    c->cur = 0;
+    c->box_pending = n > 0;
+    c->stepped_since_upload = false;
+    return SPHB_OK;
+}
+
+static int reset_box_and_speed(sphb_ctx* c) {
+    // ordered-int identities: min slots start at +max, max slots at -max
+    const int init[6] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, (int)0x80000000, (int)0x80000000, (int)0x80000000};
+    CU(c, cudaMemcpyAsync(c->d_box, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemsetAsync(&c->sc->max_v2_bits, 0, sizeof(unsigned), c->stream));
+    return SPHB_OK;
+}
+
+}  // extern "C"
+
+// bounding box of the uploaded positions, reduced on the device
+namespace sphb {
+int launch_bbox(size_t n, const float4* posm, int* d_box, cudaStream_t st);
+}
+
+extern "C" {
+
+int sphb_upload(sphb_ctx* c, size_t n, const float* pos3, const float* vel3, const float* mass) {
+    if (!c) return SPHB_E_INVALID;
+    if (n > c->capacity) return fail(c, SPHB_E_CAPACITY, "upload of %zu particles exceeds capacity %zu", n, c->capacity);
+    if (n > 0 && !pos3) return fail(c, SPHB_E_INVALID, "pos3 is NULL");
+    CU(c, cudaSetDevice(c->device));
+    if (n == 0) return after_upload(c, 0);
+    int rc = ensure_stage(c, n * 7 * sizeof(float));
+    if (rc) return rc;
+    float* d_pos = reinterpret_cast<float*>(c->d_stage);
+    float* d_vel = d_pos + 3 * n;
+    float* d_mass = d_vel + 3 * n;
+    CU(c, cudaMemcpyAsync(d_pos, pos3, n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if (vel3) CU(c, cudaMemcpyAsync(d_vel, vel3, n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if (mass) CU(c, cudaMemcpyAsync(d_mass, mass, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    rc = reset_box_and_speed(c);
+    if (rc) return rc;
+    c->stats.kernel_launches += launch_pack_upload(n, d_pos, vel3 ? d_vel : nullptr, mass ? d_mass : nullptr,
+                                                   c->prm.particle_mass, c->posm[0], c->velid[0], c->sc, c->stream);
+    c->stats.kernel_launches += launch_bbox(n, c->posm[0], c->d_box, c->stream);
+    CU(c, cudaGetLastError());
+    return after_upload(c, n);
+}
+
+int sphb_upload_strided(sphb_ctx* c, size_t n, const void* base, size_t stride, size_t off_pos, size_t off_vel,
+                        size_t off_mass) {
+    if (!c) return SPHB_E_INVALID;
+    if (n > c->capacity) return fail(c, SPHB_E_CAPACITY, "upload of %zu particles exceeds capacity %zu", n, c->capacity);
+    if (n > 0 && !base) return fail(c, SPHB_E_INVALID, "base is NULL");
+    if (stride % 4 || off_pos % 4 || off_vel % 4 || off_mass % 4 || off_pos + 12 > stride || off_vel + 12 > stride ||
+        off_mass + 4 > stride)
+        return fail(c, SPHB_E_INVALID, "stride/offsets must be 4-byte aligned and inside the record");
+    CU(c, cudaSetDevice(c->device));
+    if (n == 0) return after_upload(c, 0);
+    int rc = ensure_stage(c, n * stride);
+    if (rc) return rc;
+    CU(c, cudaMemcpyAsync(c->d_stage, base, n * stride, cudaMemcpyHostToDevice, c->stream));
+    rc = reset_box_and_speed(c);
+    if (rc) return rc;
+    c->stats.kernel_launches +=
+        launch_unpack_strided(n, c->d_stage, stride, off_pos, off_vel, off_mass, c->posm[0], c->velid[0], c->sc, c->stream);
+    c->stats.kernel_launches += launch_bbox(n, c->posm[0], c->d_box, c->stream);
+    CU(c, cudaGetLastError());
+    return after_upload(c, n);
+}
+
+int sphb_download(sphb_ctx* c, float* pos3, float* vel3, float* rho, float* pressure, float* acc3) {
+    if (!c) return SPHB_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    const size_t n = c->n;
+    if (n == 0) return SPHB_OK;
+    int rc = ensure_stage(c, n * 11 * sizeof(float));
+    if (rc) return rc;
+    float* d_pos = reinterpret_cast<float*>(c->d_stage);
+    float* d_vel = d_pos + 3 * n;
+    float* d_acc = d_vel + 3 * n;
+    float* d_rho = d_acc + 3 * n;
+    float* d_P = d_rho + n;
+    c->stats.kernel_launches += launch_unpermute(n, c->posm[c->cur], c->velid[c->cur], c->rho_p, c->acc, nullptr, nullptr,
+                                                 pos3 ? d_pos : nullptr, vel3 ? d_vel : nullptr, rho ? d_rho : nullptr,
+                                                 pressure ? d_P : nullptr, acc3 ? d_acc : nullptr, nullptr, nullptr, nullptr,
+                                                 c->stream);
+    CU(c, cudaGetLastError());
+    if (pos3) CU(c, cudaMemcpyAsync(pos3, d_pos, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (vel3) CU(c, cudaMemcpyAsync(vel3, d_vel, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (acc3) CU(c, cudaMemcpyAsync(acc3, d_acc, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (rho) CU(c, cudaMemcpyAsync(rho, d_rho, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (pressure) CU(c, cudaMemcpyAsync(pressure, d_P, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return SPHB_OK;
+}
+
+int sphb_download_strided(sphb_ctx* c, void* base, size_t stride, size_t off_pos, size_t off_vel, size_t off_density,
+                          size_t off_pressure) {
+    if (!c) return SPHB_E_INVALID;
+    const size_t n = c->n;
+    if (n == 0) return SPHB_OK;
+    if (!base) return fail(c, SPHB_E_INVALID, "base is NULL");
+    const size_t none = (size_t)-1;
+    CU(c, cudaSetDevice(c->device));
+    int rc = ensure_bounce(c, n * 8 * sizeof(float));
+    if (rc) return rc;
+    float* h_pos = reinterpret_cast<float*>(c->h_bounce);
+    float* h_vel = h_pos + 3 * n;
+    float* h_rho = h_vel + 3 * n;
+    float* h_P = h_rho + n;
+    rc = sphb_download(c, off_pos != none ? h_pos : nullptr, off_vel != none ? h_vel : nullptr,
+                       off_density != none ? h_rho : nullptr, off_pressure != none ? h_P : nullptr, nullptr);
+    if (rc) return rc;
+    unsigned char* b = static_cast<unsigned char*>(base);
+    for (size_t i = 0; i < n; ++i) {
+        unsigned char* rec = b + i * stride;
+        if (off_pos != none) memcpy(rec + off_pos, h_pos + 3 * i, 12);
+        if (off_vel != none) memcpy(rec + off_vel, h_vel + 3 * i, 12);
+        if (off_density != none) memcpy(rec + off_density, h_rho + i, 4);
+        if (off_pressure != none) memcpy(rec + off_pressure, h_P + i, 4);
+    }
+    return SPHB_OK;
+}
+
+int sphb_step(sphb_ctx* c, float dt) {
+    if (!c) return SPHB_E_INVALID;
+    if (!c->have_params) return fail(c, SPHB_E_INVALID, "sphb_step before sphb_set_params");
+    if (c->n == 0) return SPHB_OK;  // SPHEngine::step returns early on an empty system (sph_engine.cpp:94)
+    CU(c, cudaSetDevice(c->device));
+    int rc = fetch_box(c);
+    if (rc) return rc;
+    GridDesc g;
+    rc = make_grid(c, &g);
+    if (rc) return rc;
+    rc = ensure_cell_table(c, g);
+    if (rc) return rc;
+    if (c->debug_capture) { rc = ensure_debug(c); if (rc) return rc; }
+
+    cudaStream_t st = c->stream;
+    const size_t n = c->n;
+    const IntegrateConsts ic = make_integrate_consts(c->prm);
+    uint64_t launches = 0;
+    const bool timing = c->stage_timing != 0;
+
+    launches += (dt <= 0.0f) ? launch_cfl_dt(c->sc, ic, st) : launch_set_dt(c->sc, dt, st);
+
+    if (timing) cudaEventRecord(c->ev[0], st);
+    const int in = c->cur, outb = c->cur ^ 1;
+    launches += launch_cell_keys(n, c->posm[in], c->velid[in], g, c->sb.keys[0], c->sb.vals[0],
+                                 c->debug_capture ? c->refkeys[in] : nullptr, c->sc, st);
+    int sorted = 0;
+    launches += launch_radix_sort(c->sb, n, g.id_bits + g.cell_bits, &sorted, st);
+    launches += launch_cell_table(n, c->sb.keys[sorted], g, c->cell_start, c->sb.block_sums, st);
+    launches += launch_reorder(n, c->sb.vals[sorted], c->posm[in], c->velid[in], c->debug_capture ? c->refkeys[in] : nullptr,
+                               c->posm[outb], c->velid[outb], c->debug_capture ? c->refkeys[outb] : nullptr, st);
+    c->cur = outb;
+    if (timing) cudaEventRecord(c->ev[1], st);
+
+    PairArgs pa;
+    pa.n = n;
+    pa.posm = c->posm[c->cur];
+    pa.velid = c->velid[c->cur];
+    pa.cell_start = c->cell_start;
+    pa.rho_p = c->rho_p;
+    pa.fa = c->fa;
+    pa.fb = c->fb;
+    pa.acc = c->acc;
+    pa.nbr_count = c->debug_capture ? c->nbr_count : nullptr;
+    pa.sc = c->sc;
+    pa.grid = g;
+    pa.k = make_pair_consts(c->prm);
+    pa.walk_radius = c->walk_radius;
+    pa.strict = c->math_mode == 0;
+    pa.variant = c->pair_kernel;
+    launches += launch_density(pa, st);
+    if (timing) cudaEventRecord(c->ev[2], st);
+    launches += launch_force(pa, st);
+    if (timing) cudaEventRecord(c->ev[3], st);
+    launches += launch_integrate(n, c->posm[c->cur], c->velid[c->cur], c->acc, ic, c->sc, st);
+    if (timing) cudaEventRecord(c->ev[4], st);
+    CU(c, cudaGetLastError());
+
+    // after the clamp every position lies inside the AABB (particle.cpp:122-153)
+    c->box_min[0] = c->prm.xmin; c->box_max[0] = c->prm.xmax;
+    c->box_min[1] = c->prm.ymin; c->box_max[1] = c->prm.ymax;
+    c->box_min[2] = c->prm.zmin; c->box_max[2] = c->prm.zmax;
+    c->stepped_since_upload = true;
+
+    c->step_count++;
+    c->stats.steps++;
+    c->stats.total_neighbor_queries += n;
+    c->stats.kernel_launches += launches;
+
+    if (timing) {
+        CU(c, cudaEventSynchronize(c->ev[4]));
+        float ms[4];
+        for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]);
+        c->stats.neighbor_search_time += 1e-3 * ms[0];
+        c->stats.density_computation_time += 1e-3 * ms[1];
+        c->stats.force_computation_time += 1e-3 * ms[2];
+        c->stats.integration_time += 1e-3 * ms[3];
+        c->stats.total_time += 1e-3 * (ms[0] + ms[1] + ms[2] + ms[3]);
+    }
+    return SPHB_OK;
+}
+
+int sphb_run_steps(sphb_ctx* c, size_t n, float dt) {
+    for (size_t i = 0; i < n; ++i) {
+        int rc = sphb_step(c, dt);
+        if (rc) return rc;
+    }
+    return SPHB_OK;
+}
+
+int sphb_get_time(sphb_ctx* c, float* current_time, uint64_t* step_count) {
+    if (!c) return SPHB_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    int rc = read_scalars(c);
+    if (rc) return rc;
+    if (current_time) *current_time = c->h_sc->time;
+    if (step_count) *step_count = c->step_count;
+    return SPHB_OK;
+}
+
+int sphb_set_time(sphb_ctx* c, float current_time, uint64_t step_count) {
+    if (!c) return SPHB_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaMemcpyAsync(&c->sc->time, &current_time, sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->step_count = step_count;
+    return SPHB_OK;
+}
+
+int sphb_cfl_timestep(sphb_ctx* c, float* dt) {
+    if (!c || !dt) return SPHB_E_INVALID;
+    if (!c->have_params) return fail(c, SPHB_E_INVALID, "sphb_cfl_timestep before sphb_set_params");
+    CU(c, cudaSetDevice(c->device));
+    c->stats.kernel_launches += launch_cfl_probe(c->sc, make_integrate_consts(c->prm), c->stream);
+    int rc = read_scalars(c);
+    if (rc) return rc;
+    *dt = c->h_sc->dt;
+    return SPHB_OK;
+}
+
+int sphb_get_stats(sphb_ctx* c, sphb_stats* out) {
+    if (!c || !out) return SPHB_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    int rc = read_scalars(c);
+    if (rc) return rc;
+    c->stats.max_neighbors = c->h_sc->max_neighbors;
+    *out = c->stats;
+    return SPHB_OK;
+}
+
+int sphb_reset_stats(sphb_ctx* c) {
+    if (!c) return SPHB_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaMemsetAsync(&c->sc->max_neighbors, 0, sizeof(unsigned), c->stream));
+    c->stats = sphb_stats{};
+    return SPHB_OK;
+}
+
+int sphb_diagnostics(sphb_ctx* c, double* sum_density, double* kinetic, float* max_speed) {
+    if (!c) return SPHB_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaMemsetAsync(&c->sc->sum_rho, 0, 2 * sizeof(double) + sizeof(unsigned), c->stream));
+    c->stats.kernel_launches += launch_diagnostics(c->n, c->posm[c->cur], c->velid[c->cur], c->rho_p, c->sc, c->stream);
+    int rc = read_scalars(c);
+    if (rc) return rc;
+    if (sum_density) *sum_density = c->h_sc->sum_rho;
+    if (kinetic) *kinetic = c->h_sc->kinetic;
+    if (max_speed) {
+        float v2;
+        memcpy(&v2, &c->h_sc->diag_max_v2_bits, 4);
+        *max_speed = sqrtf(v2);
+    }
+    return SPHB_OK;
+}
+
+int sphb_debug_dump(sphb_ctx* c, uint64_t* keys, uint32_t* perm, uint32_t* nbr_count) {
+    if (!c) return SPHB_E_INVALID;
+    if (!c->debug_capture || !c->refkeys[0]) return fail(c, SPHB_E_INVALID, "enable SPHB_OPT_DEBUG_CAPTURE before the step");
+    if (!c->stepped_since_upload) return fail(c, SPHB_E_INVALID, "no step has run since the last upload");
+    CU(c, cudaSetDevice(c->device));
+    const size_t n = c->n;
+    if (n == 0) return SPHB_OK;
+    int rc = ensure_stage(c, n * 16);
+    if (rc) return rc;
+    uint64_t* d_keys = reinterpret_cast<uint64_t*>(c->d_stage);
+    uint32_t* d_perm = reinterpret_cast<uint32_t*>(d_keys + n);
+    uint32_t* d_cnt = d_perm + n;
+    c->stats.kernel_launches += launch_unpermute(n, c->posm[c->cur], c->velid[c->cur], c->rho_p, c->acc, c->refkeys[c->cur],
+                                                 c->nbr_count, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                                 keys ? d_keys : nullptr, perm ? d_perm : nullptr,
+                                                 nbr_count ? d_cnt : nullptr, c->stream);
+    CU(c, cudaGetLastError());
+    if (keys) CU(c, cudaMemcpyAsync(keys, d_keys, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (perm) CU(c, cudaMemcpyAsync(perm, d_perm, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (nbr_count) CU(c, cudaMemcpyAsync(nbr_count, d_cnt, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return SPHB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,100 @@
+// Fused leapfrog integration + AABB boundary clamp + CFL reduction, and the on-device timestep.
+//
+// Replaces SPHEngine::integrate_leapfrog (reference src/sph_engine.cpp:290-310),
+// ParticleSystem::apply_boundary_conditions (src/particle.cpp:122-153, serial and untimed in the
+// reference), the max|v| loop of SPHEngine::compute_cfl_timestep (src/sph_engine.cpp:312-333) and
+// "current_time_ += dt" (src/sph_engine.cpp:138) in ONE streaming pass: 48 B read + 32 B written per
+// particle.  Every fp32 operation is issued with explicit round-to-nearest intrinsics in the
+// reference's association order, so this stage is bit-exact in both math modes.
+#include "sphb_internal.cuh"
+
+namespace sphb {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ void clamp_axis(float& p, float& v, float lo, float hi) {
+    // particle.cpp:127-133: restitution 0.8 hard-coded, independent of params.damping
+    if (p < lo) { p = lo; v = __fmul_rn(v, -0.8f); }
+    else if (p > hi) { p = hi; v = __fmul_rn(v, -0.8f); }
+}
+
+__global__ void __launch_bounds__(kThreads) k_integrate(size_t n, float4* __restrict__ posm, float4* __restrict__ velid,
+                                                        const float4* __restrict__ acc, IntegrateConsts ic,
+                                                        DeviceScalars* sc) {
+    const size_t s = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    const float dt = sc->dt;
+    float v2 = 0.0f;
+    if (s < n) {
+        float4 p = posm[s];
+        float4 v = velid[s];
+        const float4 a = acc[s];
+        // v += 0.5f * a * dt   ((0.5f * a) * dt, sph_engine.cpp:299)
+        const float hx = __fmul_rn(__fmul_rn(0.5f, a.x), dt);
+        const float hy = __fmul_rn(__fmul_rn(0.5f, a.y), dt);
+        const float hz = __fmul_rn(__fmul_rn(0.5f, a.z), dt);
+        v.x = __fadd_rn(v.x, hx); v.y = __fadd_rn(v.y, hy); v.z = __fadd_rn(v.z, hz);
+        // x += v * dt  (302)
+        p.x = __fadd_rn(p.x, __fmul_rn(v.x, dt)); p.y = __fadd_rn(p.y, __fmul_rn(v.y, dt)); p.z = __fadd_rn(p.z, __fmul_rn(v.z, dt));
+        // v += 0.5f * a * dt  (305), v *= damping (308)
+        v.x = __fadd_rn(v.x, hx); v.y = __fadd_rn(v.y, hy); v.z = __fadd_rn(v.z, hz);
+        v.x = __fmul_rn(v.x, ic.damping); v.y = __fmul_rn(v.y, ic.damping); v.z = __fmul_rn(v.z, ic.damping);
+        clamp_axis(p.x, v.x, ic.xmin, ic.xmax);
+        clamp_axis(p.y, v.y, ic.ymin, ic.ymax);
+        clamp_axis(p.z, v.z, ic.zmin, ic.zmax);
+        posm[s] = p;
+        velid[s] = v;
+        v2 = __fadd_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)), __fmul_rn(v.z, v.z));
+        if (__float_as_uint(v.w) == 0u) { sc->a0[0] = a.x; sc->a0[1] = a.y; sc->a0[2] = a.z; }
+        if (s == 0) sc->time = __fadd_rn(sc->time, dt);
+    }
+    unsigned bits = (v2 == v2) ? __float_as_uint(v2) : 0u;
+    bits = __reduce_max_sync(0xffffffffu, bits);
+    if ((threadIdx.x & 31) == 0 && bits != 0u) atomicMax(&sc->max_v2_bits, bits);
+}
+
+__global__ void k_set_dt(DeviceScalars* sc, float dt) {
+    sc->dt = dt;
+    sc->max_v2_bits = 0u;  // consumed; k_integrate of this step accumulates the next value
+}
+
+// compute_cfl_timestep, sph_engine.cpp:312-333.  max|v| = sqrt(max |v|^2) because correctly rounded
+// sqrt is monotone; the force criterion reads accelerations_[0] only.
+__global__ void k_cfl_dt(DeviceScalars* sc, IntegrateConsts ic, int consume) {
+    const float max_velocity = __fsqrt_rn(__uint_as_float(sc->max_v2_bits));
+    const float dt_cfl = __fdiv_rn(__fmul_rn(ic.cfl, ic.h), __fadd_rn(max_velocity, 1e-6f));
+    const float a0 = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(sc->a0[0], sc->a0[0]), __fmul_rn(sc->a0[1], sc->a0[1])),
+                                          __fmul_rn(sc->a0[2], sc->a0[2])));
+    const float dt_force = __fmul_rn(ic.cfl, __fsqrt_rn(__fdiv_rn(ic.h, __fadd_rn(a0, 1e-6f))));
+    float m = dt_cfl;               // std::min({a, b, c}): first of the smallest
+    if (dt_force < m) m = dt_force;
+    if (ic.timestep < m) m = ic.timestep;
+    sc->dt = m;
+    if (consume) sc->max_v2_bits = 0u;
+}
+
+}  // namespace
+
+int launch_set_dt(DeviceScalars* sc, float dt, cudaStream_t st) {
+    k_set_dt<<<1, 1, 0, st>>>(sc, dt);
+    return 1;
+}
+
+int launch_cfl_dt(DeviceScalars* sc, IntegrateConsts ic, cudaStream_t st) {
+    k_cfl_dt<<<1, 1, 0, st>>>(sc, ic, 1);
+    return 1;
+}
+
+int launch_cfl_probe(DeviceScalars* sc, IntegrateConsts ic, cudaStream_t st) {
+    k_cfl_dt<<<1, 1, 0, st>>>(sc, ic, 0);
+    return 1;
+}
+
+int launch_integrate(size_t n, float4* posm, float4* velid, const float4* acc, IntegrateConsts ic, DeviceScalars* sc,
+                     cudaStream_t st) {
+    k_integrate<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(n, posm, velid, acc, ic, sc);
+    return 1;
+}
+
+}  // namespace sphb

@@ -1,0 +1,280 @@
+// Spatial-hash stage on the device: cell keys, dense cell table, SoA reorder, un-permute.
+//
+// Replaces ParticleSystem::get_positions + SpatialHash::build (reference src/particle.cpp:68-75,
+// src/spatial_hash.cpp:15-25) and the id-order getters (src/sph_engine.h:133-136).
+// All kernels are HBM-bound streaming passes over float4 SoA columns.
+#include "sphb_internal.cuh"
+
+namespace sphb {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline unsigned blocks_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// (int)floorf(p * inv_cell), reference spatial_hash.h:30-36.  __float2int_rd is floor + convert and,
+// unlike the CPU cast, is defined for NaN/out-of-range (0 / saturation) — SURVEY Q22.
+__device__ __forceinline__ int cell_coord(float p, float inv_cell) { return __float2int_rd(__fmul_rn(p, inv_cell)); }
+
+__device__ __forceinline__ void block_max_v2(float v2, DeviceScalars* sc) {
+    // |v|^2 >= 0, so its float bit pattern orders like an unsigned integer; NaN is dropped the way
+    // std::max(max_velocity, velocity) drops it (sph_engine.cpp:318).
+    unsigned bits = (v2 == v2) ? __float_as_uint(v2) : 0u;
+    bits = __reduce_max_sync(0xffffffffu, bits);
+    if ((threadIdx.x & 31) == 0 && bits != 0u) atomicMax(&sc->max_v2_bits, bits);
+}
+
+__global__ void __launch_bounds__(kThreads) k_pack_upload(size_t n, const float* __restrict__ pos3,
+                                                          const float* __restrict__ vel3, const float* __restrict__ mass,
+                                                          float default_mass, float4* __restrict__ posm,
+                                                          float4* __restrict__ velid, DeviceScalars* sc) {
+    size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    float v2 = 0.0f;
+    if (i < n) {
+        float4 p, v;
+        p.x = pos3[3 * i]; p.y = pos3[3 * i + 1]; p.z = pos3[3 * i + 2];
+        p.w = mass ? mass[i] : default_mass;
+        if (vel3) { v.x = vel3[3 * i]; v.y = vel3[3 * i + 1]; v.z = vel3[3 * i + 2]; }
+        else { v.x = 0.0f; v.y = 0.0f; v.z = 0.0f; }
+        v.w = __uint_as_float((unsigned)i);
+        posm[i] = p;
+        velid[i] = v;
+        v2 = __fadd_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)), __fmul_rn(v.z, v.z));
+    }
+    block_max_v2(v2, sc);
+}
+
+__global__ void __launch_bounds__(kThreads) k_cell_keys(size_t n, const float4* __restrict__ posm,
+                                                        const float4* __restrict__ velid, GridDesc g,
+                                                        uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                        uint64_t* __restrict__ refkeys, DeviceScalars* sc) {
+    size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    float4 p = posm[i];
+    unsigned id = __float_as_uint(velid[i].w);
+    int c[3] = {cell_coord(p.x, g.inv_cell), cell_coord(p.y, g.inv_cell), cell_coord(p.z, g.inv_cell)};
+    if (refkeys) {
+        // SpatialHash::hash_position, reference spatial_hash.h:20-27
+        refkeys[i] = ((uint64_t)(c[0] & 0x1FFFFF) << 42) | ((uint64_t)(c[1] & 0x1FFFFF) << 21) | (uint64_t)(c[2] & 0x1FFFFF);
+    }
+    bool outside = false;
+    uint32_t cell = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        if (c[a] < g.lo[a]) { c[a] = g.lo[a]; outside = true; }
+        if (c[a] > g.hi[a]) { c[a] = g.hi[a]; outside = true; }
+        cell = cell * (uint32_t)g.ext[a] + (uint32_t)grid_rank(g, a, c[a]);
+    }
+    if (outside) atomicOr(&sc->error_flags, 1u);
+    keys[i] = ((uint64_t)cell << g.id_bits) | (uint64_t)id;
+    vals[i] = (uint32_t)i;
+}
+
+// cell_start[c + 1] = (last sorted slot of cell c) + 1; a max-scan then turns the table into
+// "number of particles in cells < c", valid for empty cells too.
+__global__ void __launch_bounds__(kThreads) k_cell_ends(size_t n, const uint64_t* __restrict__ sorted_keys, int id_bits,
+                                                        uint32_t* __restrict__ cell_start) {
+    size_t s = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    if (s >= n) return;
+    uint32_t c = (uint32_t)(sorted_keys[s] >> id_bits);
+    uint32_t cn = (s + 1 < n) ? (uint32_t)(sorted_keys[s + 1] >> id_bits) : 0xFFFFFFFFu;
+    if (c != cn) cell_start[c + 1] = (uint32_t)(s + 1);
+}
+
+__global__ void __launch_bounds__(kThreads) k_reorder(size_t n, const uint32_t* __restrict__ sorted_vals,
+                                                      const float4* __restrict__ posm_in, const float4* __restrict__ velid_in,
+                                                      const uint64_t* __restrict__ refkeys_in, float4* __restrict__ posm_out,
+                                                      float4* __restrict__ velid_out, uint64_t* __restrict__ refkeys_out) {
+    size_t s = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    if (s >= n) return;
+    uint32_t src = sorted_vals[s];
+    posm_out[s] = posm_in[src];
+    velid_out[s] = velid_in[src];
+    if (refkeys_in) refkeys_out[s] = refkeys_in[src];
+}
+
+__global__ void __launch_bounds__(kThreads) k_unpermute(size_t n, const float4* __restrict__ posm,
+                                                        const float4* __restrict__ velid, const float2* __restrict__ rho_p,
+                                                        const float4* __restrict__ acc, const uint64_t* __restrict__ refkeys,
+                                                        const uint32_t* __restrict__ nbr_count, float* __restrict__ pos3,
+                                                        float* __restrict__ vel3, float* __restrict__ rho, float* __restrict__ P,
+                                                        float* __restrict__ acc3, uint64_t* __restrict__ keys,
+                                                        uint32_t* __restrict__ perm, uint32_t* __restrict__ counts) {
+    size_t s = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    if (s >= n) return;
+    float4 v = velid[s];
+    size_t id = __float_as_uint(v.w);
+    if (pos3) { float4 p = posm[s]; pos3[3 * id] = p.x; pos3[3 * id + 1] = p.y; pos3[3 * id + 2] = p.z; }
+    if (vel3) { vel3[3 * id] = v.x; vel3[3 * id + 1] = v.y; vel3[3 * id + 2] = v.z; }
+    if (rho || P) { float2 rp = rho_p[s]; if (rho) rho[id] = rp.x; if (P) P[id] = rp.y; }
+    if (acc3) { float4 a = acc[s]; acc3[3 * id] = a.x; acc3[3 * id + 1] = a.y; acc3[3 * id + 2] = a.z; }
+    if (keys) keys[id] = refkeys[s];
+    if (perm) perm[s] = (uint32_t)id;
+    if (counts) counts[id] = nbr_count[s];
+}
+
+__global__ void __launch_bounds__(kThreads) k_diagnostics(size_t n, const float4* __restrict__ posm,
+                                                          const float4* __restrict__ velid, const float2* __restrict__ rho_p,
+                                                          DeviceScalars* sc) {
+    __shared__ double s_rho[kThreads / 32], s_ke[kThreads / 32];
+    double rho = 0.0, ke = 0.0;
+    unsigned vbits = 0;
+    for (size_t s = (size_t)blockIdx.x * kThreads + threadIdx.x; s < n; s += (size_t)gridDim.x * kThreads) {
+        float4 v = velid[s];
+        float m = posm[s].w;
+        float v2 = __fadd_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)), __fmul_rn(v.z, v.z));
+        rho += (double)rho_p[s].x;
+        ke += 0.5 * (double)m * (double)v2;
+        if (v2 == v2) vbits = max(vbits, __float_as_uint(v2));
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        rho += __shfl_down_sync(0xffffffffu, rho, d);
+        ke += __shfl_down_sync(0xffffffffu, ke, d);
+    }
+    vbits = __reduce_max_sync(0xffffffffu, vbits);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { s_rho[w] = rho; s_ke[w] = ke; if (vbits) atomicMax(&sc->diag_max_v2_bits, vbits); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int i = 0; i < kThreads / 32; ++i) { a += s_rho[i]; b += s_ke[i]; }
+        atomicAdd(&sc->sum_rho, a);
+        atomicAdd(&sc->kinetic, b);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_max_speed(size_t n, const float4* __restrict__ velid, DeviceScalars* sc) {
+    size_t s = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    float v2 = 0.0f;
+    if (s < n) {
+        float4 v = velid[s];
+        v2 = __fadd_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)), __fmul_rn(v.z, v.z));
+    }
+    block_max_v2(v2, sc);
+}
+
+// Signed-int image of a float that orders like the float (for atomicMin/atomicMax).
+__device__ __forceinline__ int ordered_int(float f) {
+    int s = __float_as_int(f);
+    return s >= 0 ? s : s ^ 0x7FFFFFFF;
+}
+
+__global__ void __launch_bounds__(kThreads) k_bbox(size_t n, const float4* __restrict__ posm, int* box) {
+    int lo[3] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF};
+    int hi[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads) {
+        const float4 p = posm[i];
+        const float c[3] = {p.x, p.y, p.z};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            if (c[a] == c[a]) {
+                const int o = ordered_int(c[a]);
+                lo[a] = min(lo[a], o);
+                hi[a] = max(hi[a], o);
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = __reduce_min_sync(0xffffffffu, lo[a]);
+        hi[a] = __reduce_max_sync(0xffffffffu, hi[a]);
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            atomicMin(&box[a], lo[a]);
+            atomicMax(&box[3 + a], hi[a]);
+        }
+    }
+}
+
+// Array-of-structs input (e.g. the reference's 76-byte sph::Particle, particle.h:17-49) → float4 SoA.
+__global__ void __launch_bounds__(kThreads) k_unpack_strided(size_t n, const unsigned char* __restrict__ base, size_t stride,
+                                                             size_t off_pos, size_t off_vel, size_t off_mass,
+                                                             float4* __restrict__ posm, float4* __restrict__ velid,
+                                                             DeviceScalars* sc) {
+    size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    float v2 = 0.0f;
+    if (i < n) {
+        const unsigned char* rec = base + i * stride;
+        const float* p = reinterpret_cast<const float*>(rec + off_pos);
+        const float* v = reinterpret_cast<const float*>(rec + off_vel);
+        const float m = *reinterpret_cast<const float*>(rec + off_mass);
+        posm[i] = make_float4(p[0], p[1], p[2], m);
+        velid[i] = make_float4(v[0], v[1], v[2], __uint_as_float((unsigned)i));
+        v2 = __fadd_rn(__fadd_rn(__fmul_rn(v[0], v[0]), __fmul_rn(v[1], v[1])), __fmul_rn(v[2], v[2]));
+    }
+    block_max_v2(v2, sc);
+}
+
+}  // namespace
+
+int launch_pack_upload(size_t n, const float* d_pos3, const float* d_vel3, const float* d_mass, float default_mass,
+                       float4* posm, float4* velid, DeviceScalars* sc, cudaStream_t st) {
+    if (n == 0) return 0;
+    k_pack_upload<<<blocks_for(n, kThreads), kThreads, 0, st>>>(n, d_pos3, d_vel3, d_mass, default_mass, posm, velid, sc);
+    return 1;
+}
+
+int launch_cell_keys(size_t n, const float4* posm, const float4* velid, GridDesc g, uint64_t* keys, uint32_t* vals,
+                     uint64_t* refkeys_or_null, DeviceScalars* sc, cudaStream_t st) {
+    k_cell_keys<<<blocks_for(n, kThreads), kThreads, 0, st>>>(n, posm, velid, g, keys, vals, refkeys_or_null, sc);
+    return 1;
+}
+
+int launch_cell_table(size_t n, const uint64_t* sorted_keys, GridDesc g, uint32_t* cell_start, uint32_t* block_sums,
+                      cudaStream_t st) {
+    cudaMemsetAsync(cell_start, 0, ((size_t)g.ncells + 1) * sizeof(uint32_t), st);
+    k_cell_ends<<<blocks_for(n, kThreads), kThreads, 0, st>>>(n, sorted_keys, g.id_bits, cell_start);
+    return 1 + launch_scan_max_inclusive(cell_start, (size_t)g.ncells + 1, block_sums, st);
+}
+
+int launch_reorder(size_t n, const uint32_t* sorted_vals, const float4* posm_in, const float4* velid_in,
+                   const uint64_t* refkeys_in, float4* posm_out, float4* velid_out, uint64_t* refkeys_out, cudaStream_t st) {
+    k_reorder<<<blocks_for(n, kThreads), kThreads, 0, st>>>(n, sorted_vals, posm_in, velid_in, refkeys_in, posm_out,
+                                                             velid_out, refkeys_out);
+    return 1;
+}
+
+int launch_unpermute(size_t n, const float4* posm, const float4* velid, const float2* rho_p, const float4* acc,
+                     const uint64_t* refkeys, const uint32_t* nbr_count, float* pos3, float* vel3, float* rho, float* P,
+                     float* acc3, uint64_t* keys, uint32_t* perm, uint32_t* counts, cudaStream_t st) {
+    if (n == 0) return 0;
+    k_unpermute<<<blocks_for(n, kThreads), kThreads, 0, st>>>(n, posm, velid, rho_p, acc, refkeys, nbr_count, pos3, vel3,
+                                                               rho, P, acc3, keys, perm, counts);
+    return 1;
+}
+
+int launch_diagnostics(size_t n, const float4* posm, const float4* velid, const float2* rho_p, DeviceScalars* sc,
+                       cudaStream_t st) {
+    if (n == 0) return 0;
+    unsigned nb = blocks_for(n, kThreads);
+    if (nb > (unsigned)(kSMs * 8)) nb = kSMs * 8;
+    k_diagnostics<<<nb, kThreads, 0, st>>>(n, posm, velid, rho_p, sc);
+    return 1;
+}
+
+int launch_max_speed(size_t n, const float4* velid, DeviceScalars* sc, cudaStream_t st) {
+    if (n == 0) return 0;
+    k_max_speed<<<blocks_for(n, kThreads), kThreads, 0, st>>>(n, velid, sc);
+    return 1;
+}
+
+int launch_bbox(size_t n, const float4* posm, int* d_box, cudaStream_t st) {
+    if (n == 0) return 0;
+    unsigned nb = blocks_for(n, kThreads);
+    if (nb > (unsigned)(kSMs * 8)) nb = kSMs * 8;
+    k_bbox<<<nb, kThreads, 0, st>>>(n, posm, d_box);
+    return 1;
+}
+
+int launch_unpack_strided(size_t n, const unsigned char* d_base, size_t stride, size_t off_pos, size_t off_vel, size_t off_mass,
+                          float4* posm, float4* velid, DeviceScalars* sc, cudaStream_t st) {
+    if (n == 0) return 0;
+    k_unpack_strided<<<blocks_for(n, kThreads), kThreads, 0, st>>>(n, d_base, stride, off_pos, off_vel, off_mass, posm, velid, sc);
+    return 1;
+}
+
+}  // namespace sphb

@@ -1,0 +1,146 @@
+// Density (+ equation of state) and force passes over the cell-sorted SoA.
+//
+// Replaces SPHEngine::update_neighbor_lists' query loop, compute_densities, compute_pressures and
+// compute_forces (reference src/sph_engine.cpp:335-353, 203-244): no neighbour lists are ever
+// materialised (the reference writes ~1.6 kB of list per particle per step); both passes walk the
+// (2R+1)^3 neighbour cells directly in the reference's visiting order — dx, dy, dz ascending, ascending
+// particle id inside a cell (src/spatial_hash.cpp:38-52) — so each particle's sums are accumulated in
+// the same order as the reference accumulates them over its list.
+//
+// Because the sort key is (x, y, z)-lexicographic, the 2R+1 cells of one (dx, dy) column are
+// contiguous in memory: a particle walks (2R+1)^2 contiguous runs of float4 records (two runs where
+// the column crosses the sign change of the masked key, see GridDesc).
+#include "pair_math.cuh"
+
+namespace sphb {
+
+namespace {
+
+constexpr int kThreads = 128;
+
+__device__ __forceinline__ int cell_coord(float p, float inv_cell) { return __float2int_rd(__fmul_rn(p, inv_cell)); }
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// Calls body(begin, end) for every contiguous slot run of the neighbourhood of cell (cx, cy, cz),
+// in the reference's visiting order.
+template <typename Body>
+__device__ __forceinline__ void walk_runs(const GridDesc& g, const uint32_t* __restrict__ cell_start, int R, int cx, int cy,
+                                          int cz, Body&& body) {
+    const int za = max(cz - R, g.lo[2]), zb = min(cz + R, g.hi[2]);
+    if (za > zb) return;
+    const bool split = (za < 0) && (zb >= 0);
+    for (int dx = -R; dx <= R; ++dx) {
+        const int x = cx + dx;
+        if (x < g.lo[0] || x > g.hi[0]) continue;
+        const uint32_t bx = (uint32_t)grid_rank(g, 0, x) * (uint32_t)g.ext[1];
+        for (int dy = -R; dy <= R; ++dy) {
+            const int y = cy + dy;
+            if (y < g.lo[1] || y > g.hi[1]) continue;
+            const uint32_t base = (bx + (uint32_t)grid_rank(g, 1, y)) * (uint32_t)g.ext[2];
+            if (!split) {
+                body(cell_start[base + grid_rank(g, 2, za)], cell_start[base + grid_rank(g, 2, zb) + 1]);
+            } else {
+                body(cell_start[base + grid_rank(g, 2, za)], cell_start[base + grid_rank(g, 2, -1) + 1]);
+                body(cell_start[base + grid_rank(g, 2, 0)], cell_start[base + grid_rank(g, 2, zb) + 1]);
+            }
+        }
+    }
+}
+
+// ---- variant 0: one thread per particle, private walk -------------------------------------------------
+template <bool STRICT>
+__global__ void __launch_bounds__(kThreads) k_density_simple(PairArgs a) {
+    const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    unsigned count = 0;
+    if (i < a.n) {
+        const float4 pi = a.posm[i];
+        const int cx = clampi(cell_coord(pi.x, a.grid.inv_cell), a.grid.lo[0], a.grid.hi[0]);
+        const int cy = clampi(cell_coord(pi.y, a.grid.inv_cell), a.grid.lo[1], a.grid.hi[1]);
+        const int cz = clampi(cell_coord(pi.z, a.grid.inv_cell), a.grid.lo[2], a.grid.hi[2]);
+        // density = m_i * W(0)   (sph_engine.cpp:373)
+        float rho = STRICT ? __fmul_rn(pi.w, a.k.w0) : pi.w * a.k.w0;
+        const float r2 = a.k.r2;
+        walk_runs(a.grid, a.cell_start, a.walk_radius, cx, cy, cz, [&](uint32_t b, uint32_t e) {
+            for (uint32_t j = b; j < e; ++j) {
+                const float4 pj = __ldg(&a.posm[j]);
+                const float dx = __fsub_rn(pi.x, pj.x), dy = __fsub_rn(pi.y, pj.y), dz = __fsub_rn(pi.z, pj.z);
+                const float d2 = dist2_exact(dx, dy, dz);
+                if (d2 <= r2) {
+                    ++count;
+                    if (j != (uint32_t)i) {
+                        if (STRICT) rho = __fadd_rn(rho, __fmul_rn(pj.w, w_strict(a.k, d2)));
+                        else rho += pj.w * w_fast(a.k, d2);
+                    }
+                }
+            }
+        });
+        float P;
+        if (STRICT) P = __fmul_rn(a.k.gas_constant, __fsub_rn(rho, a.k.rest_density));
+        else P = a.k.gas_constant * (rho - a.k.rest_density);
+        a.rho_p[i] = make_float2(rho, P);
+        const float4 v = a.velid[i];
+        if (STRICT) {
+            a.fb[i] = make_float4(v.x, v.y, v.z, rho);
+        } else {
+            const float A = pi.w / (2.0f * rho);
+            a.fa[i] = make_float4(pi.x, pi.y, pi.z, A);
+            a.fb[i] = make_float4(v.x, v.y, v.z, A * P);
+        }
+        if (a.nbr_count) a.nbr_count[i] = count;
+    }
+    count = __reduce_max_sync(0xffffffffu, count);
+    if ((threadIdx.x & 31) == 0) atomicMax(&a.sc->max_neighbors, count);
+}
+
+template <bool STRICT>
+__global__ void __launch_bounds__(kThreads) k_force_simple(PairArgs a) {
+    const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= a.n) return;
+    const float4 pi = a.posm[i];
+    const float4 vi = a.velid[i];
+    const float P_i = a.rho_p[i].y;
+    const int cx = clampi(cell_coord(pi.x, a.grid.inv_cell), a.grid.lo[0], a.grid.hi[0]);
+    const int cy = clampi(cell_coord(pi.y, a.grid.inv_cell), a.grid.lo[1], a.grid.hi[1]);
+    const int cz = clampi(cell_coord(pi.z, a.grid.inv_cell), a.grid.lo[2], a.grid.hi[2]);
+    ForceAccum f = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    const float r2 = a.k.r2;
+    const float4* __restrict__ ja = STRICT ? a.posm : a.fa;
+    walk_runs(a.grid, a.cell_start, a.walk_radius, cx, cy, cz, [&](uint32_t b, uint32_t e) {
+        for (uint32_t j = b; j < e; ++j) {
+            const float4 pj = __ldg(&ja[j]);
+            const float rx = __fsub_rn(pi.x, pj.x), ry = __fsub_rn(pi.y, pj.y), rz = __fsub_rn(pi.z, pj.z);
+            const float d2 = dist2_exact(rx, ry, rz);
+            if (d2 <= r2 && j != (uint32_t)i) {
+                const float4 vj = __ldg(&a.fb[j]);
+                if (STRICT) {
+                    force_pair_strict(a.k, f, rx, ry, rz, d2, __fsub_rn(vj.x, vi.x), __fsub_rn(vj.y, vi.y),
+                                      __fsub_rn(vj.z, vi.z), P_i, pj.w, vj.w);
+                } else {
+                    force_pair_fast(a.k, f, rx, ry, rz, d2, vj.x - vi.x, vj.y - vi.y, vj.z - vi.z, P_i, pj.w, vj.w);
+                }
+            }
+        }
+    });
+    a.acc[i] = STRICT ? accel_strict(a.k, f, pi.w) : accel_fast(a.k, f, pi.w);
+}
+
+}  // namespace
+
+int launch_density(const PairArgs& a, cudaStream_t st) {
+    if (a.n == 0) return 0;
+    const unsigned nb = (unsigned)((a.n + kThreads - 1) / kThreads);
+    if (a.strict) k_density_simple<true><<<nb, kThreads, 0, st>>>(a);
+    else k_density_simple<false><<<nb, kThreads, 0, st>>>(a);
+    return 1;
+}
+
+int launch_force(const PairArgs& a, cudaStream_t st) {
+    if (a.n == 0) return 0;
+    const unsigned nb = (unsigned)((a.n + kThreads - 1) / kThreads);
+    if (a.strict) k_force_simple<true><<<nb, kThreads, 0, st>>>(a);
+    else k_force_simple<false><<<nb, kThreads, 0, st>>>(a);
+    return 1;
+}
+
+}  // namespace sphb

@@ -1,0 +1,132 @@
+// Internal declarations shared by the CUDA translation units of libsphb.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "sphb.h"
+
+namespace sphb {
+
+constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs; grids of the persistent kernels are sized from this
+
+// ---- cell grid ----------------------------------------------------------------------------------
+// The reference hashes cell coordinates c = floor(p * inv_cell) into a 63-bit key
+// ((cx & 0x1FFFFF) << 42 | (cy & 0x1FFFFF) << 21 | (cz & 0x1FFFFF), spatial_hash.h:20-27).  Sorting
+// by that key is lexicographic in the MASKED coordinates, i.e. on each axis the non-negative cells
+// come first (ascending) and the negative ones after them (ascending).  `rank` reproduces exactly
+// that order inside the bounding cell box [lo, hi], so the dense linear cell index
+//     cell = (rank_x * ext_y + rank_y) * ext_z + rank_z
+// is strictly monotone in the reference key and a sort by it yields the reference-key order.
+struct GridDesc {
+    float inv_cell;
+    int lo[3], hi[3];      // inclusive cell-coordinate box covering every position that can occur
+    int pos_lo[3];         // max(lo, 0)
+    int npos[3];           // number of non-negative cells on the axis
+    int ext[3];            // hi - lo + 1
+    uint32_t ncells;
+    int id_bits;           // bits of the particle id inside the composite sort key
+    int cell_bits;
+};
+
+__host__ __device__ inline int grid_rank(const GridDesc& g, int axis, int c) {
+    return c >= 0 ? c - g.pos_lo[axis] : c - g.lo[axis] + g.npos[axis];
+}
+
+// ---- physics constants, precomputed on the host in the reference's own fp32 expression order ----
+struct PairConsts {
+    float h;            // smoothing length (CubicSplineKernel::h_)
+    float h_sq;         // h*h (kernels.cpp:13)
+    float sigma;        // 1/(pi*h*h*h) (kernels.cpp:27)
+    float r2;           // nsr*nsr (sph_engine.cpp:347)
+    float w0;           // W(0) = sigma*(2/3 - 0 + 0) (kernels.cpp:60)
+    float rest_density, gas_constant, viscosity, gravity;
+    // fast-mode folded constants
+    float inv_h;        // 1/h
+    float sig_h;        // sigma / h
+    float sig_h2;       // sigma / h_sq
+};
+
+struct IntegrateConsts {
+    float damping;
+    float xmin, xmax, ymin, ymax, zmin, zmax;
+    float cfl, h, timestep;
+};
+
+// Small block of device-resident scalars (one allocation, zero-initialised).
+struct DeviceScalars {
+    float dt;             // dt of the step being executed
+    float time;           // SPHEngine::current_time_, accumulated on the device in fp32
+    float a0[3];          // accelerations_[0] of the last step (compute_cfl_timestep, sph_engine.cpp:330)
+    unsigned int max_v2_bits;   // max |v|^2 over the current velocities, as float bits (non-negative)
+    unsigned int max_neighbors; // running max of neighbour-list length, self included
+    unsigned int error_flags;   // bit0: a particle fell outside the cell box
+    double sum_rho, kinetic;    // diagnostics scratch
+    unsigned int diag_max_v2_bits;
+    unsigned int pad;
+};
+
+// ---- launch wrappers (each returns the number of kernels it enqueued) ---------------------------
+struct SortBuffers {
+    uint64_t* keys[2];
+    uint32_t* vals[2];
+    uint32_t* counts;     // 256 * ntiles digit counts, scanned in place
+    uint32_t* block_sums; // scratch of the device-wide scan
+    size_t counts_cap;    // elements available in counts
+    size_t block_sums_cap;
+};
+
+constexpr int kSortTile = 2048;   // keys per CTA tile of the radix sort
+constexpr int kScanTile = 4096;   // elements per CTA of the device-wide scan
+
+// LSD radix sort of (key, val) pairs by the low `bits` bits of key, 8 bits per pass, stable.
+// Input in buffers [0]; returns the index (0/1) of the buffer pair holding the result in *out_buf.
+int launch_radix_sort(const SortBuffers& sb, size_t n, int bits, int* out_buf, cudaStream_t st);
+
+// out[i] = sum(in[0..i-1]) (exclusive) or out[i] = max(in[0..i]) (inclusive); in == out allowed.
+int launch_scan_sum_exclusive(uint32_t* data, size_t n, uint32_t* block_sums, cudaStream_t st);
+int launch_scan_max_inclusive(uint32_t* data, size_t n, uint32_t* block_sums, cudaStream_t st);
+
+int launch_pack_upload(size_t n, const float* d_pos3, const float* d_vel3, const float* d_mass, float default_mass,
+                       float4* posm, float4* velid, DeviceScalars* sc, cudaStream_t st);
+int launch_cell_keys(size_t n, const float4* posm, const float4* velid, GridDesc g, uint64_t* keys, uint32_t* vals,
+                     uint64_t* refkeys_or_null, DeviceScalars* sc, cudaStream_t st);
+// cell_start has ncells + 1 entries; block_sums is scan scratch.
+int launch_cell_table(size_t n, const uint64_t* sorted_keys, GridDesc g, uint32_t* cell_start, uint32_t* block_sums,
+                      cudaStream_t st);
+int launch_reorder(size_t n, const uint32_t* sorted_vals, const float4* posm_in, const float4* velid_in,
+                   const uint64_t* refkeys_in, float4* posm_out, float4* velid_out, uint64_t* refkeys_out, cudaStream_t st);
+
+struct PairArgs {
+    size_t n;
+    const float4* posm;        // x, y, z, mass   (cell-sorted)
+    const float4* velid;       // vx, vy, vz, id bits
+    const uint32_t* cell_start;
+    float2* rho_p;             // density, pressure
+    float4* fa;                // force-pass staging A (fast: x,y,z,m/(2 rho) ; strict: x,y,z,m)
+    float4* fb;                // force-pass staging B (fast: v, A*P ; strict: v, rho)
+    float4* acc;               // ax, ay, az, (unused)
+    uint32_t* nbr_count;       // optional, per sorted slot
+    DeviceScalars* sc;
+    GridDesc grid;
+    PairConsts k;
+    int walk_radius;
+    int strict;
+    int variant;
+};
+int launch_density(const PairArgs& a, cudaStream_t st);
+int launch_force(const PairArgs& a, cudaStream_t st);
+
+int launch_set_dt(DeviceScalars* sc, float dt, cudaStream_t st);
+int launch_cfl_dt(DeviceScalars* sc, IntegrateConsts ic, cudaStream_t st);
+int launch_integrate(size_t n, float4* posm, float4* velid, const float4* acc, IntegrateConsts ic, DeviceScalars* sc,
+                     cudaStream_t st);
+int launch_max_speed(size_t n, const float4* velid, DeviceScalars* sc, cudaStream_t st);
+
+int launch_unpermute(size_t n, const float4* posm, const float4* velid, const float2* rho_p, const float4* acc,
+                     const uint64_t* refkeys, const uint32_t* nbr_count, float* pos3, float* vel3, float* rho, float* P,
+                     float* acc3, uint64_t* keys, uint32_t* perm, uint32_t* counts, cudaStream_t st);
+int launch_diagnostics(size_t n, const float4* posm, const float4* velid, const float2* rho_p, DeviceScalars* sc,
+                       cudaStream_t st);
+
+}  // namespace sphb
