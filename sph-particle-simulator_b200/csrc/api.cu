@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "sphb_internal.cuh"
 
@@ -66,7 +67,10 @@ struct sphb_ctx {
 
     uint64_t step_count = 0;
     sphb_stats stats{};
-    cudaEvent_t ev[6] = {};
+    // stage-timing events: one set of 5 per step, resolved lazily (no sync inside sphb_step)
+    struct EventSet { cudaEvent_t e[5]; };
+    std::vector<EventSet> ev_pool;
+    size_t ev_used = 0;
 
     char err[512] = "";
 };
@@ -241,7 +245,38 @@ void free_all(sphb_ctx* c) {
     cudaFree(c->sc); cudaFree(c->d_stage); cudaFree(c->d_box);
     if (c->h_sc) cudaFreeHost(c->h_sc);
     if (c->h_bounce) cudaFreeHost(c->h_bounce);
-    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto& set : c->ev_pool) for (auto& e : set.e) if (e) cudaEventDestroy(e);
+    c->ev_pool.clear();
+}
+
+// Resolve all pending stage-timing event sets into the stats accumulators.
+void drain_events(sphb_ctx* c) {
+    for (size_t i = 0; i < c->ev_used; ++i) {
+        auto& set = c->ev_pool[i];
+        if (cudaEventSynchronize(set.e[4]) != cudaSuccess) continue;
+        float ms[4] = {0, 0, 0, 0};
+        for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&ms[k], set.e[k], set.e[k + 1]);
+        c->stats.neighbor_search_time += 1e-3 * ms[0];
+        c->stats.density_computation_time += 1e-3 * ms[1];
+        c->stats.force_computation_time += 1e-3 * ms[2];
+        c->stats.integration_time += 1e-3 * ms[3];
+        c->stats.total_time += 1e-3 * (ms[0] + ms[1] + ms[2] + ms[3]);
+    }
+    c->ev_used = 0;
+}
+
+cudaEvent_t* next_event_set(sphb_ctx* c) {
+    if (c->ev_used == c->ev_pool.size()) {
+        if (c->ev_pool.size() >= 512) {
+            drain_events(c);
+        } else {
+            sphb_ctx::EventSet set{};
+            for (auto& e : set.e)
+                if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+            c->ev_pool.push_back(set);
+        }
+    }
+    return c->ev_pool[c->ev_used++].e;
 }
 
 int read_scalars(sphb_ctx* c) {
@@ -307,7 +342,6 @@ int sphb_create(sphb_ctx** out, size_t capacity, int device) {
     CUC(cudaMallocHost(&c->h_sc, sizeof(DeviceScalars)));
     memset(c->h_sc, 0, sizeof(DeviceScalars));
     CUC(cudaMalloc(&c->d_box, 6 * sizeof(int)));
-    for (auto& ev : c->ev) CUC(cudaEventCreate(&ev));
 #undef CUC
     *out = c;
     return SPHB_OK;
@@ -333,6 +367,7 @@ int sphb_set_option(sphb_ctx* c, int option, int64_t value) {
             c->walk_radius = (int)value;
             return SPHB_OK;
         case SPHB_OPT_STAGE_TIMING:
+            if (!value) drain_events(c);
             c->stage_timing = value ? 1 : 0;
             return SPHB_OK;
         case SPHB_OPT_DEBUG_CAPTURE:
@@ -536,11 +571,12 @@ int sphb_step(sphb_ctx* c, float dt) {
     const size_t n = c->n;
     const IntegrateConsts ic = make_integrate_consts(c->prm);
     uint64_t launches = 0;
-    const bool timing = c->stage_timing != 0;
+    cudaEvent_t* ev = c->stage_timing ? next_event_set(c) : nullptr;
+    const bool timing = ev != nullptr;
 
     launches += (dt <= 0.0f) ? launch_cfl_dt(c->sc, ic, st) : launch_set_dt(c->sc, dt, st);
 
-    if (timing) cudaEventRecord(c->ev[0], st);
+    if (timing) cudaEventRecord(ev[0], st);
     const int in = c->cur, outb = c->cur ^ 1;
     launches += launch_cell_keys(n, c->posm[in], c->velid[in], g, c->sb.keys[0], c->sb.vals[0],
                                  c->debug_capture ? c->refkeys[in] : nullptr, c->sc, st);
@@ -550,7 +586,7 @@ int sphb_step(sphb_ctx* c, float dt) {
     launches += launch_reorder(n, c->sb.vals[sorted], c->posm[in], c->velid[in], c->debug_capture ? c->refkeys[in] : nullptr,
                                c->posm[outb], c->velid[outb], c->debug_capture ? c->refkeys[outb] : nullptr, st);
     c->cur = outb;
-    if (timing) cudaEventRecord(c->ev[1], st);
+    if (timing) cudaEventRecord(ev[1], st);
 
     PairArgs pa;
     pa.n = n;
@@ -569,11 +605,11 @@ int sphb_step(sphb_ctx* c, float dt) {
     pa.strict = c->math_mode == 0;
     pa.variant = c->pair_kernel;
     launches += launch_density(pa, st);
-    if (timing) cudaEventRecord(c->ev[2], st);
+    if (timing) cudaEventRecord(ev[2], st);
     launches += launch_force(pa, st);
-    if (timing) cudaEventRecord(c->ev[3], st);
+    if (timing) cudaEventRecord(ev[3], st);
     launches += launch_integrate(n, c->posm[c->cur], c->velid[c->cur], c->acc, ic, c->sc, st);
-    if (timing) cudaEventRecord(c->ev[4], st);
+    if (timing) cudaEventRecord(ev[4], st);
     CU(c, cudaGetLastError());
 
     // after the clamp every position lies inside the AABB (particle.cpp:122-153)
@@ -587,16 +623,6 @@ int sphb_step(sphb_ctx* c, float dt) {
     c->stats.total_neighbor_queries += n;
     c->stats.kernel_launches += launches;
 
-    if (timing) {
-        CU(c, cudaEventSynchronize(c->ev[4]));
-        float ms[4];
-        for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]);
-        c->stats.neighbor_search_time += 1e-3 * ms[0];
-        c->stats.density_computation_time += 1e-3 * ms[1];
-        c->stats.force_computation_time += 1e-3 * ms[2];
-        c->stats.integration_time += 1e-3 * ms[3];
-        c->stats.total_time += 1e-3 * (ms[0] + ms[1] + ms[2] + ms[3]);
-    }
     return SPHB_OK;
 }
 
@@ -643,6 +669,7 @@ int sphb_get_stats(sphb_ctx* c, sphb_stats* out) {
     CU(c, cudaSetDevice(c->device));
     int rc = read_scalars(c);
     if (rc) return rc;
+    drain_events(c);
     c->stats.max_neighbors = c->h_sc->max_neighbors;
     *out = c->stats;
     return SPHB_OK;
@@ -652,6 +679,7 @@ int sphb_reset_stats(sphb_ctx* c) {
     if (!c) return SPHB_E_INVALID;
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaMemsetAsync(&c->sc->max_neighbors, 0, sizeof(unsigned), c->stream));
+    drain_events(c);
     c->stats = sphb_stats{};
     return SPHB_OK;
 }

@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(kThreads) k_bbox(size_t n, const float4* __res
         const float c[3] = {p.x, p.y, p.z};
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            if (c[a] == c[a]) {
+            if (fabsf(c[a]) <= 3.4028235e38f) {   // finite only: NaN/inf are clamped into the box by k_cell_keys
                 const int o = ordered_int(c[a]);
                 lo[a] = min(lo[a], o);
                 hi[a] = max(hi[a], o);

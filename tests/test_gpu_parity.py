@@ -1,0 +1,271 @@
+"""GPU: the CUDA path through the C ABI against the oracle and the committed golden vectors.
+
+Bars (BASELINE.json north star):
+  * cell keys, sorted permutation, neighbour counts: bit-exact in both math modes
+  * strict math mode: density, pressure, acceleration, position, velocity, time bit-exact
+  * fast math mode (default): single step rho rel <= 2e-5, acc <= 1e-4 of max|acc|, pos abs <= 1e-6 * L
+    (SURVEY.md §8c gates; the reference's own fast-math vs strict noise floor is 4.4e-7 / 1.5e-8)
+"""
+import json
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, STEP_FIXTURES, assert_bits, golden_steps, load_golden, params_from, rel_err, stable_perm
+
+pytestmark = pytest.mark.gpu
+
+TOL_RHO = 2e-5
+TOL_ACC = 1e-4
+TOL_POS = 1e-6
+
+
+def make_ctx(pkg, n, params, strict=True, **opts):
+    capi = pkg.capi
+    ctx = pkg.Context(max(n, 1), 0)
+    ctx.set_option(capi.OPT_MATH_MODE, capi.MATH_STRICT if strict else capi.MATH_FAST)
+    ctx.set_option(capi.OPT_DEBUG_CAPTURE, 1)
+    for k, v in opts.items():
+        ctx.set_option(getattr(capi, k), v)
+    ctx.set_params(params)
+    return ctx
+
+
+def check_fast(got, want, L, what):
+    assert rel_err(got["rho"], want["rho"]) <= TOL_RHO, f"{what}: rho rel {rel_err(got['rho'], want['rho'])}"
+    amax = np.abs(want["acc"]).max()
+    if np.isfinite(amax) and amax > 0:
+        assert np.abs(got["acc"].astype(np.float64) - want["acc"]).max() <= TOL_ACC * amax, f"{what}: acc"
+    assert np.abs(got["pos"].astype(np.float64) - want["pos"]).max() <= TOL_POS * L, f"{what}: pos"
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("name", STEP_FIXTURES)
+def test_strict_bit_exact_vs_reference_golden(pkg, name, variant):
+    g = load_golden(name)
+    prm = params_from(g["params"])
+    n = g["pos"].shape[0]
+    ctx = make_ctx(pkg, n, prm, strict=True, OPT_PAIR_KERNEL=variant)
+    ctx.upload(g["pos"], g["vel"], g["mass"])
+    keep = golden_steps(g)
+    for k, dt in enumerate(g["dts"]):
+        ctx.step(float(dt))
+        if k in keep:
+            d = ctx.debug_dump()
+            assert_bits(d["keys"], g[f"s{k}_keys"], f"{name} step {k} keys")
+            assert_bits(d["perm"], stable_perm(g[f"s{k}_keys"]), f"{name} step {k} sorted permutation")
+            assert_bits(d["nbr_count"], g[f"s{k}_counts"], f"{name} step {k} neighbour counts")
+            s = ctx.download()
+            for f in ("rho", "P", "acc", "pos", "vel"):
+                if f"s{k}_{f}" in g:
+                    assert_bits(s[f], g[f"s{k}_{f}"], f"{name} step {k} {f}")
+            t, sc = ctx.get_time()
+            assert np.float32(t) == g[f"s{k}_time"] and sc == k + 1
+    assert ctx.stats()["max_neighbors"] == int(g["final_max_neighbors"])
+    ctx.close()
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("name", ["micro_pair", "micro_coincident", "micro_lattice27", "cloud600", "cloud600_truncated_support",
+                                  "cloud600_wide_cell", "dam_break_13k_tame"])
+def test_fast_mode_single_step_tolerance(pkg, name, variant):
+    g = load_golden(name)
+    prm = params_from(g["params"])
+    n = g["pos"].shape[0]
+    ctx = make_ctx(pkg, n, prm, strict=False, OPT_PAIR_KERNEL=variant)
+    ctx.upload(g["pos"], g["vel"], g["mass"])
+    k0 = golden_steps(g)[0]                     # first step the fixture holds (0 or 1)
+    for k in range(k0 + 1):
+        ctx.step(float(g["dts"][k]))
+    d = ctx.debug_dump()
+    if k0 == 0:                                 # after >1 fast steps positions differ in the last bits
+        assert_bits(d["keys"], g["s0_keys"], f"{name} keys")
+        assert_bits(d["perm"], stable_perm(g["s0_keys"]), f"{name} permutation")
+        assert_bits(d["nbr_count"], g["s0_counts"], f"{name} counts (fast mode must keep neighbour sets)")
+    got = ctx.download()
+    want = {f: g[f"s{k0}_{f}"] for f in ("rho", "P", "acc", "pos", "vel")}
+    L = float(max(prm["xmax"] - prm["xmin"], prm["ymax"] - prm["ymin"], prm["zmax"] - prm["zmin"]))
+    check_fast(got, want, L, name)
+    ctx.close()
+
+
+def test_ten_steps_vs_oracle(pkg, po):
+    """N-step parity on the 13k tame dam break: strict stays bit-exact; fast stays inside 10x the
+    single-step gates (10 steps 10x looser)."""
+    from sph_b200 import scenes
+    pos, mass, prm, dt = scenes.dam_break_scene(0.02)
+    n = pos.shape[0]
+    ora = po.Engine("port", n); ora.initialize(prm); ora.add_particles(pos, None, mass)
+    cs = make_ctx(pkg, n, prm, strict=True); cs.upload(pos, None, mass)
+    cf = make_ctx(pkg, n, prm, strict=False); cf.upload(pos, None, mass)
+    for k in range(10):
+        keys = ora.keys()
+        ora.step(dt); cs.step(dt); cf.step(dt)
+        d = cs.debug_dump()
+        assert_bits(d["keys"], keys, f"step {k} keys")
+        assert_bits(d["perm"], stable_perm(keys), f"step {k} permutation")
+        assert_bits(d["nbr_count"], ora.neighbor_counts(), f"step {k} counts")
+    want = ora.state(); got = cs.download(); fast = cf.download()
+    for f in ("rho", "P", "acc", "pos", "vel"):
+        assert_bits(got[f], want[f], f"10 steps strict {f}")
+    assert rel_err(fast["rho"], want["rho"]) <= 10 * TOL_RHO
+    assert np.abs(fast["pos"].astype(np.float64) - want["pos"]).max() <= 10 * TOL_POS * 0.8
+    assert np.abs(fast["acc"].astype(np.float64) - want["acc"]).max() <= 10 * TOL_ACC * np.abs(want["acc"]).max()
+    # diagnostics agree (mass = sum rho * h^3, kinetic energy)
+    sum_rho, ke, vmax = cs.diagnostics()
+    h = np.float32(prm["smoothing_length"])
+    assert abs(sum_rho * float(h * h * h) - ora.total_mass()) <= 1e-4 * abs(ora.total_mass())
+    assert abs(ke - ora.total_energy()) <= 1e-4 * abs(ora.total_energy()) + 1e-12
+    assert abs(vmax - np.sqrt((want["vel"].astype(np.float64) ** 2).sum(1)).max()) <= 1e-6 * max(vmax, 1e-9)
+    ora.close(); cs.close(); cf.close()
+
+
+def test_adaptive_timestep(pkg):
+    meta = json.loads((GOLDEN / "scalars.json").read_text())
+    from sph_b200 import scenes
+    pos, mass, prm, dt = scenes.dam_break_scene(0.02)
+    ctx = make_ctx(pkg, pos.shape[0], prm, strict=True)
+    ctx.upload(pos, None, mass)
+    for want_dt, want_t in zip(meta["adaptive_dts"], meta["adaptive_times"]):
+        assert np.float32(ctx.cfl_timestep()) == np.float32(want_dt)
+        ctx.step(0.0)
+        assert np.float32(ctx.get_time()[0]) == np.float32(want_t)
+    import hashlib
+    s = ctx.download()
+    assert hashlib.sha256(s["pos"].tobytes()).hexdigest() == meta["adaptive_final_pos_sha256"]
+    assert hashlib.sha256(s["rho"].tobytes()).hexdigest() == meta["adaptive_final_rho_sha256"]
+    ctx.close()
+
+
+def test_walk_radius_two_equals_one(pkg):
+    """27-cell walk vs the reference's 125-cell walk (spatial_hash.cpp:35): identical sets and sums."""
+    g = load_golden("cloud600")
+    prm = params_from(g["params"])
+    outs = []
+    for r in (1, 2):
+        ctx = make_ctx(pkg, 600, prm, strict=True, OPT_WALK_RADIUS=r)
+        ctx.upload(g["pos"], g["vel"], g["mass"]); ctx.step(float(g["dts"][0]))
+        outs.append((ctx.download(), ctx.debug_dump())); ctx.close()
+    for f in ("rho", "acc", "pos"):
+        assert_bits(outs[0][0][f], outs[1][0][f], f"walk radius {f}")
+    assert_bits(outs[0][1]["nbr_count"], outs[1][1]["nbr_count"], "walk radius counts")
+
+
+def test_edge_cases(pkg, po):
+    capi = pkg.capi
+    prm = dict(pkg.DEFAULT_PARAMS)
+    # empty system: step is a no-op (sph_engine.cpp:94)
+    ctx = make_ctx(pkg, 16, prm)
+    ctx.step(0.001)
+    assert ctx.get_time() == (0.0, 0) and ctx.size == 0
+    assert ctx.download()["pos"].shape == (0, 3)
+    # over capacity → error, state untouched
+    with pytest.raises(pkg.SphbError) as ei:
+        ctx.upload(np.zeros((17, 3), np.float32))
+    assert ei.value.code == -3
+    # step before set_params
+    c2 = pkg.Context(4, 0)
+    c2.upload(np.zeros((2, 3), np.float32))
+    with pytest.raises(pkg.SphbError):
+        c2.step(0.001)
+    c2.close()
+    # default mass = params.particle_mass, default velocity 0; exactly-full capacity
+    pts = np.random.default_rng(7).uniform(-0.05, 0.05, size=(16, 3)).astype(np.float32)
+    ctx.upload(pts)
+    ctx.step(0.001)
+    ora = po.Engine("port", 16); ora.initialize(prm); ora.add_particles(pts, None, np.full(16, prm["particle_mass"], np.float32)); ora.step(0.001)
+    for f in ("rho", "pos", "vel", "acc"):
+        assert_bits(ctx.download()[f], ora.state()[f], f"edge {f}")
+    # NaN / inf positions must not crash (undefined in the reference: (int)floorf(NaN))
+    bad = pts.copy(); bad[3] = np.nan; bad[5, 0] = np.inf
+    ctx.upload(bad); ctx.step(0.001); ctx.step(0.001)
+    out = ctx.download()
+    assert np.isfinite(out["pos"][0]).all()
+    ctx.close(); ora.close()
+    # a grid too large for the dense cell table is refused, not mis-handled
+    big = dict(prm); big["neighbor_search_radius"] = 1e-4; big["smoothing_length"] = 5e-5
+    c3 = make_ctx(pkg, 4, big)
+    c3.upload(np.array([[-1, -1, -1], [1, 1, 1]], np.float32))
+    with pytest.raises(pkg.SphbError) as ei:
+        c3.step(0.001)
+    assert ei.value.code == -4
+    c3.close()
+
+
+def test_strided_aos_roundtrip(pkg, po):
+    """Upload/download through the 76-byte sph::Particle layout (particle.h:17-49)."""
+    g = load_golden("cloud600")
+    prm = params_from(g["params"])
+    n = 600
+    rec = np.zeros((n, 19), np.float32)      # 76 bytes: pos 0, vel 12, acc 24, density 36, pressure 40, mass 44, ...
+    rec[:, 0:3] = g["pos"]; rec[:, 3:6] = g["vel"]; rec[:, 11] = g["mass"]
+    ctx = make_ctx(pkg, n, prm, strict=True)
+    ctx.upload_strided(n, rec.ctypes.data, 76, 0, 12, 44)
+    ctx.step(float(g["dts"][0]))
+    ctx.download_strided(rec.ctypes.data, 76, 0, 12, 36, 40)
+    assert_bits(np.ascontiguousarray(rec[:, 0:3]), g["s0_pos"], "aos pos")
+    assert_bits(np.ascontiguousarray(rec[:, 3:6]), g["s0_vel"], "aos vel")
+    assert_bits(np.ascontiguousarray(rec[:, 9]), g["s0_rho"], "aos rho")
+    assert_bits(np.ascontiguousarray(rec[:, 10]), g["s0_P"], "aos P")
+    assert_bits(np.ascontiguousarray(rec[:, 11]), g["mass"], "aos mass untouched")
+    ctx.close()
+
+
+def test_reupload_and_parameter_change(pkg, po):
+    """initialize()/set_smoothing_length between steps (cell size follows nsr), re-upload resets ids."""
+    g = load_golden("cloud600")
+    prm = params_from(g["params"])
+    ctx = make_ctx(pkg, 1000, prm, strict=True)
+    ora = po.Engine("port", 1000); ora.initialize(prm); ora.add_particles(g["pos"], g["vel"], g["mass"])
+    ctx.upload(g["pos"], g["vel"], g["mass"])
+    dt = float(g["dts"][0])
+    ora.step(dt); ctx.step(dt)
+    ora.set_smoothing_length(0.03); p2 = ora.get_parameters(); ctx.set_params(p2)
+    ora.step(dt); ctx.step(dt)
+    ora.set_boundaries(-0.1, 0.1, 0.2, 0.4, -0.1, 0.1); ctx.set_params(ora.get_parameters())
+    ora.step(dt); ctx.step(dt)
+    ora.step(dt); ctx.step(dt)
+    want, got = ora.state(), ctx.download()
+    for f in ("rho", "P", "acc", "pos", "vel"):
+        assert_bits(got[f], want[f], f"param change {f}")
+    assert_bits(ctx.debug_dump()["nbr_count"], ora.neighbor_counts(), "param change counts")
+    ctx.close(); ora.close()
+
+
+def test_full_size_properties_1M(pkg):
+    """BASELINE.json configs[1] at full size (N = 1 130 000) through size-independent properties:
+    the permutation is a bijection that sorts the keys stably; neighbour relation is symmetric (even
+    total of off-diagonal pairs); strict and fast agree within the fast-mode gates; both pair-kernel
+    variants agree bit-for-bit in strict mode."""
+    from sph_b200 import scenes
+    pos, mass, prm, dt = scenes.make_scene("dam_break_1M")
+    n = pos.shape[0]
+    res = {}
+    for name, strict, variant in (("s0", True, 0), ("s1", True, 1), ("f1", False, 1)):
+        ctx = make_ctx(pkg, n, prm, strict=strict, OPT_PAIR_KERNEL=variant)
+        ctx.upload(pos, None, mass)
+        ctx.step(dt)
+        first = (ctx.download(), ctx.debug_dump())      # identical inputs → discrete outputs must agree
+        ctx.step(dt)
+        res[name] = (first, ctx.download(), ctx.debug_dump())
+        ctx.close()
+    for which in (0, 2):                                  # step 1 and step 2 dumps of the strict run
+        d = res["s1"][which][1] if which == 0 else res["s1"][2]
+        perm, keys, cnt = d["perm"], d["keys"], d["nbr_count"]
+        assert np.array_equal(np.sort(perm), np.arange(n, dtype=np.uint32)), "permutation is not a bijection"
+        sk = keys[perm]
+        assert (np.diff(sk.astype(np.int64)) >= 0).all(), "keys not sorted"
+        same = sk[1:] == sk[:-1]
+        assert (perm[1:][same] > perm[:-1][same]).all(), "sort not stable (ids not ascending inside a cell)"
+        assert (cnt >= 1).all() and int((cnt.astype(np.int64) - 1).sum()) % 2 == 0, "neighbour relation not symmetric"
+    assert_bits(res["f1"][0][1]["nbr_count"], res["s1"][0][1]["nbr_count"], "fast vs strict counts (step 1)")
+    assert_bits(res["f1"][0][1]["perm"], res["s1"][0][1]["perm"], "fast vs strict perm (step 1)")
+    assert_bits(res["f1"][0][1]["keys"], res["s1"][0][1]["keys"], "fast vs strict keys (step 1)")
+    for f in ("rho", "P", "acc", "pos", "vel"):
+        assert_bits(res["s0"][1][f], res["s1"][1][f], f"pair-kernel variants differ in strict mode: {f}")
+    check_fast(res["f1"][0][0], res["s1"][0][0], 0.8, "1M fast vs strict, step 1")
+    # after two steps ulp-level position differences may move lattice particles across cell faces, so only
+    # the continuous fields are compared (2x the single-step gates)
+    a, b = res["f1"][1], res["s1"][1]
+    assert rel_err(a["rho"], b["rho"]) <= 2 * TOL_RHO
+    assert np.abs(a["pos"].astype(np.float64) - b["pos"]).max() <= 2 * TOL_POS * 0.8
