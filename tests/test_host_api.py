@@ -1,0 +1,171 @@
+"""The drop-in boundary: pybind11 module `sph` (reference python/bindings.cpp surface) over the host shell.
+
+CPU part: import, names, host-side generators/containers, loud failure without a GPU.
+GPU part: sph.Simulator driven exactly as a reference user would, checked against the oracle."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from helpers import assert_bits, rel_err
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def sph(pkg):
+    import subprocess
+    pydir = ROOT / "sph-particle-simulator_b200" / "python"
+    if not list(pydir.glob("sph.*.so")):
+        subprocess.run(["bash", str(ROOT / "sph-particle-simulator_b200" / "host" / "build.sh")], check=True)
+    sys.path.insert(0, str(pydir))
+    import sph
+    return sph
+
+
+SIM_METHODS = ["initialize", "initialize_dam_break", "initialize_fluid_drop", "initialize_granular_flow", "add_particles",
+               "clear_particles", "step", "run_steps", "get_particles", "get_parameters", "get_current_time", "get_step_count",
+               "set_parameters", "set_gravity", "set_viscosity", "set_smoothing_length", "set_boundaries",
+               "get_performance_stats", "reset_performance_stats", "compute_conservation_errors", "get_total_mass",
+               "get_total_energy", "validate_simulation", "is_initialized", "get_positions", "get_velocities",
+               "get_densities", "get_pressures"]
+
+
+def test_module_surface(sph):
+    # names of reference python/bindings.cpp:8-166
+    for name in ("SPHParameters", "ParticleType", "Particle", "ParticleSystem", "PerformanceStats", "Simulator",
+                 "create_fluid_block", "create_boundary_box"):
+        assert hasattr(sph, name), name
+    assert sph.__version__ == "1.0.0"
+    for meth in SIM_METHODS:
+        assert hasattr(sph.Simulator, meth), meth
+    p = sph.SPHParameters()
+    assert (p.rest_density, p.gas_constant, p.particle_mass) == (1000.0, 2000.0, pytest.approx(0.001))
+    assert p.damping == pytest.approx(0.99) and p.gravity == pytest.approx(-9.81)
+    assert not hasattr(p, "CFL_factor") and not hasattr(p, "bounds")        # Q20: 8 fields only
+    assert [t.name for t in (sph.ParticleType.FLUID, sph.ParticleType.BOUNDARY, sph.ParticleType.SOLID)] == ["FLUID", "BOUNDARY", "SOLID"]
+    q = sph.Particle()
+    assert q.mass == 1.0 and q.id == -1 and q.temperature == pytest.approx(293.15) and q.position == (0.0, 0.0, 0.0)
+    q2 = sph.Particle((1, 2, 3), mass=0.5, type=sph.ParticleType.SOLID)
+    assert q2.position == (1.0, 2.0, 3.0) and q2.mass == 0.5
+
+
+def test_generators_match_reference(sph, po):
+    for args in [((0, 0.3, 0), (0.4, 0.6, 0.8), 0.02), ((0.1, -0.2, 0.3), (0.37, 0.61, 0.83), 0.03)]:
+        c, s, dx = (np.array(args[0], np.float32), np.array(args[1], np.float32), args[2])
+        blk = sph.create_fluid_block(c, s, dx, mass=0.25)
+        ref, _ = po.gen_fluid_block(args[0], args[1], dx, 0.25, kind="port")
+        assert_bits(np.array([p.position for p in blk], np.float32), ref, "create_fluid_block")
+        assert blk[0].mass == 0.25 and blk[0].type == sph.ParticleType.FLUID
+        box = sph.create_boundary_box(c, s, dx)
+        ref, _ = po.gen_boundary_box(args[0], args[1], dx, 1.0, kind="port")
+        assert_bits(np.array([p.position for p in box], np.float32), ref, "create_boundary_box")
+        assert box[0].type == sph.ParticleType.BOUNDARY and box[0].mass == 1.0
+    with pytest.raises(ValueError):
+        sph.create_fluid_block(np.zeros(2, np.float32), np.ones(3, np.float32), 0.1)
+
+
+def test_no_gpu_fails_loudly(sph, has_gpu):
+    if has_gpu:
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError) as ei:
+        sph.Simulator(max_particles=100)
+    assert "no CPU fallback" in str(ei.value)
+    with pytest.raises(TypeError):
+        sph.Simulator(particles=100)          # Q20: the README's keyword is wrong in the reference too
+
+
+# ------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+def test_simulator_default_dam_break_vs_oracle(sph, po):
+    """A reference user's session: Simulator(), initialize_dam_break(), step(dt) — default (exploding)
+    parameters, strict math: bit-exact against the oracle for two steps."""
+    sim = sph.Simulator(max_particles=100000)
+    sim.set_math_mode(0)
+    assert not sim.is_initialized()
+    sim.step(0.001)                                   # no-op before initialisation
+    assert sim.get_step_count() == 0
+    sim.initialize_dam_break()
+    ora = po.Engine("port", 100000); ora.initialize_dam_break()
+    assert sim.is_initialized() and sim.get_particles().size() == ora.size == 84800
+    assert sim.get_particles().capacity() == 100000
+    assert_bits(sim.get_positions(), ora.state()["pos"], "initial positions")
+    for _ in range(2):
+        sim.step(0.001); ora.step(0.001)
+    want = ora.state()
+    assert sim.get_step_count() == 2 and np.float32(sim.get_current_time()) == np.float32(ora.time)
+    pos, vel = sim.get_positions(), sim.get_velocities()
+    assert pos.shape == (84800, 3) and pos.dtype == np.float32
+    assert_bits(pos, want["pos"], "positions"); assert_bits(vel, want["vel"], "velocities")
+    rho, P = sim.get_densities(), sim.get_pressures()
+    assert rho.shape == (100000,) and P.shape == (100000,)          # Q13: capacity-length
+    assert_bits(rho[:84800], want["rho"], "densities"); assert_bits(P[:84800], want["P"], "pressures")
+    assert not rho[84800:].any()
+    assert_bits(sim.get_accelerations(), want["acc"], "accelerations")
+    ps = sim.get_particles()                                         # live AoS, refreshed lazily
+    assert_bits(ps.get_positions(), want["pos"], "ParticleSystem positions")
+    assert_bits(ps.get_densities(), want["rho"], "ParticleSystem densities")
+    st = sim.get_performance_stats()
+    assert st.max_neighbors == ora.stats()["max_neighbors"] and st.total_neighbor_queries == 2 * 84800
+    assert st.force_computation_time > 0 and st.total_time >= st.force_computation_time
+    m_err, e_err = sim.compute_conservation_errors()
+    assert e_err == 0.0 and rel_err(m_err, ora.conservation_errors()[0]) < 1e-4
+    assert rel_err(sim.get_total_mass(), ora.total_mass()) < 1e-4
+    assert rel_err(sim.get_total_energy(), ora.total_energy()) < 1e-4
+    sim.reset_performance_stats()
+    assert sim.get_performance_stats().max_neighbors == 0
+    ora.close()
+
+
+@pytest.mark.gpu
+def test_simulator_public_api_scene_and_quirks(sph, po):
+    """Scene built through the public API (create_boundary_box + create_fluid_block + add_particles,
+    set_smoothing_length, set_boundaries), adaptive stepping, capacity truncation, re-initialisation."""
+    dx = 0.02
+    m = 1.5 * 1000 * dx ** 3
+    prm = sph.SPHParameters()
+    prm.gas_constant = 100.0 * m / 1000.0; prm.viscosity = 1e-3 * m; prm.particle_mass = m; prm.damping = 0.999
+    prm.timestep = 0.25 * 2 * dx / 10.0
+    sim = sph.Simulator(max_particles=13000)                         # 13 200 generated → 200 dropped (Q14)
+    sim.set_math_mode(0)
+    sim.initialize(prm)
+    c, s = np.array([0, 0.3, 0], np.float32), np.array([0.4, 0.6, 0.8], np.float32)
+    sim.add_particles(sph.create_boundary_box(c, s, dx, m))
+    sim.add_particles(sph.create_fluid_block(np.array([-0.1, 0.2, 0], np.float32), np.array([0.2, 0.4, 0.8], np.float32), dx, m))
+    sim.set_smoothing_length(2 * dx)
+    sim.set_boundaries(-0.2, 0.2, 0.0, 0.6, -0.4, 0.4)
+    assert sim.get_particles().size() == 13000
+
+    ora = po.Engine("port", 13000)
+    op = dict(po.default_params("port"))
+    op.update(gas_constant=prm.gas_constant, viscosity=prm.viscosity, particle_mass=prm.particle_mass, damping=prm.damping,
+              timestep=prm.timestep)
+    ora.initialize(op)
+    bp, bm = po.gen_boundary_box((0, 0.3, 0), (0.4, 0.6, 0.8), dx, m, kind="port")
+    fp, fm = po.gen_fluid_block((-0.1, 0.2, 0), (0.2, 0.4, 0.8), dx, m, kind="port")
+    ora.add_particles(bp, None, bm); ora.add_particles(fp, None, fm)
+    ora.set_smoothing_length(2 * dx); ora.set_boundaries(-0.2, 0.2, 0.0, 0.6, -0.4, 0.4)
+    assert ora.size == 13000
+    assert np.float32(sim.compute_cfl_timestep()) == np.float32(ora.cfl_timestep())
+    sim.run_steps(3)                                                  # adaptive by default (Q12)
+    ora.run_steps(3, True)
+    sim.run_steps(2, adaptive_timestep=False); ora.run_steps(2, False)
+    assert sim.get_step_count() == 5 and np.float32(sim.get_current_time()) == np.float32(ora.time)
+    want = ora.state()
+    assert_bits(sim.get_positions(), want["pos"], "positions"); assert_bits(sim.get_velocities(), want["vel"], "velocities")
+    assert_bits(sim.get_densities()[:13000], want["rho"], "densities")
+    # appending after stepping: host AoS is refreshed first, ids continue (capacity reached → dropped)
+    sim.add_particles([sph.Particle((0, 0.3, 0), m)])
+    assert sim.get_particles().size() == 13000
+    # re-initialising keeps the clock (Q15); clear_particles resets it
+    t = sim.get_current_time()
+    sim.initialize_fluid_drop()
+    assert sim.get_step_count() == 5 and sim.get_current_time() == t and sim.get_particles().size() == 8144
+    sim.step(0.0005)
+    assert sim.get_step_count() == 6
+    sim.clear_particles()
+    assert sim.get_step_count() == 0 and sim.get_current_time() == 0.0 and sim.get_particles().size() == 0
+    sim.step(0.001)
+    assert sim.get_step_count() == 0
+    ora.close()
