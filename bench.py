@@ -179,6 +179,7 @@ def run_ours(args):
     ctx.set_stream(stream.cuda_stream)
     ctx.set_option(capi.OPT_MATH_MODE, capi.MATH_STRICT if args.math == "strict" else capi.MATH_FAST)
     ctx.set_option(capi.OPT_PAIR_KERNEL, args.pair_kernel)
+    ctx.set_option(capi.OPT_GRID_REFINE, args.refine)
     ctx.set_params(params)
 
     # pinned host buffers (the user's arrays at the API boundary)
@@ -288,7 +289,7 @@ def run_ours(args):
         "ms_per_step": round(total_ms_max / args.steps, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.scene, "particles_per_gpu": n, "particles_total": n * world, "h_over_dx": 2.0,
-                   "params": "P-tame", "dt": dt, "math": args.math, "pair_kernel": args.pair_kernel,
+                   "params": "P-tame", "dt": dt, "math": args.math, "pair_kernel": args.pair_kernel, "grid_refine": args.refine,
                    "parallelism": parallelism, "l2": "flushed between timed steps (512 MiB write outside the event bracket)"},
         "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "what": "sphb_upload(host pos,vel,mass) + sphb_step + sphb_download(host pos,vel,rho) per step"},
@@ -313,7 +314,8 @@ def main():
     ap.add_argument("--scene", default="dam_break_1M")
     ap.add_argument("--cpu-scene", default=None)
     ap.add_argument("--math", default="fast", choices=["fast", "strict"])
-    ap.add_argument("--pair-kernel", type=int, default=1)
+    ap.add_argument("--pair-kernel", type=int, default=0)
+    ap.add_argument("--refine", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

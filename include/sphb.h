@@ -86,8 +86,14 @@ enum {
     SPHB_OPT_STAGE_TIMING = 3,
     /* 1 = keep per-particle cell keys and neighbour counts of every step for sphb_debug_dump (default 0) */
     SPHB_OPT_DEBUG_CAPTURE = 4,
-    /* pair kernel variant: 0 = per-thread walk (baseline), 1 = warp-cooperative tiled walk (default) */
-    SPHB_OPT_PAIR_KERNEL = 5
+    /* pair kernel variant: 0 = scalar per-thread walk (default), 1 = packed-f32x2 walk (fast mode only;
+     * measured slower on B200 — kept selectable) */
+    SPHB_OPT_PAIR_KERNEL = 5,
+    /* fast mode only: the device sorts on an internal grid of cell size neighbor_search_radius / f and
+     * walks (2 f + 1)^3 cells, which cuts the candidates per particle (27 r^3 -> 15.6 r^3 at f = 2).  The
+     * reference's 63-bit keys, its permutation and the neighbour sets are unaffected (1..4, default 2;
+     * strict mode always uses 1 so that its layout and summation order are the reference's). */
+    SPHB_OPT_GRID_REFINE = 6
 };
 
 /* ---- lifetime ---------------------------------------------------------------------------------

@@ -32,6 +32,7 @@ OPT_WALK_RADIUS = 2
 OPT_STAGE_TIMING = 3
 OPT_DEBUG_CAPTURE = 4
 OPT_PAIR_KERNEL = 5
+OPT_GRID_REFINE = 6
 MATH_STRICT = 0
 MATH_FAST = 1
 

@@ -38,7 +38,8 @@ struct sphb_ctx {
     int walk_radius = 1;
     int stage_timing = 0;
     int debug_capture = 0;
-    int pair_kernel = 1;
+    int pair_kernel = 0;
+    int grid_refine = 2;     // internal cell = neighbor_search_radius / grid_refine (fast mode; strict always 1)
 
     float4* posm[2] = {nullptr, nullptr};
     float4* velid[2] = {nullptr, nullptr};
@@ -46,9 +47,15 @@ struct sphb_ctx {
     float2* rho_p = nullptr;
     float4* fa = nullptr;
     float4* fb = nullptr;
+    float4* pp2 = nullptr;   // pair-interleaved mirrors (packed-f32x2 kernels)
+    float4* fa2 = nullptr;
+    float4* fb2 = nullptr;
     float4* acc = nullptr;
     uint32_t* nbr_count = nullptr;
     uint64_t* refkeys[2] = {nullptr, nullptr};
+    uint64_t* dbg_keys[2] = {nullptr, nullptr};   // reference-order composite keys (debug capture with a refined grid)
+    int dbg_sorted = -1;                          // which dbg_keys buffer holds the sorted keys of the last step, -1: layout order is the reference order
+    int dbg_id_bits = 0;
     SortBuffers sb{};
     uint32_t* cell_start = nullptr;
     size_t cell_cap = 0;
@@ -124,6 +131,8 @@ int ensure_debug(sphb_ctx* c) {
     CU(c, cudaMalloc(&c->refkeys[0], cap * sizeof(uint64_t)));
     CU(c, cudaMalloc(&c->refkeys[1], cap * sizeof(uint64_t)));
     CU(c, cudaMalloc(&c->nbr_count, cap * sizeof(uint32_t)));
+    CU(c, cudaMalloc(&c->dbg_keys[0], cap * sizeof(uint64_t)));
+    CU(c, cudaMalloc(&c->dbg_keys[1], cap * sizeof(uint64_t)));
     CU(c, cudaMemset(c->refkeys[0], 0, cap * sizeof(uint64_t)));
     CU(c, cudaMemset(c->refkeys[1], 0, cap * sizeof(uint64_t)));
     CU(c, cudaMemset(c->nbr_count, 0, cap * sizeof(uint32_t)));
@@ -159,10 +168,11 @@ int host_cell(float p, float inv_cell) {
     return (int)f;
 }
 
-int make_grid(sphb_ctx* c, GridDesc* g) {
+int make_grid(sphb_ctx* c, GridDesc* g, int refine) {
     const float cell = c->prm.neighbor_search_radius;
     if (!(cell > 0.0f)) return fail(c, SPHB_E_INVALID, "neighbor_search_radius must be > 0 (got %g)", (double)cell);
-    g->inv_cell = 1.0f / cell;  // SpatialHash::set_cell_size, reference spatial_hash.h:63-66
+    g->ref_inv_cell = 1.0f / cell;  // SpatialHash::set_cell_size, reference spatial_hash.h:63-66
+    g->inv_cell = g->ref_inv_cell * (float)refine;
     uint64_t ncells = 1;
     for (int a = 0; a < 3; ++a) {
         int lo = host_cell(c->box_min[a], g->inv_cell), hi = host_cell(c->box_max[a], g->inv_cell);
@@ -221,6 +231,7 @@ PairConsts make_pair_consts(const sphb_params& p) {
     k.inv_h = 1.0f / h;
     k.sig_h = k.sigma / h;
     k.sig_h2 = k.sigma / k.h_sq;
+    k.neg_zero = -0.0f;
     return k;
 }
 
@@ -237,9 +248,10 @@ IntegrateConsts make_integrate_consts(const sphb_params& p) {
 void free_all(sphb_ctx* c) {
     cudaSetDevice(c->device);
     for (int i = 0; i < 2; ++i) {
-        cudaFree(c->posm[i]); cudaFree(c->velid[i]); cudaFree(c->refkeys[i]);
+        cudaFree(c->posm[i]); cudaFree(c->velid[i]); cudaFree(c->refkeys[i]); cudaFree(c->dbg_keys[i]);
         cudaFree(c->sb.keys[i]); cudaFree(c->sb.vals[i]);
     }
+    cudaFree(c->pp2); cudaFree(c->fa2); cudaFree(c->fb2);
     cudaFree(c->rho_p); cudaFree(c->fa); cudaFree(c->fb); cudaFree(c->acc); cudaFree(c->nbr_count);
     cudaFree(c->sb.counts); cudaFree(c->sb.block_sums); cudaFree(c->cell_start);
     cudaFree(c->sc); cudaFree(c->d_stage); cudaFree(c->d_box);
@@ -330,6 +342,15 @@ int sphb_create(sphb_ctx** out, size_t capacity, int device) {
     CUC(cudaMalloc(&c->fa, cap * sizeof(float4)));
     CUC(cudaMalloc(&c->fb, cap * sizeof(float4)));
     CUC(cudaMalloc(&c->acc, cap * sizeof(float4)));
+    {   // pair records: ceil(cap/2) pairs of 32 B; zero-filled so the unused half of an odd tail is finite
+        const size_t pair_bytes = ((cap + 1) / 2) * 2 * sizeof(float4);
+        CUC(cudaMalloc(&c->pp2, pair_bytes));
+        CUC(cudaMalloc(&c->fa2, pair_bytes));
+        CUC(cudaMalloc(&c->fb2, pair_bytes));
+        CUC(cudaMemset(c->pp2, 0, pair_bytes));
+        CUC(cudaMemset(c->fa2, 0, pair_bytes));
+        CUC(cudaMemset(c->fb2, 0, pair_bytes));
+    }
     // densities_/pressures_/accelerations_ are value-initialised by initialize() (sph_engine.cpp:26-28)
     CUC(cudaMemset(c->rho_p, 0, cap * sizeof(float2)));
     CUC(cudaMemset(c->acc, 0, cap * sizeof(float4)));
@@ -378,6 +399,10 @@ int sphb_set_option(sphb_ctx* c, int option, int64_t value) {
             if (value < 0 || value > 1) return fail(c, SPHB_E_INVALID, "pair kernel variant must be 0 or 1");
             c->pair_kernel = (int)value;
             return SPHB_OK;
+        case SPHB_OPT_GRID_REFINE:
+            if (value < 1 || value > 4) return fail(c, SPHB_E_INVALID, "grid refine must be 1..4");
+            c->grid_refine = (int)value;
+            return SPHB_OK;
         default:
             return fail(c, SPHB_E_INVALID, "unknown option %d", option);
     }
@@ -391,6 +416,7 @@ int sphb_get_option(const sphb_ctx* c, int option, int64_t* value) {
         case SPHB_OPT_STAGE_TIMING: *value = c->stage_timing; return SPHB_OK;
         case SPHB_OPT_DEBUG_CAPTURE: *value = c->debug_capture; return SPHB_OK;
         case SPHB_OPT_PAIR_KERNEL: *value = c->pair_kernel; return SPHB_OK;
+        case SPHB_OPT_GRID_REFINE: *value = c->grid_refine; return SPHB_OK;
         default: return SPHB_E_INVALID;
     }
 }
@@ -560,9 +586,16 @@ int sphb_step(sphb_ctx* c, float dt) {
     CU(c, cudaSetDevice(c->device));
     int rc = fetch_box(c);
     if (rc) return rc;
-    GridDesc g;
-    rc = make_grid(c, &g);
+    // strict mode keeps the reference's cell size so the device layout IS the reference order; fast mode
+    // may sort on a finer grid (fewer candidates per particle) and walk refine x as many cells per axis
+    int refine = (c->math_mode == 0) ? 1 : c->grid_refine;
+    GridDesc g, gc;
+    rc = make_grid(c, &g, refine);
+    if (rc == SPHB_E_GRID && refine > 1) { refine = 1; rc = make_grid(c, &g, 1); }   // refined table too large: coarse grid
     if (rc) return rc;
+    gc = g;
+    const bool dbg_ref_sort = c->debug_capture && refine > 1;
+    if (dbg_ref_sort) { rc = make_grid(c, &gc, 1); if (rc) return rc; }
     rc = ensure_cell_table(c, g);
     if (rc) return rc;
     if (c->debug_capture) { rc = ensure_debug(c); if (rc) return rc; }
@@ -579,14 +612,24 @@ int sphb_step(sphb_ctx* c, float dt) {
     if (timing) cudaEventRecord(ev[0], st);
     const int in = c->cur, outb = c->cur ^ 1;
     launches += launch_cell_keys(n, c->posm[in], c->velid[in], g, c->sb.keys[0], c->sb.vals[0],
-                                 c->debug_capture ? c->refkeys[in] : nullptr, c->sc, st);
+                                 c->debug_capture ? c->refkeys[in] : nullptr, dbg_ref_sort ? c->dbg_keys[0] : nullptr, gc, c->sc, st);
     int sorted = 0;
     launches += launch_radix_sort(c->sb, n, g.id_bits + g.cell_bits, &sorted, st);
     launches += launch_cell_table(n, c->sb.keys[sorted], g, c->cell_start, c->sb.block_sums, st);
     launches += launch_reorder(n, c->sb.vals[sorted], c->posm[in], c->velid[in], c->debug_capture ? c->refkeys[in] : nullptr,
-                               c->posm[outb], c->velid[outb], c->debug_capture ? c->refkeys[outb] : nullptr, st);
+                               c->posm[outb], c->velid[outb], c->debug_capture ? c->refkeys[outb] : nullptr,
+                               (c->pair_kernel == 1 && c->math_mode == 1) ? c->pp2 : nullptr, st);
     c->cur = outb;
     if (timing) cudaEventRecord(ev[1], st);
+    c->dbg_sorted = -1;
+    if (dbg_ref_sort) {   // debug only: the reference-order permutation, by the same radix sort over (reference cell, id)
+        SortBuffers ds = c->sb;
+        ds.keys[0] = c->dbg_keys[0]; ds.keys[1] = c->dbg_keys[1];   // vals buffers are free again after the reorder
+        int o = 0;
+        launches += launch_radix_sort(ds, n, gc.id_bits + gc.cell_bits, &o, st);
+        c->dbg_sorted = o;
+        c->dbg_id_bits = gc.id_bits;
+    }
 
     PairArgs pa;
     pa.n = n;
@@ -596,12 +639,15 @@ int sphb_step(sphb_ctx* c, float dt) {
     pa.rho_p = c->rho_p;
     pa.fa = c->fa;
     pa.fb = c->fb;
+    pa.pp2 = c->pp2;
+    pa.fa2 = c->fa2;
+    pa.fb2 = c->fb2;
     pa.acc = c->acc;
     pa.nbr_count = c->debug_capture ? c->nbr_count : nullptr;
     pa.sc = c->sc;
     pa.grid = g;
     pa.k = make_pair_consts(c->prm);
-    pa.walk_radius = c->walk_radius;
+    pa.walk_radius = c->walk_radius * refine;
     pa.strict = c->math_mode == 0;
     pa.variant = c->pair_kernel;
     launches += launch_density(pa, st);
@@ -719,9 +765,20 @@ int sphb_debug_dump(sphb_ctx* c, uint64_t* keys, uint32_t* perm, uint32_t* nbr_c
                                                  nbr_count ? d_cnt : nullptr, c->stream);
     CU(c, cudaGetLastError());
     if (keys) CU(c, cudaMemcpyAsync(keys, d_keys, n * 8, cudaMemcpyDeviceToHost, c->stream));
-    if (perm) CU(c, cudaMemcpyAsync(perm, d_perm, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (perm && c->dbg_sorted < 0) CU(c, cudaMemcpyAsync(perm, d_perm, n * 4, cudaMemcpyDeviceToHost, c->stream));
     if (nbr_count) CU(c, cudaMemcpyAsync(nbr_count, d_cnt, n * 4, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
+    if (perm && c->dbg_sorted >= 0) {
+        // refined layout: the reference-order permutation is the id field of the separately sorted
+        // (reference cell, id) keys
+        uint64_t* h = static_cast<uint64_t*>(malloc(n * sizeof(uint64_t)));
+        if (!h) return fail(c, SPHB_E_NOMEM, "out of host memory");
+        cudaError_t e = cudaMemcpy(h, c->dbg_keys[c->dbg_sorted], n * sizeof(uint64_t), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { free(h); return fail(c, SPHB_E_CUDA, "debug perm copy: %s", cudaGetErrorString(e)); }
+        const uint64_t mask = (1ull << c->dbg_id_bits) - 1ull;
+        for (size_t s = 0; s < n; ++s) perm[s] = (uint32_t)(h[s] & mask);
+        free(h);
+    }
     return SPHB_OK;
 }
 

@@ -45,30 +45,41 @@ __global__ void __launch_bounds__(kThreads) k_pack_upload(size_t n, const float*
     block_max_v2(v2, sc);
 }
 
+__device__ __forceinline__ uint32_t dense_cell(const GridDesc& g, const float4& p, bool* outside) {
+    int c[3] = {cell_coord(p.x, g.inv_cell), cell_coord(p.y, g.inv_cell), cell_coord(p.z, g.inv_cell)};
+    uint32_t cell = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        if (c[a] < g.lo[a]) { c[a] = g.lo[a]; *outside = true; }
+        if (c[a] > g.hi[a]) { c[a] = g.hi[a]; *outside = true; }
+        cell = cell * (uint32_t)g.ext[a] + (uint32_t)grid_rank(g, a, c[a]);
+    }
+    return cell;
+}
+
 __global__ void __launch_bounds__(kThreads) k_cell_keys(size_t n, const float4* __restrict__ posm,
                                                         const float4* __restrict__ velid, GridDesc g,
                                                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                                                        uint64_t* __restrict__ refkeys, DeviceScalars* sc) {
+                                                        uint64_t* __restrict__ refkeys, uint64_t* __restrict__ ckeys, GridDesc gc,
+                                                        DeviceScalars* sc) {
     size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
     float4 p = posm[i];
     unsigned id = __float_as_uint(velid[i].w);
-    int c[3] = {cell_coord(p.x, g.inv_cell), cell_coord(p.y, g.inv_cell), cell_coord(p.z, g.inv_cell)};
     if (refkeys) {
-        // SpatialHash::hash_position, reference spatial_hash.h:20-27
-        refkeys[i] = ((uint64_t)(c[0] & 0x1FFFFF) << 42) | ((uint64_t)(c[1] & 0x1FFFFF) << 21) | (uint64_t)(c[2] & 0x1FFFFF);
+        // SpatialHash::get_grid_coords + hash_position, reference spatial_hash.h:20-36
+        const int cx = cell_coord(p.x, g.ref_inv_cell), cy = cell_coord(p.y, g.ref_inv_cell), cz = cell_coord(p.z, g.ref_inv_cell);
+        refkeys[i] = ((uint64_t)(cx & 0x1FFFFF) << 42) | ((uint64_t)(cy & 0x1FFFFF) << 21) | (uint64_t)(cz & 0x1FFFFF);
     }
     bool outside = false;
-    uint32_t cell = 0;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        if (c[a] < g.lo[a]) { c[a] = g.lo[a]; outside = true; }
-        if (c[a] > g.hi[a]) { c[a] = g.hi[a]; outside = true; }
-        cell = cell * (uint32_t)g.ext[a] + (uint32_t)grid_rank(g, a, c[a]);
-    }
+    const uint32_t cell = dense_cell(g, p, &outside);
     if (outside) atomicOr(&sc->error_flags, 1u);
     keys[i] = ((uint64_t)cell << g.id_bits) | (uint64_t)id;
     vals[i] = (uint32_t)i;
+    if (ckeys) {   // (reference cell, id) composite: sorting it yields the reference-order permutation
+        bool o2 = false;
+        ckeys[i] = ((uint64_t)dense_cell(gc, p, &o2) << gc.id_bits) | (uint64_t)id;
+    }
 }
 
 // cell_start[c + 1] = (last sorted slot of cell c) + 1; a max-scan then turns the table into
@@ -85,12 +96,18 @@ __global__ void __launch_bounds__(kThreads) k_cell_ends(size_t n, const uint64_t
 __global__ void __launch_bounds__(kThreads) k_reorder(size_t n, const uint32_t* __restrict__ sorted_vals,
                                                       const float4* __restrict__ posm_in, const float4* __restrict__ velid_in,
                                                       const uint64_t* __restrict__ refkeys_in, float4* __restrict__ posm_out,
-                                                      float4* __restrict__ velid_out, uint64_t* __restrict__ refkeys_out) {
+                                                      float4* __restrict__ velid_out, uint64_t* __restrict__ refkeys_out,
+                                                      float4* __restrict__ pp2_out) {
     size_t s = (size_t)blockIdx.x * kThreads + threadIdx.x;
     if (s >= n) return;
     uint32_t src = sorted_vals[s];
-    posm_out[s] = posm_in[src];
+    const float4 p = posm_in[src];
+    posm_out[s] = p;
     velid_out[s] = velid_in[src];
+    if (pp2_out) {   // pair-interleaved mirror {x0,x1,y0,y1 | z0,z1,m0,m1} for the packed-f32x2 pair kernels
+        float* f = reinterpret_cast<float*>(pp2_out) + 8 * (s >> 1) + (s & 1);
+        f[0] = p.x; f[2] = p.y; f[4] = p.z; f[6] = p.w;
+    }
     if (refkeys_in) refkeys_out[s] = refkeys_in[src];
 }
 
@@ -219,8 +236,8 @@ int launch_pack_upload(size_t n, const float* d_pos3, const float* d_vel3, const
 }
 
 int launch_cell_keys(size_t n, const float4* posm, const float4* velid, GridDesc g, uint64_t* keys, uint32_t* vals,
-                     uint64_t* refkeys_or_null, DeviceScalars* sc, cudaStream_t st) {
-    k_cell_keys<<<blocks_for(n, kThreads), kThreads, 0, st>>>(n, posm, velid, g, keys, vals, refkeys_or_null, sc);
+                     uint64_t* refkeys_or_null, uint64_t* ckeys_or_null, GridDesc gc, DeviceScalars* sc, cudaStream_t st) {
+    k_cell_keys<<<blocks_for(n, kThreads), kThreads, 0, st>>>(n, posm, velid, g, keys, vals, refkeys_or_null, ckeys_or_null, gc, sc);
     return 1;
 }
 
@@ -232,9 +249,10 @@ int launch_cell_table(size_t n, const uint64_t* sorted_keys, GridDesc g, uint32_
 }
 
 int launch_reorder(size_t n, const uint32_t* sorted_vals, const float4* posm_in, const float4* velid_in,
-                   const uint64_t* refkeys_in, float4* posm_out, float4* velid_out, uint64_t* refkeys_out, cudaStream_t st) {
+                   const uint64_t* refkeys_in, float4* posm_out, float4* velid_out, uint64_t* refkeys_out, float4* pp2_out,
+                   cudaStream_t st) {
     k_reorder<<<blocks_for(n, kThreads), kThreads, 0, st>>>(n, sorted_vals, posm_in, velid_in, refkeys_in, posm_out,
-                                                             velid_out, refkeys_out);
+                                                             velid_out, refkeys_out, pp2_out);
     return 1;
 }
 

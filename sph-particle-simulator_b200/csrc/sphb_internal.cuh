@@ -19,7 +19,8 @@ constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs; grids of the persistent ker
 //     cell = (rank_x * ext_y + rank_y) * ext_z + rank_z
 // is strictly monotone in the reference key and a sort by it yields the reference-key order.
 struct GridDesc {
-    float inv_cell;
+    float inv_cell;        // 1 / (internal cell size) — internal cell = neighbor_search_radius / refine
+    float ref_inv_cell;    // 1 / neighbor_search_radius: the reference's hash cell (spatial_hash.h:63-66), for the 63-bit keys
     int lo[3], hi[3];      // inclusive cell-coordinate box covering every position that can occur
     int pos_lo[3];         // max(lo, 0)
     int npos[3];           // number of non-negative cells on the axis
@@ -45,6 +46,7 @@ struct PairConsts {
     float inv_h;        // 1/h
     float sig_h;        // sigma / h
     float sig_h2;       // sigma / h_sq
+    float neg_zero;     // -0.0f, deliberately a RUN-TIME value: see f2_sq_exact in pair.cu
 };
 
 struct IntegrateConsts {
@@ -89,13 +91,16 @@ int launch_scan_max_inclusive(uint32_t* data, size_t n, uint32_t* block_sums, cu
 
 int launch_pack_upload(size_t n, const float* d_pos3, const float* d_vel3, const float* d_mass, float default_mass,
                        float4* posm, float4* velid, DeviceScalars* sc, cudaStream_t st);
+// refkeys (63-bit reference keys) and ckeys (composite keys on the coarse reference grid gc) are optional
+// debug outputs.
 int launch_cell_keys(size_t n, const float4* posm, const float4* velid, GridDesc g, uint64_t* keys, uint32_t* vals,
-                     uint64_t* refkeys_or_null, DeviceScalars* sc, cudaStream_t st);
+                     uint64_t* refkeys_or_null, uint64_t* ckeys_or_null, GridDesc gc, DeviceScalars* sc, cudaStream_t st);
 // cell_start has ncells + 1 entries; block_sums is scan scratch.
 int launch_cell_table(size_t n, const uint64_t* sorted_keys, GridDesc g, uint32_t* cell_start, uint32_t* block_sums,
                       cudaStream_t st);
 int launch_reorder(size_t n, const uint32_t* sorted_vals, const float4* posm_in, const float4* velid_in,
-                   const uint64_t* refkeys_in, float4* posm_out, float4* velid_out, uint64_t* refkeys_out, cudaStream_t st);
+                   const uint64_t* refkeys_in, float4* posm_out, float4* velid_out, uint64_t* refkeys_out, float4* pp2_out,
+                   cudaStream_t st);
 
 struct PairArgs {
     size_t n;
@@ -105,6 +110,11 @@ struct PairArgs {
     float2* rho_p;             // density, pressure
     float4* fa;                // force-pass staging A (fast: x,y,z,m/(2 rho) ; strict: x,y,z,m)
     float4* fb;                // force-pass staging B (fast: v, A*P ; strict: v, rho)
+    // pair-interleaved mirrors for the packed-f32x2 kernels: record k = particles 2k, 2k+1 as
+    // {x0,x1,y0,y1 | z0,z1,w0,w1} (two float4)
+    const float4* pp2;         // position + mass pairs (written by the reorder kernel)
+    float4* fa2;               // x, y, z, A' = (sigma/h) m / (2 rho)
+    float4* fb2;               // vx, vy, vz, B' = A' P
     float4* acc;               // ax, ay, az, (unused)
     uint32_t* nbr_count;       // optional, per sorted slot
     DeviceScalars* sc;
