@@ -170,6 +170,40 @@ int sphb_diagnostics(sphb_ctx* ctx, double* sum_density, double* kinetic, float*
  * Any pointer may be NULL. */
 int sphb_debug_dump(sphb_ctx* ctx, uint64_t* keys, uint32_t* perm, uint32_t* nbr_count);
 
+/* ---- slab decomposition across GPUs (one context per GPU) ------------------------------------------
+ * NEW, no reference counterpart: the reference is a single-process CPU program.  The domain is cut
+ * into slabs of whole reference cells along one axis; each context owns [own_lo, own_hi) and, before a
+ * step, also holds copies ("ghosts") of the halo_layers cell layers beyond each face.  With two layers
+ * a step needs ONE halo exchange: densities of the first layer are recomputed locally from the second.
+ * The host driver (sph-particle-simulator_b200/slab.py) moves the 32-byte records
+ * {x, y, z, mass, vx, vy, vz, id} between contexts over NCCL (torch.distributed); d_* pointers below are
+ * DEVICE memory owned by the caller.  Because every step re-sorts owned + ghost particles by
+ * (cell, global id), results do not depend on the number of slabs. */
+typedef struct sphb_slab {
+    int32_t axis;                   /* 0 = x, 1 = y, 2 = z */
+    int32_t own_lo, own_hi;         /* owned reference cells [own_lo, own_hi) on that axis */
+    int32_t halo_layers;            /* ghost layers per face (>= 2) */
+    uint64_t id_space;              /* global ids are < id_space (< 2^31) */
+    float box_min[3], box_max[3];   /* global box containing every position that can occur */
+} sphb_slab;
+
+int sphb_set_slab(sphb_ctx* ctx, const sphb_slab* slab);   /* NULL: back to the whole-domain mode */
+/* like sphb_upload, with explicit global ids (slab mode: the particles this context owns) */
+int sphb_upload_ids(sphb_ctx* ctx, size_t n, const float* pos3, const float* vel3, const float* mass, const uint32_t* ids);
+/* Drop all ghosts; move every owned particle whose reference cell left [own_lo, own_hi) into d_out,
+ * grouped by destination rank d (cell in [cuts[d], cuts[d+1]), nranks + 1 cuts); counts[d] = records for
+ * rank d, counts[my_rank] = particles kept.  Synchronises. */
+int sphb_slab_extract_migrants(sphb_ctx* ctx, const int32_t* cuts, int nranks, int my_rank, void* d_out,
+                               size_t cap_records, uint64_t* counts);
+/* Copy the owned particles within halo_layers cells of the lower (side 0) / upper (side 1) face into d_out. */
+int sphb_slab_extract_halo(sphb_ctx* ctx, int side, void* d_out, size_t cap_records, uint64_t* count);
+/* Append records (received migrants: ghost = 0, received halo: ghost = 1). */
+int sphb_slab_append(sphb_ctx* ctx, const void* d_in, size_t count, int ghost);
+/* Owned particles of this context in arbitrary order: ids[k] with the matching fields (host pointers,
+ * any field may be NULL); *count = number written (<= cap). */
+int sphb_slab_download(sphb_ctx* ctx, size_t cap, uint32_t* ids, float* pos3, float* vel3, float* rho, float* pressure,
+                       float* acc3, size_t* count);
+
 #ifdef __cplusplus
 }
 #endif

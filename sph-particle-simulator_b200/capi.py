@@ -43,6 +43,8 @@ ABI_SYMBOLS = (
     "sphb_upload_strided", "sphb_download", "sphb_download_strided", "sphb_size", "sphb_step", "sphb_run_steps",
     "sphb_get_time", "sphb_set_time", "sphb_cfl_timestep", "sphb_get_stats", "sphb_reset_stats",
     "sphb_diagnostics", "sphb_debug_dump",
+    "sphb_set_slab", "sphb_upload_ids", "sphb_slab_extract_migrants", "sphb_slab_extract_halo", "sphb_slab_append",
+    "sphb_slab_download",
 )
 
 
@@ -57,6 +59,11 @@ class SphbStats(C.Structure):
         ("integration_time", C.c_double), ("max_neighbors", C.c_uint64),
         ("total_neighbor_queries", C.c_uint64), ("steps", C.c_uint64), ("kernel_launches", C.c_uint64),
     ]
+
+
+class SphbSlab(C.Structure):
+    _fields_ = [("axis", C.c_int32), ("own_lo", C.c_int32), ("own_hi", C.c_int32), ("halo_layers", C.c_int32),
+                ("id_space", C.c_uint64), ("box_min", C.c_float * 3), ("box_max", C.c_float * 3)]
 
 
 class SphbError(RuntimeError):
@@ -103,6 +110,12 @@ def load_library() -> C.CDLL:
     L.sphb_reset_stats.argtypes = [vp]
     L.sphb_diagnostics.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), fp]
     L.sphb_debug_dump.argtypes = [vp, vp, vp, vp]
+    L.sphb_set_slab.argtypes = [vp, C.POINTER(SphbSlab)]
+    L.sphb_upload_ids.argtypes = [vp, sz, vp, vp, vp, vp]
+    L.sphb_slab_extract_migrants.argtypes = [vp, vp, C.c_int, C.c_int, vp, sz, vp]
+    L.sphb_slab_extract_halo.argtypes = [vp, C.c_int, vp, sz, C.POINTER(C.c_uint64)]
+    L.sphb_slab_append.argtypes = [vp, vp, sz, C.c_int]
+    L.sphb_slab_download.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, C.POINTER(sz)]
     _lib = L
     return L
 
@@ -250,3 +263,49 @@ class Context:
         cnt = np.zeros(n, np.uint32)
         self._ck(self.L.sphb_debug_dump(self.h, _ptr(keys), _ptr(perm), _ptr(cnt)))
         return {"keys": keys, "perm": perm, "nbr_count": cnt}
+
+    # ---- slab decomposition (multi-GPU) -----------------------------------------------------------
+    def set_slab(self, axis: int, own_lo: int, own_hi: int, halo_layers: int, id_space: int, box_min, box_max):
+        sl = SphbSlab(int(axis), int(own_lo), int(own_hi), int(halo_layers), int(id_space),
+                      (C.c_float * 3)(*map(float, box_min)), (C.c_float * 3)(*map(float, box_max)))
+        self._ck(self.L.sphb_set_slab(self.h, C.byref(sl)))
+
+    def clear_slab(self):
+        self._ck(self.L.sphb_set_slab(self.h, None))
+
+    def upload_ids(self, pos, vel, mass, ids):
+        pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+        n = pos.shape[0]
+        vel = None if vel is None else np.ascontiguousarray(vel, np.float32).reshape(n, 3)
+        mass = None if mass is None else np.ascontiguousarray(np.broadcast_to(np.asarray(mass, np.float32), (n,)))
+        ids = np.ascontiguousarray(ids, np.uint32).reshape(n)
+        self._ck(self.L.sphb_upload_ids(self.h, n, _ptr(pos), _ptr(vel), _ptr(mass), _ptr(ids)))
+
+    def slab_extract_migrants(self, cuts, my_rank: int, d_out_ptr: int, cap_records: int) -> np.ndarray:
+        cuts = np.ascontiguousarray(cuts, np.int32)
+        nranks = cuts.shape[0] - 1
+        counts = np.zeros(nranks, np.uint64)
+        self._ck(self.L.sphb_slab_extract_migrants(self.h, _ptr(cuts), nranks, int(my_rank), C.c_void_p(d_out_ptr), int(cap_records),
+                                                   _ptr(counts)))
+        return counts
+
+    def slab_extract_halo(self, side: int, d_out_ptr: int, cap_records: int) -> int:
+        n = C.c_uint64()
+        self._ck(self.L.sphb_slab_extract_halo(self.h, int(side), C.c_void_p(d_out_ptr), int(cap_records), C.byref(n)))
+        return n.value
+
+    def slab_append(self, d_in_ptr: int, count: int, ghost: bool):
+        self._ck(self.L.sphb_slab_append(self.h, C.c_void_p(d_in_ptr), int(count), 1 if ghost else 0))
+
+    def slab_download(self, pos=True, vel=True, rho=True, pressure=True, acc=True) -> dict:
+        cap = self.size
+        out = {"ids": np.zeros(cap, np.uint32)}
+        if pos: out["pos"] = np.zeros((cap, 3), np.float32)
+        if vel: out["vel"] = np.zeros((cap, 3), np.float32)
+        if rho: out["rho"] = np.zeros(cap, np.float32)
+        if pressure: out["P"] = np.zeros(cap, np.float32)
+        if acc: out["acc"] = np.zeros((cap, 3), np.float32)
+        n = C.c_size_t()
+        self._ck(self.L.sphb_slab_download(self.h, cap, _ptr(out["ids"]), _ptr(out.get("pos")), _ptr(out.get("vel")),
+                                           _ptr(out.get("rho")), _ptr(out.get("P")), _ptr(out.get("acc")), C.byref(n)))
+        return {k: v[: n.value] for k, v in out.items()}

@@ -72,6 +72,10 @@ struct sphb_ctx {
     int* d_box = nullptr;      // 6 ordered-int encoded floats
     bool stepped_since_upload = false;
 
+    bool slab_on = false;
+    sphb_slab slab{};
+    unsigned int* d_counts = nullptr;   // kMaxRanks + 1 counters / cursors
+
     uint64_t step_count = 0;
     sphb_stats stats{};
     // stage-timing events: one set of 5 per step, resolved lazily (no sync inside sphb_step)
@@ -177,6 +181,15 @@ int make_grid(sphb_ctx* c, GridDesc* g, int refine) {
     for (int a = 0; a < 3; ++a) {
         int lo = host_cell(c->box_min[a], g->inv_cell), hi = host_cell(c->box_max[a], g->inv_cell);
         if (hi < lo) { int t = lo; lo = hi; hi = t; }
+        if (c->slab_on && a == c->slab.axis) {
+            // only the owned cells and their ghost layers can be populated (+1 internal cell of slack for
+            // the rounding difference between floor(p * inv) * refine and floor(p * (inv * refine)))
+            const int slo = refine * (c->slab.own_lo - c->slab.halo_layers) - 1;
+            const int shi = refine * (c->slab.own_hi + c->slab.halo_layers);
+            if (lo < slo) lo = slo;
+            if (hi > shi) hi = shi;
+            if (hi < lo) hi = lo;
+        }
         if (lo < -kMaxCoord || hi >= kMaxCoord)
             return fail(c, SPHB_E_GRID, "cell coordinates [%d, %d] on axis %d exceed the 21-bit key range", lo, hi, a);
         g->lo[a] = lo;
@@ -190,7 +203,7 @@ int make_grid(sphb_ctx* c, GridDesc* g, int refine) {
                         (unsigned long long)kMaxCells);
     }
     g->ncells = (uint32_t)ncells;
-    g->id_bits = bits_for(c->capacity > 1 ? c->capacity : 2);
+    g->id_bits = bits_for(c->slab_on ? (c->slab.id_space > 1 ? c->slab.id_space : 2) : (c->capacity > 1 ? c->capacity : 2));
     g->cell_bits = bits_for(ncells > 1 ? ncells : 2);
     if (g->id_bits + g->cell_bits > 64) return fail(c, SPHB_E_GRID, "composite sort key exceeds 64 bits");
     return SPHB_OK;
@@ -254,7 +267,7 @@ void free_all(sphb_ctx* c) {
     cudaFree(c->pp2); cudaFree(c->fa2); cudaFree(c->fb2);
     cudaFree(c->rho_p); cudaFree(c->fa); cudaFree(c->fb); cudaFree(c->acc); cudaFree(c->nbr_count);
     cudaFree(c->sb.counts); cudaFree(c->sb.block_sums); cudaFree(c->cell_start);
-    cudaFree(c->sc); cudaFree(c->d_stage); cudaFree(c->d_box);
+    cudaFree(c->sc); cudaFree(c->d_stage); cudaFree(c->d_box); cudaFree(c->d_counts);
     if (c->h_sc) cudaFreeHost(c->h_sc);
     if (c->h_bounce) cudaFreeHost(c->h_bounce);
     for (auto& set : c->ev_pool) for (auto& e : set.e) if (e) cudaEventDestroy(e);
@@ -314,7 +327,7 @@ int sphb_create(sphb_ctx** out, size_t capacity, int device) {
         return fail(nullptr, SPHB_E_CUDA, "no usable CUDA device (%s); libsphb has no CPU fallback",
                     e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
     if (device < 0 || device >= ndev) return fail(nullptr, SPHB_E_INVALID, "device %d out of range [0, %d)", device, ndev);
-    if (capacity >= (1ull << 32) - 1) return fail(nullptr, SPHB_E_CAPACITY, "capacity must be below 2^32 - 1");
+    if (capacity >= (1ull << 31)) return fail(nullptr, SPHB_E_CAPACITY, "capacity must be below 2^31");
     sphb_ctx* c = new (std::nothrow) sphb_ctx();
     if (!c) return fail(nullptr, SPHB_E_NOMEM, "out of host memory");
     c->device = device;
@@ -363,6 +376,7 @@ int sphb_create(sphb_ctx** out, size_t capacity, int device) {
     CUC(cudaMallocHost(&c->h_sc, sizeof(DeviceScalars)));
     memset(c->h_sc, 0, sizeof(DeviceScalars));
     CUC(cudaMalloc(&c->d_box, 6 * sizeof(int)));
+    CUC(cudaMalloc(&c->d_counts, (kMaxRanks + 1) * sizeof(unsigned int)));
 #undef CUC
     *out = c;
     return SPHB_OK;
@@ -586,6 +600,9 @@ int sphb_step(sphb_ctx* c, float dt) {
     CU(c, cudaSetDevice(c->device));
     int rc = fetch_box(c);
     if (rc) return rc;
+    if (c->slab_on) {
+        for (int a = 0; a < 3; ++a) { c->box_min[a] = c->slab.box_min[a]; c->box_max[a] = c->slab.box_max[a]; }
+    }
     // strict mode keeps the reference's cell size so the device layout IS the reference order; fast mode
     // may sort on a finer grid (fewer candidates per particle) and walk refine x as many cells per axis
     int refine = (c->math_mode == 0) ? 1 : c->grid_refine;
@@ -594,7 +611,7 @@ int sphb_step(sphb_ctx* c, float dt) {
     if (rc == SPHB_E_GRID && refine > 1) { refine = 1; rc = make_grid(c, &g, 1); }   // refined table too large: coarse grid
     if (rc) return rc;
     gc = g;
-    const bool dbg_ref_sort = c->debug_capture && refine > 1;
+    const bool dbg_ref_sort = c->debug_capture && refine > 1 && !c->slab_on;
     if (dbg_ref_sort) { rc = make_grid(c, &gc, 1); if (rc) return rc; }
     rc = ensure_cell_table(c, g);
     if (rc) return rc;
@@ -650,6 +667,9 @@ int sphb_step(sphb_ctx* c, float dt) {
     pa.walk_radius = c->walk_radius * refine;
     pa.strict = c->math_mode == 0;
     pa.variant = c->pair_kernel;
+    pa.slab_axis = c->slab_on ? c->slab.axis : -1;
+    pa.rho_lo = c->slab_on ? c->slab.own_lo - 1 : 0;
+    pa.rho_hi = c->slab_on ? c->slab.own_hi + 1 : 0;
     launches += launch_density(pa, st);
     if (timing) cudaEventRecord(ev[2], st);
     launches += launch_force(pa, st);
@@ -779,6 +799,149 @@ int sphb_debug_dump(sphb_ctx* c, uint64_t* keys, uint32_t* perm, uint32_t* nbr_c
         for (size_t s = 0; s < n; ++s) perm[s] = (uint32_t)(h[s] & mask);
         free(h);
     }
+    return SPHB_OK;
+}
+
+
+// ---- slab decomposition -----------------------------------------------------------------------------
+
+int sphb_set_slab(sphb_ctx* c, const sphb_slab* slab) {
+    if (!c) return SPHB_E_INVALID;
+    if (!slab) { c->slab_on = false; return SPHB_OK; }
+    if (slab->axis < 0 || slab->axis > 2) return fail(c, SPHB_E_INVALID, "slab axis must be 0..2");
+    if (slab->own_hi <= slab->own_lo) return fail(c, SPHB_E_INVALID, "empty slab [%d, %d)", slab->own_lo, slab->own_hi);
+    if (slab->halo_layers < 2) return fail(c, SPHB_E_INVALID, "halo_layers must be >= 2 (density of the first ghost layer is recomputed locally)");
+    if (slab->id_space == 0 || slab->id_space > (1ull << 31)) return fail(c, SPHB_E_INVALID, "id_space must be in [1, 2^31]");
+    c->slab = *slab;
+    c->slab_on = true;
+    return SPHB_OK;
+}
+
+int sphb_upload_ids(sphb_ctx* c, size_t n, const float* pos3, const float* vel3, const float* mass, const uint32_t* ids) {
+    if (!c) return SPHB_E_INVALID;
+    if (n > c->capacity) return fail(c, SPHB_E_CAPACITY, "upload of %zu particles exceeds capacity %zu", n, c->capacity);
+    if (n > 0 && (!pos3 || !ids)) return fail(c, SPHB_E_INVALID, "pos3 / ids is NULL");
+    CU(c, cudaSetDevice(c->device));
+    if (n == 0) return after_upload(c, 0);
+    int rc = ensure_stage(c, n * 8 * sizeof(float));
+    if (rc) return rc;
+    float* d_pos = reinterpret_cast<float*>(c->d_stage);
+    float* d_vel = d_pos + 3 * n;
+    float* d_mass = d_vel + 3 * n;
+    uint32_t* d_ids = reinterpret_cast<uint32_t*>(d_mass + n);
+    CU(c, cudaMemcpyAsync(d_pos, pos3, n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if (vel3) CU(c, cudaMemcpyAsync(d_vel, vel3, n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if (mass) CU(c, cudaMemcpyAsync(d_mass, mass, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(d_ids, ids, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    rc = reset_box_and_speed(c);
+    if (rc) return rc;
+    c->stats.kernel_launches += launch_pack_upload_ids(n, d_pos, vel3 ? d_vel : nullptr, mass ? d_mass : nullptr, d_ids,
+                                                       c->prm.particle_mass, c->posm[0], c->velid[0], c->stream);
+    c->stats.kernel_launches += launch_max_speed(n, c->velid[0], c->sc, c->stream);
+    c->stats.kernel_launches += launch_bbox(n, c->posm[0], c->d_box, c->stream);
+    CU(c, cudaGetLastError());
+    return after_upload(c, n);
+}
+
+int sphb_slab_extract_migrants(sphb_ctx* c, const int32_t* cuts, int nranks, int my_rank, void* d_out, size_t cap_records,
+                               uint64_t* counts) {
+    if (!c || !cuts || !counts) return SPHB_E_INVALID;
+    if (!c->slab_on) return fail(c, SPHB_E_INVALID, "sphb_set_slab first");
+    if (nranks < 1 || nranks > kMaxRanks || my_rank < 0 || my_rank >= nranks) return fail(c, SPHB_E_INVALID, "bad rank layout");
+    CU(c, cudaSetDevice(c->device));
+    SlabCuts sc;
+    sc.nranks = nranks;
+    for (int d = 0; d <= nranks; ++d) sc.cuts[d] = cuts[d];
+    const float ref_inv = 1.0f / c->prm.neighbor_search_radius;
+    const int in = c->cur, out = c->cur ^ 1;
+    unsigned int h[kMaxRanks];
+    CU(c, cudaMemsetAsync(c->d_counts, 0, (kMaxRanks + 1) * sizeof(unsigned int), c->stream));
+    c->stats.kernel_launches += launch_slab_count(c->n, c->posm[in], c->velid[in], sc, c->slab.axis, ref_inv, c->d_counts, c->stream);
+    CU(c, cudaMemcpyAsync(h, c->d_counts, nranks * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    SlabOffsets off;
+    size_t total = 0;
+    for (int d = 0; d < nranks; ++d) {
+        off.start[d] = (unsigned int)total;
+        if (d != my_rank) total += h[d];
+        counts[d] = h[d];
+    }
+    if (total > cap_records) return fail(c, SPHB_E_CAPACITY, "%zu migrants exceed the exchange buffer (%zu records)", total, cap_records);
+    if (total > 0 && !d_out) return fail(c, SPHB_E_INVALID, "d_out is NULL");
+    CU(c, cudaMemsetAsync(c->d_counts, 0, (kMaxRanks + 1) * sizeof(unsigned int), c->stream));
+    c->stats.kernel_launches += launch_slab_split(c->n, c->posm[in], c->velid[in], sc, c->slab.axis, ref_inv, my_rank, c->posm[out],
+                                                  c->velid[out], static_cast<float4*>(d_out), off, c->d_counts, c->stream);
+    CU(c, cudaGetLastError());
+    c->cur = out;
+    c->n = h[my_rank];
+    c->stepped_since_upload = false;   // device order no longer matches the per-slot outputs of the last step
+    return SPHB_OK;
+}
+
+int sphb_slab_extract_halo(sphb_ctx* c, int side, void* d_out, size_t cap_records, uint64_t* count) {
+    if (!c || !count) return SPHB_E_INVALID;
+    if (!c->slab_on) return fail(c, SPHB_E_INVALID, "sphb_set_slab first");
+    CU(c, cudaSetDevice(c->device));
+    const int L = c->slab.halo_layers;
+    const int lo = side == 0 ? c->slab.own_lo : c->slab.own_hi - L;
+    const int hi = side == 0 ? c->slab.own_lo + L : c->slab.own_hi;
+    const float ref_inv = 1.0f / c->prm.neighbor_search_radius;
+    unsigned int h = 0;
+    CU(c, cudaMemsetAsync(c->d_counts, 0, sizeof(unsigned int), c->stream));
+    c->stats.kernel_launches += launch_slab_halo(c->n, c->posm[c->cur], c->velid[c->cur], c->slab.axis, ref_inv, lo, hi,
+                                                 static_cast<float4*>(d_out), cap_records, c->d_counts, c->stream);
+    CU(c, cudaMemcpyAsync(&h, c->d_counts, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (h > cap_records) return fail(c, SPHB_E_CAPACITY, "%u halo particles exceed the exchange buffer (%zu records)", h, cap_records);
+    *count = h;
+    return SPHB_OK;
+}
+
+int sphb_slab_append(sphb_ctx* c, const void* d_in, size_t count, int ghost) {
+    if (!c) return SPHB_E_INVALID;
+    if (count == 0) return SPHB_OK;
+    if (!d_in) return fail(c, SPHB_E_INVALID, "d_in is NULL");
+    if (c->n + count > c->capacity) return fail(c, SPHB_E_CAPACITY, "append of %zu records overflows capacity %zu (have %zu)", count, c->capacity, c->n);
+    CU(c, cudaSetDevice(c->device));
+    c->stats.kernel_launches += launch_slab_append(count, static_cast<const float4*>(d_in), ghost != 0, c->posm[c->cur] + c->n,
+                                                   c->velid[c->cur] + c->n, c->stream);
+    CU(c, cudaGetLastError());
+    c->n += count;
+    c->stepped_since_upload = false;
+    return SPHB_OK;
+}
+
+int sphb_slab_download(sphb_ctx* c, size_t cap, uint32_t* ids, float* pos3, float* vel3, float* rho, float* pressure,
+                       float* acc3, size_t* count) {
+    if (!c || !ids || !count) return SPHB_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    const size_t n = c->n;
+    *count = 0;
+    if (n == 0) return SPHB_OK;
+    int rc = ensure_stage(c, n * 12 * sizeof(float));
+    if (rc) return rc;
+    float* d_pos = reinterpret_cast<float*>(c->d_stage);
+    float* d_vel = d_pos + 3 * n;
+    float* d_acc = d_vel + 3 * n;
+    float* d_rho = d_acc + 3 * n;
+    float* d_P = d_rho + n;
+    uint32_t* d_ids = reinterpret_cast<uint32_t*>(d_P + n);
+    unsigned int h = 0;
+    CU(c, cudaMemsetAsync(c->d_counts, 0, sizeof(unsigned int), c->stream));
+    c->stats.kernel_launches += launch_slab_export(n, c->posm[c->cur], c->velid[c->cur], c->rho_p, c->acc, d_ids, pos3 ? d_pos : nullptr,
+                                                   vel3 ? d_vel : nullptr, rho ? d_rho : nullptr, pressure ? d_P : nullptr,
+                                                   acc3 ? d_acc : nullptr, c->d_counts, c->stream);
+    CU(c, cudaMemcpyAsync(&h, c->d_counts, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (h > cap) return fail(c, SPHB_E_CAPACITY, "%u owned particles exceed the output capacity %zu", h, cap);
+    CU(c, cudaMemcpyAsync(ids, d_ids, h * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (pos3) CU(c, cudaMemcpyAsync(pos3, d_pos, (size_t)h * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (vel3) CU(c, cudaMemcpyAsync(vel3, d_vel, (size_t)h * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (acc3) CU(c, cudaMemcpyAsync(acc3, d_acc, (size_t)h * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (rho) CU(c, cudaMemcpyAsync(rho, d_rho, h * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (pressure) CU(c, cudaMemcpyAsync(pressure, d_P, h * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    *count = h;
     return SPHB_OK;
 }
 

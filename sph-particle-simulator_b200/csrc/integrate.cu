@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(kThreads) k_integrate(size_t n, float4* __rest
     const size_t s = (size_t)blockIdx.x * kThreads + threadIdx.x;
     const float dt = sc->dt;
     float v2 = 0.0f;
-    if (s < n) {
+    if (s < n && !(__float_as_uint(velid[s].w) & 0x80000000u)) {   // bit 31 of the id word: halo copy (slab mode), not advanced
         float4 p = posm[s];
         float4 v = velid[s];
         const float4 a = acc[s];
@@ -47,8 +47,8 @@ __global__ void __launch_bounds__(kThreads) k_integrate(size_t n, float4* __rest
         velid[s] = v;
         v2 = __fadd_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)), __fmul_rn(v.z, v.z));
         if (__float_as_uint(v.w) == 0u) { sc->a0[0] = a.x; sc->a0[1] = a.y; sc->a0[2] = a.z; }
-        if (s == 0) sc->time = __fadd_rn(sc->time, dt);
     }
+    if (s == 0) sc->time = __fadd_rn(sc->time, dt);   // current_time_ += dt (sph_engine.cpp:138)
     unsigned bits = (v2 == v2) ? __float_as_uint(v2) : 0u;
     bits = __reduce_max_sync(0xffffffffu, bits);
     if ((threadIdx.x & 31) == 0 && bits != 0u) atomicMax(&sc->max_v2_bits, bits);

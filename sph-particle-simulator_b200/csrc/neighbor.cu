@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(kThreads) k_cell_keys(size_t n, const float4* 
     size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
     float4 p = posm[i];
-    unsigned id = __float_as_uint(velid[i].w);
+    unsigned id = __float_as_uint(velid[i].w) & 0x7FFFFFFFu;   // bit 31 marks halo copies in slab mode
     if (refkeys) {
         // SpatialHash::get_grid_coords + hash_position, reference spatial_hash.h:20-36
         const int cx = cell_coord(p.x, g.ref_inv_cell), cy = cell_coord(p.y, g.ref_inv_cell), cz = cell_coord(p.z, g.ref_inv_cell);

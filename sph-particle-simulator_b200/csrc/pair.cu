@@ -22,6 +22,15 @@ __device__ __forceinline__ int cell_coord(float p, float inv_cell) { return __fl
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+// slab mode: is the density of this particle needed here (owned or first halo layer)?
+__device__ __forceinline__ bool wants_density(const PairArgs& a, const float4& p) {
+    if (a.slab_axis < 0) return true;
+    const float c = a.slab_axis == 0 ? p.x : (a.slab_axis == 1 ? p.y : p.z);
+    const int cell = cell_coord(c, a.grid.ref_inv_cell);
+    return cell >= a.rho_lo && cell < a.rho_hi;
+}
+__device__ __forceinline__ bool is_ghost(const float4& velid) { return (__float_as_uint(velid.w) & 0x80000000u) != 0u; }
+
 // Calls body(begin, end) for every contiguous slot run of the neighbourhood of cell (cx, cy, cz),
 // in the reference's visiting order.
 template <typename Body>
@@ -107,6 +116,7 @@ __global__ void __launch_bounds__(kThreads) k_force_simple(PairArgs a) {
     if (i >= a.n) return;
     const float4 pi = a.posm[i];
     const float4 vi = a.velid[i];
+    if (is_ghost(vi)) return;   // slab mode: halo copies are never advanced here
     const float P_i = a.rho_p[i].y;
     const int cx = clampi(cell_coord(pi.x, a.grid.inv_cell), a.grid.lo[0], a.grid.hi[0]);
     const int cy = clampi(cell_coord(pi.y, a.grid.inv_cell), a.grid.lo[1], a.grid.hi[1]);
@@ -183,7 +193,7 @@ template <int R_UNUSED = 0>
 __global__ void __launch_bounds__(kThreads) k_density_packed(PairArgs a) {
     const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
     unsigned count = 0;
-    if (i < a.n) {
+    if (i < a.n && wants_density(a, a.posm[i])) {
         const float4 pi = a.posm[i];
         const int cx = clampi(cell_coord(pi.x, a.grid.inv_cell), a.grid.lo[0], a.grid.hi[0]);
         const int cy = clampi(cell_coord(pi.y, a.grid.inv_cell), a.grid.lo[1], a.grid.hi[1]);
@@ -238,6 +248,7 @@ __global__ void __launch_bounds__(kThreads) k_force_packed(PairArgs a) {
     if (i >= a.n) return;
     const float4 pi = a.posm[i];
     const float4 vi = a.velid[i];
+    if (is_ghost(vi)) return;
     const int cx = clampi(cell_coord(pi.x, a.grid.inv_cell), a.grid.lo[0], a.grid.hi[0]);
     const int cy = clampi(cell_coord(pi.y, a.grid.inv_cell), a.grid.lo[1], a.grid.hi[1]);
     const int cz = clampi(cell_coord(pi.z, a.grid.inv_cell), a.grid.lo[2], a.grid.hi[2]);

@@ -123,6 +123,10 @@ struct PairArgs {
     int walk_radius;
     int strict;
     int variant;
+    // slab mode (slab_axis >= 0): density is evaluated for particles whose reference cell on the axis lies in
+    // [rho_lo, rho_hi) (owned + one halo layer); force only for owned particles (id word bit 31 clear)
+    int slab_axis;
+    int rho_lo, rho_hi;
 };
 int launch_density(const PairArgs& a, cudaStream_t st);
 int launch_force(const PairArgs& a, cudaStream_t st);
@@ -138,5 +142,23 @@ int launch_unpermute(size_t n, const float4* posm, const float4* velid, const fl
                      float* acc3, uint64_t* keys, uint32_t* perm, uint32_t* counts, cudaStream_t st);
 int launch_diagnostics(size_t n, const float4* posm, const float4* velid, const float2* rho_p, DeviceScalars* sc,
                        cudaStream_t st);
+
+// ---- slab decomposition (slab.cu) ----------------------------------------------------------------
+constexpr int kMaxRanks = 64;
+struct SlabCuts { int nranks; int cuts[kMaxRanks + 1]; };       // rank d owns reference cells [cuts[d], cuts[d+1])
+struct SlabOffsets { unsigned int start[kMaxRanks]; };           // record offset of each destination group
+int launch_slab_count(size_t n, const float4* posm, const float4* velid, const SlabCuts& sc, int axis, float ref_inv_cell,
+                      unsigned int* counts, cudaStream_t st);
+int launch_slab_split(size_t n, const float4* posm, const float4* velid, const SlabCuts& sc, int axis, float ref_inv_cell,
+                      int me, float4* posm_out, float4* velid_out, float4* rec, const SlabOffsets& off, unsigned int* cursors,
+                      cudaStream_t st);
+int launch_slab_halo(size_t n, const float4* posm, const float4* velid, int axis, float ref_inv_cell, int lo, int hi,
+                     float4* rec, size_t cap, unsigned int* cursor, cudaStream_t st);
+int launch_slab_append(size_t count, const float4* rec, bool ghost, float4* posm, float4* velid, cudaStream_t st);
+int launch_slab_export(size_t n, const float4* posm, const float4* velid, const float2* rho_p, const float4* acc,
+                       uint32_t* ids, float* pos3, float* vel3, float* rho, float* P, float* acc3, unsigned int* cursor,
+                       cudaStream_t st);
+int launch_pack_upload_ids(size_t n, const float* d_pos3, const float* d_vel3, const float* d_mass, const uint32_t* d_ids,
+                           float default_mass, float4* posm, float4* velid, cudaStream_t st);
 
 }  // namespace sphb

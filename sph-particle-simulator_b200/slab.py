@@ -1,0 +1,259 @@
+"""Slab domain decomposition across GPUs: host-side planning and the per-step exchange protocol.
+
+NEW functionality — the reference is a single-process CPU program.  One process per
+GPU (torch.distributed, NCCL over NVLink); rank d owns the reference cells [cuts[d], cuts[d+1]) along one
+axis.  Per step:
+
+  1. migration   owned particles whose cell left the slab go to the rank that now owns them
+                 (all_to_all_single: counts, then 32-byte records) — general, not just ±1 neighbours
+  2. halo        each rank sends copies of its two outermost cell layers to the adjacent ranks
+                 (batched isend/irecv); with two layers the density of the first ghost layer is recomputed
+                 locally, so a step needs ONE halo exchange
+  3. local step  sphb_step on owned + ghosts; ghosts are neither advanced nor kept
+
+All packing / unpacking runs in CUDA kernels of libsphb (csrc/slab.cu); this module only plans the cuts
+and moves device buffers.  Because every local step re-sorts owned + ghost particles by (cell, global id),
+an N-GPU run reproduces the 1-GPU run bit for bit in strict math mode (tests/test_slab_*.py).
+
+The exchange logic is written against a small "store" interface so that it can be exercised on CPU with
+gloo (tests/ supplies a numpy store as a test double); the product store is GpuStore below.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+REC = 8                    # floats per exchange record {x, y, z, m, vx, vy, vz, id}
+OPEN_LO, OPEN_HI = -(1 << 28), (1 << 28)   # open-ended first / last slab
+
+
+def axis_cells(pos: np.ndarray, axis: int, nsr: float) -> np.ndarray:
+    """Reference cell index along `axis`: (int)floorf(p * (1.0f / nsr)) in fp32 (spatial_hash.h:30-36)."""
+    inv = np.float32(1.0) / np.float32(nsr)
+    return np.floor(pos[:, axis].astype(np.float32) * inv).astype(np.int64)
+
+
+def plan_cuts(cells: np.ndarray, nranks: int, min_width: int = 2) -> np.ndarray:
+    """Cut the occupied cell range into `nranks` slabs of whole cells with near-equal particle counts.
+
+    Returns int32[nranks + 1]; the end slabs are open-ended so every cell maps to exactly one rank.
+    Every slab is at least `min_width` cells wide (the halo depth), which keeps halos nearest-neighbour."""
+    lo, hi = int(cells.min()), int(cells.max()) + 1
+    if hi - lo < nranks * min_width:
+        raise ValueError(f"{hi - lo} cells along the slab axis cannot host {nranks} slabs of >= {min_width} cells")
+    hist = np.bincount(cells - lo, minlength=hi - lo).astype(np.int64)
+    cum = np.concatenate([[0], np.cumsum(hist)])
+    total = cum[-1]
+    inner = []
+    prev = lo
+    for d in range(1, nranks):
+        target = total * d / nranks
+        c = lo + int(np.searchsorted(cum, target, side="left"))
+        # choose the closer of the two neighbouring cell faces
+        if c > lo and abs(cum[c - lo - 1] - target) < abs(cum[min(c - lo, hi - lo)] - target):
+            c -= 1
+        c = max(c, prev + min_width)
+        c = min(c, hi - (nranks - d) * min_width)
+        inner.append(c)
+        prev = c
+    return np.array([OPEN_LO] + inner + [OPEN_HI], dtype=np.int32)
+
+
+def rank_of_cells(cuts: np.ndarray, cells: np.ndarray) -> np.ndarray:
+    return np.clip(np.searchsorted(cuts, cells, side="right") - 1, 0, len(cuts) - 2)
+
+
+class GpuStore:
+    """One sphb context on one GPU, seen through the store interface the exchange protocol uses."""
+
+    def __init__(self, pkg, capacity: int, device_index: int, params: dict, strict: bool = False, stream=None, options=None):
+        self.pkg = pkg
+        self.device = torch.device("cuda", device_index)
+        self.ctx = pkg.Context(capacity, device_index)
+        capi = pkg.capi
+        self.ctx.set_option(capi.OPT_MATH_MODE, capi.MATH_STRICT if strict else capi.MATH_FAST)
+        for k, v in (options or {}).items():
+            self.ctx.set_option(k, v)
+        if stream is not None:
+            self.ctx.set_stream(stream)
+        self.ctx.set_params(params)
+        self.capacity = capacity
+
+    def configure(self, axis, own_lo, own_hi, layers, id_space, box_min, box_max):
+        self.ctx.set_slab(axis, own_lo, own_hi, layers, id_space, box_min, box_max)
+
+    def load(self, pos, vel, mass, ids):
+        self.ctx.upload_ids(pos, vel, mass, ids)
+
+    def extract_migrants(self, cuts, me, buf: torch.Tensor):
+        return self.ctx.slab_extract_migrants(cuts, me, buf.data_ptr(), buf.shape[0])
+
+    def extract_halo(self, side, buf: torch.Tensor) -> int:
+        return self.ctx.slab_extract_halo(side, buf.data_ptr(), buf.shape[0])
+
+    def append(self, buf: torch.Tensor, count: int, ghost: bool):
+        if count:
+            self.ctx.slab_append(buf.data_ptr(), count, ghost)
+
+    def step(self, dt):
+        self.ctx.step(dt)
+
+    def synchronize(self):
+        self.ctx.synchronize()
+
+    def download(self, **kw):
+        return self.ctx.slab_download(**kw)
+
+    @property
+    def size(self):
+        return self.ctx.size
+
+    def close(self):
+        self.ctx.close()
+
+
+class SlabRank:
+    """Per-rank state of the decomposition: its slab, its store and its exchange buffers."""
+
+    def __init__(self, store, rank: int, cuts: np.ndarray, axis: int, layers: int, id_space: int, box_min, box_max,
+                 exchange_capacity: int):
+        self.store, self.rank, self.cuts, self.axis, self.layers = store, rank, np.asarray(cuts, np.int32), axis, layers
+        self.nranks = len(cuts) - 1
+        for d in range(self.nranks):
+            if self.cuts[d + 1] - self.cuts[d] < layers:
+                raise ValueError("slab thinner than the halo depth")
+        store.configure(axis, int(cuts[rank]), int(cuts[rank + 1]), layers, id_space, box_min, box_max)
+        dev = store.device
+        self.send = torch.empty((exchange_capacity, REC), dtype=torch.float32, device=dev)
+        self.recv = torch.empty((exchange_capacity, REC), dtype=torch.float32, device=dev)
+        self.halo_out = [torch.empty((exchange_capacity, REC), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.halo_in = [torch.empty((exchange_capacity, REC), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.stats = {"migrants_sent": 0, "halo_sent": 0, "steps": 0}
+
+    def load_initial(self, pos, vel, mass, nsr: float):
+        """Every rank sees the same synthetic scene and keeps the particles of its own slab (global id = index)."""
+        cells = axis_cells(pos, self.axis, nsr)
+        mine = np.flatnonzero(rank_of_cells(self.cuts, cells) == self.rank)
+        self.store.load(pos[mine], None if vel is None else vel[mine], None if mass is None else mass[mine], mine.astype(np.uint32))
+        return mine
+
+    # -- phase helpers shared by both drivers ---------------------------------------------------------
+    def pack_migrants(self):
+        counts = self.store.extract_migrants(self.cuts, self.rank, self.send)
+        counts = [int(c) for c in counts]
+        counts[self.rank] = 0
+        self.stats["migrants_sent"] += sum(counts)
+        return counts
+
+    def pack_halo(self, side: int) -> int:
+        nbr = self.rank - 1 if side == 0 else self.rank + 1
+        if nbr < 0 or nbr >= self.nranks:
+            return 0
+        n = self.store.extract_halo(side, self.halo_out[side])
+        self.stats["halo_sent"] += n
+        return n
+
+
+def step_local(ranks: list[SlabRank], dt: float):
+    """All ranks inside ONE process (several contexts, possibly on one GPU): the same protocol with device
+    copies instead of NCCL.  Used by the single-GPU tests of the multi-GPU path."""
+    G = len(ranks)
+    counts = [r.pack_migrants() for r in ranks]
+    for r in ranks:
+        r.store.synchronize()
+    offs = [np.concatenate([[0], np.cumsum(c)]) for c in counts]
+    for dst in range(G):
+        for src in range(G):
+            n = counts[src][dst]
+            if n:
+                tmp = ranks[src].send[offs[src][dst]: offs[src][dst] + n].to(ranks[dst].store.device).contiguous()
+                torch.cuda.synchronize() if tmp.is_cuda else None
+                ranks[dst].store.append(tmp, n, False)
+                ranks[dst].store.synchronize()
+    halo = [[r.pack_halo(0), r.pack_halo(1)] for r in ranks]
+    for r in ranks:
+        r.store.synchronize()
+    for k, r in enumerate(ranks):
+        if k > 0 and halo[k][0]:
+            tmp = r.halo_out[0][: halo[k][0]].to(ranks[k - 1].store.device).contiguous()
+            torch.cuda.synchronize() if tmp.is_cuda else None
+            ranks[k - 1].store.append(tmp, halo[k][0], True)
+            ranks[k - 1].store.synchronize()
+        if k < G - 1 and halo[k][1]:
+            tmp = r.halo_out[1][: halo[k][1]].to(ranks[k + 1].store.device).contiguous()
+            torch.cuda.synchronize() if tmp.is_cuda else None
+            ranks[k + 1].store.append(tmp, halo[k][1], True)
+            ranks[k + 1].store.synchronize()
+    for r in ranks:
+        r.store.step(dt)
+        r.stats["steps"] += 1
+
+
+def step_distributed(r: SlabRank, dt: float, group=None):
+    """One process per GPU: the protocol over torch.distributed (NCCL on GPUs, gloo in the CPU tests)."""
+    import torch.distributed as dist
+
+    G, me, dev = r.nranks, r.rank, r.store.device
+    # 1. migration: counts, then records, both as all-to-all
+    counts = r.pack_migrants()
+    c_out = torch.tensor(counts, dtype=torch.int64, device=dev)
+    c_in = torch.empty(G, dtype=torch.int64, device=dev)
+    dist.all_to_all_single(c_in, c_out, group=group)
+    c_in = [int(x) for x in c_in.tolist()]
+    n_out, n_in = sum(counts), sum(c_in)
+    if n_in > r.recv.shape[0]:
+        raise RuntimeError(f"rank {me}: {n_in} incoming migrants exceed the exchange buffer")
+    # skip the payload round when nobody moves (one extra tiny all-reduce would cost the same as sending it)
+    any_t = torch.tensor([n_out + n_in], dtype=torch.int64, device=dev)
+    dist.all_reduce(any_t, op=dist.ReduceOp.MAX, group=group)
+    if int(any_t.item()) > 0:
+        dist.all_to_all_single(r.recv[:n_in].view(-1), r.send[:n_out].view(-1), output_split_sizes=[c * REC for c in c_in],
+                               input_split_sizes=[c * REC for c in counts], group=group)
+        r.store.append(r.recv, n_in, False)
+    # 2. halo: counts then records with the two adjacent ranks
+    n_send = [r.pack_halo(0), r.pack_halo(1)]
+    nbrs = [me - 1, me + 1]
+    cnt_send = [torch.tensor([n_send[s]], dtype=torch.int64, device=dev) for s in range(2)]
+    cnt_recv = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(2)]
+    ops = []
+    for s in range(2):
+        if 0 <= nbrs[s] < G:
+            ops.append(dist.P2POp(dist.isend, cnt_send[s], nbrs[s], group=group))
+            ops.append(dist.P2POp(dist.irecv, cnt_recv[s], nbrs[s], group=group))
+    for q in (dist.batch_isend_irecv(ops) if ops else []):
+        q.wait()
+    n_recv = [int(cnt_recv[s].item()) for s in range(2)]
+    ops = []
+    for s in range(2):
+        if 0 <= nbrs[s] < G:
+            if n_recv[s] > r.halo_in[s].shape[0]:
+                raise RuntimeError(f"rank {me}: {n_recv[s]} halo records exceed the exchange buffer")
+            if n_send[s]:
+                ops.append(dist.P2POp(dist.isend, r.halo_out[s][: n_send[s]], nbrs[s], group=group))
+            if n_recv[s]:
+                ops.append(dist.P2POp(dist.irecv, r.halo_in[s][: n_recv[s]], nbrs[s], group=group))
+    for q in (dist.batch_isend_irecv(ops) if ops else []):
+        q.wait()
+    for s in range(2):
+        if 0 <= nbrs[s] < G and n_recv[s]:
+            r.store.append(r.halo_in[s], n_recv[s], True)
+    # 3. local step
+    r.store.step(dt)
+    r.stats["steps"] += 1
+
+
+def gather_by_id(parts: list[dict], n_total: int) -> dict:
+    """Merge per-rank owned-particle downloads into insertion-order arrays."""
+    out = {}
+    for key in ("pos", "vel", "rho", "P", "acc"):
+        if key in parts[0]:
+            shape = (n_total, 3) if parts[0][key].ndim == 2 else (n_total,)
+            out[key] = np.zeros(shape, np.float32)
+    seen = np.zeros(n_total, np.int32)
+    for p in parts:
+        ids = p["ids"].astype(np.int64)
+        seen[ids] += 1
+        for key in out:
+            out[key][ids] = p[key]
+    out["owners"] = seen
+    return out

@@ -1,0 +1,134 @@
+"""GPU: slab decomposition parity — G slabs must reproduce the single-context run bit for bit
+(every local step re-sorts owned + ghost particles by (cell, global id), so layouts and summation
+orders do not depend on G).  Runs G contexts on ONE GPU inside one process (device copies instead of
+NCCL); the NCCL path itself needs >= 2 GPUs and is skipped otherwise."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from helpers import assert_bits, load_golden, params_from
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def single_run(pkg, params, pos, vel, mass, dt, steps, strict):
+    capi = pkg.capi
+    ctx = pkg.Context(len(pos), 0)
+    ctx.set_option(capi.OPT_MATH_MODE, capi.MATH_STRICT if strict else capi.MATH_FAST)
+    ctx.set_params(params)
+    ctx.upload(pos, vel, mass)
+    for _ in range(steps):
+        ctx.step(dt)
+    out = ctx.download()
+    ctx.close()
+    return out
+
+
+def slab_run(pkg, params, pos, vel, mass, dt, steps, strict, G, axis=2, cuts=None):
+    from sph_b200 import slab
+    n = len(pos)
+    nsr = float(params["neighbor_search_radius"])
+    if cuts is None:
+        cuts = slab.plan_cuts(slab.axis_cells(pos, axis, nsr), G, 2)
+    box_min = np.minimum(pos.min(0), [params["xmin"], params["ymin"], params["zmin"]])
+    box_max = np.maximum(pos.max(0), [params["xmax"], params["ymax"], params["zmax"]])
+    ranks = []
+    for d in range(G):
+        store = slab.GpuStore(pkg, n, 0, params, strict=strict)
+        ranks.append(slab.SlabRank(store, d, cuts, axis, 2, n, box_min, box_max, n))
+        ranks[-1].load_initial(pos, vel, mass, nsr)
+    for _ in range(steps):
+        slab.step_local(ranks, dt)
+    merged = slab.gather_by_id([r.store.download() for r in ranks], n)
+    stats = [dict(r.stats) for r in ranks]
+    for r in ranks:
+        r.store.close()
+    return merged, stats
+
+
+@pytest.mark.parametrize("strict", [True, False])
+@pytest.mark.parametrize("G", [2, 3])
+def test_dam_break_slabs_equal_single(pkg, G, strict):
+    from sph_b200 import scenes
+    pos, mass, params, dt = scenes.dam_break_scene(0.02)
+    want = single_run(pkg, params, pos, None, mass, dt, 6, strict)
+    got, stats = slab_run(pkg, params, pos, None, mass, dt, 6, strict, G)
+    assert (got["owners"] == 1).all()
+    for f in ("pos", "vel", "rho", "P", "acc"):
+        assert_bits(got[f], want[f], f"G={G} strict={strict} {f}")
+    assert all(s["halo_sent"] > 0 for s in stats)
+
+
+def test_migration_heavy_cloud(pkg):
+    """Particles streaming along the slab axis (several cells per step, bouncing off the walls)."""
+    g = load_golden("cloud600")
+    params = params_from(g["params"])
+    params = {k: float(v) for k, v in params.items()}
+    vel = g["vel"].copy()
+    vel[:, 2] = np.where(np.arange(600) % 2 == 0, 45.0, -45.0).astype(np.float32)
+    dt = 1e-3
+    want = single_run(pkg, params, g["pos"], vel, g["mass"], dt, 12, True)
+    from sph_b200 import slab
+    for G, cuts in ((2, None), (4, np.array([slab.OPEN_LO, -2, 0, 2, slab.OPEN_HI], np.int32))):
+        got, stats = slab_run(pkg, params, g["pos"], vel, g["mass"], dt, 12, True, G, cuts=cuts)
+        assert (got["owners"] == 1).all()
+        for f in ("pos", "vel", "rho", "acc"):
+            assert_bits(got[f], want[f], f"G={G} {f}")
+        assert sum(s["migrants_sent"] for s in stats) > 200
+
+
+def test_slab_along_x(pkg):
+    from sph_b200 import scenes
+    pos, mass, params, dt = scenes.dam_break_scene(0.02)
+    want = single_run(pkg, params, pos, None, mass, dt, 3, True)
+    got, _ = slab_run(pkg, params, pos, None, mass, dt, 3, True, 2, axis=0)
+    for f in ("pos", "rho", "acc"):
+        assert_bits(got[f], want[f], f"x-slabs {f}")
+
+
+NCCL_WORKER = r'''
+import sys, numpy as np, torch, torch.distributed as dist, os
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+import __graft_entry__ as g
+pkg = g.load_package()
+from sph_b200 import slab, scenes
+local = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+rank, world = dist.get_rank(), dist.get_world_size()
+pos, mass, params, dt = scenes.dam_break_scene(0.02)
+n = len(pos); nsr = float(params["neighbor_search_radius"])
+cuts = slab.plan_cuts(slab.axis_cells(pos, 2, nsr), world, 2)
+store = slab.GpuStore(pkg, n, local, params, strict=True, stream=torch.cuda.current_stream().cuda_stream)
+r = slab.SlabRank(store, rank, cuts, 2, 2, n, [-0.2, 0.0, -0.4], [0.2, 0.6, 0.4], n)
+r.load_initial(pos, None, mass, nsr)
+for _ in range(6):
+    slab.step_distributed(r, dt)
+parts = [None] * world
+dist.all_gather_object(parts, store.download())
+if rank == 0:
+    merged = slab.gather_by_id(parts, n)
+    ctx = pkg.Context(n, local); ctx.set_option(pkg.capi.OPT_MATH_MODE, 0); ctx.set_params(params); ctx.upload(pos, None, mass)
+    for _ in range(6): ctx.step(dt)
+    want = ctx.download()
+    for f in ("pos", "vel", "rho", "acc"):
+        assert np.array_equal(merged[f].view(np.uint32), want[f].view(np.uint32)), f
+    print("NCCL_SLAB_OK")
+dist.destroy_process_group()
+'''
+
+
+def test_nccl_two_gpus(pkg, tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (NCCL refuses two ranks on one device)")
+    script = tmp_path / "nccl_worker.py"
+    script.write_text(NCCL_WORKER)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29547", str(script), str(ROOT)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "NCCL_SLAB_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
