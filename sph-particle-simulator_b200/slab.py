@@ -190,39 +190,36 @@ def step_local(ranks: list[SlabRank], dt: float):
 
 
 def step_distributed(r: SlabRank, dt: float, group=None):
-    """One process per GPU: the protocol over torch.distributed (NCCL on GPUs, gloo in the CPU tests)."""
+    """One process per GPU: the protocol over torch.distributed (NCCL on GPUs, gloo in the CPU tests).
+
+    Host synchronisations per step: one per count read-back (migrants, halo) and one per count
+    all-gather — the counts are gathered (not all-to-all'ed) so that every rank knows the global migrant
+    total and the payload collective can be skipped consistently when nobody moved."""
     import torch.distributed as dist
 
     G, me, dev = r.nranks, r.rank, r.store.device
-    # 1. migration: counts, then records, both as all-to-all
-    counts = r.pack_migrants()
-    c_out = torch.tensor(counts, dtype=torch.int64, device=dev)
-    c_in = torch.empty(G, dtype=torch.int64, device=dev)
-    dist.all_to_all_single(c_in, c_out, group=group)
-    c_in = [int(x) for x in c_in.tolist()]
-    n_out, n_in = sum(counts), sum(c_in)
-    if n_in > r.recv.shape[0]:
-        raise RuntimeError(f"rank {me}: {n_in} incoming migrants exceed the exchange buffer")
-    # skip the payload round when nobody moves (one extra tiny all-reduce would cost the same as sending it)
-    any_t = torch.tensor([n_out + n_in], dtype=torch.int64, device=dev)
-    dist.all_reduce(any_t, op=dist.ReduceOp.MAX, group=group)
-    if int(any_t.item()) > 0:
+    # 1. migration
+    counts = r.pack_migrants()                                   # counts[d] = records for rank d (0 for me)
+    mine = torch.tensor(counts, dtype=torch.int64, device=dev)
+    table = torch.empty((G, G), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(table.view(-1), mine, group=group)
+    table = table.cpu().numpy()                                  # table[src, dst]
+    if table.sum() > 0:
+        c_in = [int(table[src, me]) for src in range(G)]
+        n_out, n_in = sum(counts), sum(c_in)
+        if n_in > r.recv.shape[0]:
+            raise RuntimeError(f"rank {me}: {n_in} incoming migrants exceed the exchange buffer")
         dist.all_to_all_single(r.recv[:n_in].view(-1), r.send[:n_out].view(-1), output_split_sizes=[c * REC for c in c_in],
                                input_split_sizes=[c * REC for c in counts], group=group)
         r.store.append(r.recv, n_in, False)
-    # 2. halo: counts then records with the two adjacent ranks
+    # 2. halo: both faces packed, counts all-gathered, records exchanged with the adjacent ranks
     n_send = [r.pack_halo(0), r.pack_halo(1)]
+    hs = torch.tensor(n_send, dtype=torch.int64, device=dev)
+    ht = torch.empty((G, 2), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(ht.view(-1), hs, group=group)
+    ht = ht.cpu().numpy()                                        # ht[rank, side]
     nbrs = [me - 1, me + 1]
-    cnt_send = [torch.tensor([n_send[s]], dtype=torch.int64, device=dev) for s in range(2)]
-    cnt_recv = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(2)]
-    ops = []
-    for s in range(2):
-        if 0 <= nbrs[s] < G:
-            ops.append(dist.P2POp(dist.isend, cnt_send[s], nbrs[s], group=group))
-            ops.append(dist.P2POp(dist.irecv, cnt_recv[s], nbrs[s], group=group))
-    for q in (dist.batch_isend_irecv(ops) if ops else []):
-        q.wait()
-    n_recv = [int(cnt_recv[s].item()) for s in range(2)]
+    n_recv = [int(ht[me - 1, 1]) if me > 0 else 0, int(ht[me + 1, 0]) if me < G - 1 else 0]
     ops = []
     for s in range(2):
         if 0 <= nbrs[s] < G:
@@ -235,7 +232,7 @@ def step_distributed(r: SlabRank, dt: float, group=None):
     for q in (dist.batch_isend_irecv(ops) if ops else []):
         q.wait()
     for s in range(2):
-        if 0 <= nbrs[s] < G and n_recv[s]:
+        if n_recv[s]:
             r.store.append(r.halo_in[s], n_recv[s], True)
     # 3. local step
     r.store.step(dt)
