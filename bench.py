@@ -208,7 +208,7 @@ def run_ours(args):
         store = slab.GpuStore(pkg, cap, local, params, strict=strict, stream=stream.cuda_stream, options=opts)
         box_min = np.minimum(pos.min(0), [params["xmin"], params["ymin"], params["zmin"]])
         box_max = np.maximum(pos.max(0), [params["xmax"], params["ymax"], params["zmax"]])
-        sr = slab.SlabRank(store, rank, cuts, axis, 2, n_total, box_min, box_max, max(2 * lay + 65536, n_local // 4))
+        sr = slab.SlabRank(store, rank, cuts, axis, 2, n_total, box_min, box_max, max(4 * lay + 65536, n_local // 2))
         ctx = store.ctx
         mine = np.flatnonzero(owner == rank)
         parallelism = f"slab{world}(z), 2-layer halo, NCCL all_to_all migration + isend/irecv halo"

@@ -43,7 +43,7 @@ ABI_SYMBOLS = (
     "sphb_upload_strided", "sphb_download", "sphb_download_strided", "sphb_size", "sphb_step", "sphb_run_steps",
     "sphb_get_time", "sphb_set_time", "sphb_cfl_timestep", "sphb_get_stats", "sphb_reset_stats",
     "sphb_diagnostics", "sphb_debug_dump",
-    "sphb_set_slab", "sphb_upload_ids", "sphb_slab_extract_migrants", "sphb_slab_extract_halo", "sphb_slab_append",
+    "sphb_set_slab", "sphb_upload_ids", "sphb_slab_extract_migrants", "sphb_slab_extract_halo", "sphb_slab_append", "sphb_slab_exchange_pack",
     "sphb_slab_download",
 )
 
@@ -113,6 +113,7 @@ def load_library() -> C.CDLL:
     L.sphb_set_slab.argtypes = [vp, C.POINTER(SphbSlab)]
     L.sphb_upload_ids.argtypes = [vp, sz, vp, vp, vp, vp]
     L.sphb_slab_extract_migrants.argtypes = [vp, vp, C.c_int, C.c_int, vp, sz, vp]
+    L.sphb_slab_exchange_pack.argtypes = [vp, vp, C.c_int, C.c_int, vp, sz, vp]
     L.sphb_slab_extract_halo.argtypes = [vp, C.c_int, vp, sz, C.POINTER(C.c_uint64)]
     L.sphb_slab_append.argtypes = [vp, vp, sz, C.c_int]
     L.sphb_slab_download.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, C.POINTER(sz)]
@@ -289,13 +290,22 @@ class Context:
                                                    _ptr(counts)))
         return counts
 
+    def slab_exchange_pack(self, cuts, my_rank: int, d_out_ptr: int, cap_records: int) -> np.ndarray:
+        cuts = np.ascontiguousarray(cuts, np.int32)
+        nranks = cuts.shape[0] - 1
+        counts = np.zeros(2 * nranks, np.uint64)
+        self._ck(self.L.sphb_slab_exchange_pack(self.h, _ptr(cuts), nranks, int(my_rank), C.c_void_p(d_out_ptr), int(cap_records),
+                                                _ptr(counts)))
+        return counts
+
     def slab_extract_halo(self, side: int, d_out_ptr: int, cap_records: int) -> int:
         n = C.c_uint64()
         self._ck(self.L.sphb_slab_extract_halo(self.h, int(side), C.c_void_p(d_out_ptr), int(cap_records), C.byref(n)))
         return n.value
 
     def slab_append(self, d_in_ptr: int, count: int, ghost: bool):
-        self._ck(self.L.sphb_slab_append(self.h, C.c_void_p(d_in_ptr), int(count), 1 if ghost else 0))
+        flag = -1 if ghost is None else (1 if ghost else 0)     # None: records carry their own ghost flag
+        self._ck(self.L.sphb_slab_append(self.h, C.c_void_p(d_in_ptr), int(count), flag))
 
     def slab_download(self, pos=True, vel=True, rho=True, pressure=True, acc=True) -> dict:
         cap = self.size

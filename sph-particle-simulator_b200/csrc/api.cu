@@ -74,7 +74,7 @@ struct sphb_ctx {
 
     bool slab_on = false;
     sphb_slab slab{};
-    unsigned int* d_counts = nullptr;   // kMaxRanks + 1 counters / cursors
+    unsigned int* d_counts = nullptr;   // 2 * kMaxRanks + 1 counters / cursors
 
     uint64_t step_count = 0;
     sphb_stats stats{};
@@ -376,7 +376,7 @@ int sphb_create(sphb_ctx** out, size_t capacity, int device) {
     CUC(cudaMallocHost(&c->h_sc, sizeof(DeviceScalars)));
     memset(c->h_sc, 0, sizeof(DeviceScalars));
     CUC(cudaMalloc(&c->d_box, 6 * sizeof(int)));
-    CUC(cudaMalloc(&c->d_counts, (kMaxRanks + 1) * sizeof(unsigned int)));
+    CUC(cudaMalloc(&c->d_counts, (2 * kMaxRanks + 1) * sizeof(unsigned int)));
 #undef CUC
     *out = c;
     return SPHB_OK;
@@ -878,6 +878,43 @@ int sphb_slab_extract_migrants(sphb_ctx* c, const int32_t* cuts, int nranks, int
     return SPHB_OK;
 }
 
+int sphb_slab_exchange_pack(sphb_ctx* c, const int32_t* cuts, int nranks, int my_rank, void* d_out, size_t cap_records,
+                            uint64_t* counts) {
+    if (!c || !cuts || !counts) return SPHB_E_INVALID;
+    if (!c->slab_on) return fail(c, SPHB_E_INVALID, "sphb_set_slab first");
+    if (nranks < 1 || nranks > kMaxRanks || my_rank < 0 || my_rank >= nranks) return fail(c, SPHB_E_INVALID, "bad rank layout");
+    CU(c, cudaSetDevice(c->device));
+    SlabCuts sc;
+    sc.nranks = nranks;
+    for (int d = 0; d <= nranks; ++d) sc.cuts[d] = cuts[d];
+    const float ref_inv = 1.0f / c->prm.neighbor_search_radius;
+    const int in = c->cur, out = c->cur ^ 1;
+    const int L = c->slab.halo_layers;
+    unsigned int h[2 * kMaxRanks];
+    CU(c, cudaMemsetAsync(c->d_counts, 0, (2 * kMaxRanks + 1) * sizeof(unsigned int), c->stream));
+    c->stats.kernel_launches += launch_exchange_count(c->n, c->posm[in], c->velid[in], sc, c->slab.axis, ref_inv, L, c->d_counts, c->stream);
+    CU(c, cudaMemcpyAsync(h, c->d_counts, 2 * nranks * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    ExchangeOffsets off;
+    size_t total = 0;
+    for (int k = 0; k < 2 * nranks; ++k) {
+        off.start[k] = (unsigned int)total;
+        if (k != 2 * my_rank) total += h[k];      // key 2*me = particles kept in place
+        counts[k] = h[k];
+    }
+    if (total > cap_records) return fail(c, SPHB_E_CAPACITY, "%zu exchange records exceed the buffer (%zu records)", total, cap_records);
+    if (total > 0 && !d_out) return fail(c, SPHB_E_INVALID, "d_out is NULL");
+    CU(c, cudaMemsetAsync(c->d_counts, 0, (2 * kMaxRanks + 1) * sizeof(unsigned int), c->stream));
+    c->stats.kernel_launches += launch_exchange_split(c->n, c->posm[in], c->velid[in], sc, c->slab.axis, ref_inv, L, my_rank,
+                                                      c->posm[out], c->velid[out], static_cast<float4*>(d_out), off, c->d_counts,
+                                                      c->stream);
+    CU(c, cudaGetLastError());
+    c->cur = out;
+    c->n = h[2 * my_rank];
+    c->stepped_since_upload = false;
+    return SPHB_OK;
+}
+
 int sphb_slab_extract_halo(sphb_ctx* c, int side, void* d_out, size_t cap_records, uint64_t* count) {
     if (!c || !count) return SPHB_E_INVALID;
     if (!c->slab_on) return fail(c, SPHB_E_INVALID, "sphb_set_slab first");
@@ -903,8 +940,12 @@ int sphb_slab_append(sphb_ctx* c, const void* d_in, size_t count, int ghost) {
     if (!d_in) return fail(c, SPHB_E_INVALID, "d_in is NULL");
     if (c->n + count > c->capacity) return fail(c, SPHB_E_CAPACITY, "append of %zu records overflows capacity %zu (have %zu)", count, c->capacity, c->n);
     CU(c, cudaSetDevice(c->device));
-    c->stats.kernel_launches += launch_slab_append(count, static_cast<const float4*>(d_in), ghost != 0, c->posm[c->cur] + c->n,
-                                                   c->velid[c->cur] + c->n, c->stream);
+    if (ghost < 0)   // records carry their own ghost flag (one-round exchange)
+        c->stats.kernel_launches += launch_slab_append_asis(count, static_cast<const float4*>(d_in), c->posm[c->cur] + c->n,
+                                                            c->velid[c->cur] + c->n, c->stream);
+    else
+        c->stats.kernel_launches += launch_slab_append(count, static_cast<const float4*>(d_in), ghost != 0, c->posm[c->cur] + c->n,
+                                                       c->velid[c->cur] + c->n, c->stream);
     CU(c, cudaGetLastError());
     c->n += count;
     c->stepped_since_upload = false;

@@ -148,6 +148,79 @@ __global__ void __launch_bounds__(kThreads) k_pack_upload_ids(size_t n, const fl
                            __uint_as_float(ids[i] & ~kGhostBit));
 }
 
+// ---- one-round exchange: every owned particle goes to its (possibly new) owner and, flagged as ghost,
+// to each adjacent rank whose halo layers contain its cell.  Keys: 2*r = "owned by r", 2*r+1 = "ghost for r".
+struct Route { int owner, ghost_lo, ghost_hi; };   // ranks; -1 = none
+
+__device__ __forceinline__ Route route_of(const SlabCuts& sc, int cell, int layers) {
+    Route r;
+    r.owner = dest_of(sc, cell);
+    r.ghost_lo = (r.owner > 0 && cell < sc.cuts[r.owner] + layers) ? r.owner - 1 : -1;
+    r.ghost_hi = (r.owner < sc.nranks - 1 && cell >= sc.cuts[r.owner + 1] - layers) ? r.owner + 1 : -1;
+    return r;
+}
+
+__device__ __forceinline__ void grouped_count(int key, unsigned int* counters) {
+    const unsigned peers = __match_any_sync(kFull, key);
+    if (key >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&counters[key], __popc(peers));
+}
+
+__global__ void __launch_bounds__(kThreads) k_exchange_count(size_t n, const float4* __restrict__ posm,
+                                                             const float4* __restrict__ velid, SlabCuts sc, int axis,
+                                                             float ref_inv_cell, int layers, unsigned int* __restrict__ counts) {
+    const size_t s = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    Route r = {-1, -1, -1};
+    if (s < n && !(__float_as_uint(velid[s].w) & kGhostBit)) r = route_of(sc, axis_cell(posm[s], axis, ref_inv_cell), layers);
+    grouped_count(r.owner >= 0 ? 2 * r.owner : -1, counts);
+    grouped_count(r.ghost_lo >= 0 ? 2 * r.ghost_lo + 1 : -1, counts);
+    grouped_count(r.ghost_hi >= 0 ? 2 * r.ghost_hi + 1 : -1, counts);
+}
+
+__global__ void __launch_bounds__(kThreads) k_exchange_split(size_t n, const float4* __restrict__ posm,
+                                                             const float4* __restrict__ velid, SlabCuts sc, int axis,
+                                                             float ref_inv_cell, int layers, int me, float4* __restrict__ posm_out,
+                                                             float4* __restrict__ velid_out, float4* __restrict__ rec,
+                                                             ExchangeOffsets off, unsigned int* __restrict__ cursors) {
+    const size_t s = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    Route r = {-1, -1, -1};
+    float4 p, v;
+    if (s < n) {
+        v = velid[s];
+        if (!(__float_as_uint(v.w) & kGhostBit)) {
+            p = posm[s];
+            r = route_of(sc, axis_cell(p, axis, ref_inv_cell), layers);
+        }
+    }
+    const int k0 = r.owner >= 0 ? 2 * r.owner : -1;
+    const int k1 = r.ghost_lo >= 0 ? 2 * r.ghost_lo + 1 : -1;
+    const int k2 = r.ghost_hi >= 0 ? 2 * r.ghost_hi + 1 : -1;
+    const unsigned s0 = grouped_slot(k0, cursors);
+    const unsigned s1 = grouped_slot(k1, cursors);
+    const unsigned s2 = grouped_slot(k2, cursors);
+    if (k0 < 0) return;
+    if (r.owner == me) {
+        posm_out[s0] = p;
+        velid_out[s0] = v;
+    } else {
+        const size_t q = (size_t)off.start[k0] + s0;
+        rec[2 * q] = p;
+        rec[2 * q + 1] = v;
+    }
+    float4 g = v;
+    g.w = __uint_as_float(__float_as_uint(v.w) | kGhostBit);
+    if (k1 >= 0) { const size_t q = (size_t)off.start[k1] + s1; rec[2 * q] = p; rec[2 * q + 1] = g; }
+    if (k2 >= 0) { const size_t q = (size_t)off.start[k2] + s2; rec[2 * q] = p; rec[2 * q + 1] = g; }
+}
+
+// records keep the ghost flag they arrive with
+__global__ void __launch_bounds__(kThreads) k_slab_append_asis(size_t count, const float4* __restrict__ rec,
+                                                               float4* __restrict__ posm, float4* __restrict__ velid) {
+    const size_t k = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    if (k >= count) return;
+    posm[k] = rec[2 * k];
+    velid[k] = rec[2 * k + 1];
+}
+
 }  // namespace
 
 int launch_slab_count(size_t n, const float4* posm, const float4* velid, const SlabCuts& sc, int axis, float ref_inv_cell,
@@ -191,6 +264,28 @@ int launch_pack_upload_ids(size_t n, const float* d_pos3, const float* d_vel3, c
                            float default_mass, float4* posm, float4* velid, cudaStream_t st) {
     if (n == 0) return 0;
     k_pack_upload_ids<<<blocks_for(n), kThreads, 0, st>>>(n, d_pos3, d_vel3, d_mass, d_ids, default_mass, posm, velid);
+    return 1;
+}
+
+int launch_exchange_count(size_t n, const float4* posm, const float4* velid, const SlabCuts& sc, int axis, float ref_inv_cell,
+                          int layers, unsigned int* counts, cudaStream_t st) {
+    if (n == 0) return 0;
+    k_exchange_count<<<blocks_for(n), kThreads, 0, st>>>(n, posm, velid, sc, axis, ref_inv_cell, layers, counts);
+    return 1;
+}
+
+int launch_exchange_split(size_t n, const float4* posm, const float4* velid, const SlabCuts& sc, int axis, float ref_inv_cell,
+                          int layers, int me, float4* posm_out, float4* velid_out, float4* rec, const ExchangeOffsets& off,
+                          unsigned int* cursors, cudaStream_t st) {
+    if (n == 0) return 0;
+    k_exchange_split<<<blocks_for(n), kThreads, 0, st>>>(n, posm, velid, sc, axis, ref_inv_cell, layers, me, posm_out, velid_out,
+                                                          rec, off, cursors);
+    return 1;
+}
+
+int launch_slab_append_asis(size_t count, const float4* rec, float4* posm, float4* velid, cudaStream_t st) {
+    if (count == 0) return 0;
+    k_slab_append_asis<<<blocks_for(count), kThreads, 0, st>>>(count, rec, posm, velid);
     return 1;
 }
 

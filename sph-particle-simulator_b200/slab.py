@@ -4,12 +4,12 @@ NEW functionality â€” the reference is a single-process CPU program (SURVEY.md Â
 GPU (torch.distributed, NCCL over NVLink); rank d owns the reference cells [cuts[d], cuts[d+1]) along one
 axis.  Per step:
 
-  1. migration   owned particles whose cell left the slab go to the rank that now owns them
-                 (all_to_all_single: counts, then 32-byte records) â€” general, not just Â±1 neighbours
-  2. halo        each rank sends copies of its two outermost cell layers to the adjacent ranks
-                 (batched isend/irecv); with two layers the density of the first ghost layer is recomputed
-                 locally, so a step needs ONE halo exchange
-  3. local step  sphb_step on owned + ghosts; ghosts are neither advanced nor kept
+  1. exchange    ONE round: every owned particle is routed to the rank that owns its cell now (migration â€”
+                 general, not just Â±1 neighbours) and, flagged as ghost, to each adjacent rank whose two
+                 halo layers contain the cell.  Group sizes are all-gathered (16 B x ranks^2), the 32-byte
+                 records travel in one all_to_all_single.  With two halo layers the density of the first
+                 ghost layer is recomputed locally, so no mid-step exchange of densities is needed.
+  2. local step  sphb_step on owned + ghosts; ghosts are neither advanced nor kept
 
 All packing / unpacking runs in CUDA kernels of libsphb (csrc/slab.cu); this module only plans the cuts
 and moves device buffers.  Because every local step re-sorts owned + ghost particles by (cell, global id),
@@ -85,13 +85,12 @@ class GpuStore:
     def load(self, pos, vel, mass, ids):
         self.ctx.upload_ids(pos, vel, mass, ids)
 
-    def extract_migrants(self, cuts, me, buf: torch.Tensor):
-        return self.ctx.slab_extract_migrants(cuts, me, buf.data_ptr(), buf.shape[0])
+    def exchange_pack(self, cuts, me, buf: torch.Tensor):
+        """counts[2r] = records owned by rank r (kept in place for r = me), counts[2r+1] = ghosts for rank r."""
+        return self.ctx.slab_exchange_pack(cuts, me, buf.data_ptr(), buf.shape[0])
 
-    def extract_halo(self, side, buf: torch.Tensor) -> int:
-        return self.ctx.slab_extract_halo(side, buf.data_ptr(), buf.shape[0])
-
-    def append(self, buf: torch.Tensor, count: int, ghost: bool):
+    def append(self, buf: torch.Tensor, count: int, ghost=None):
+        """ghost=None: each record carries its own ghost flag (id bit 31)."""
         if count:
             self.ctx.slab_append(buf.data_ptr(), count, ghost)
 
@@ -126,8 +125,6 @@ class SlabRank:
         dev = store.device
         self.send = torch.empty((exchange_capacity, REC), dtype=torch.float32, device=dev)
         self.recv = torch.empty((exchange_capacity, REC), dtype=torch.float32, device=dev)
-        self.halo_out = [torch.empty((exchange_capacity, REC), dtype=torch.float32, device=dev) for _ in range(2)]
-        self.halo_in = [torch.empty((exchange_capacity, REC), dtype=torch.float32, device=dev) for _ in range(2)]
         self.stats = {"migrants_sent": 0, "halo_sent": 0, "steps": 0}
 
     def load_initial(self, pos, vel, mass, nsr: float):
@@ -137,53 +134,43 @@ class SlabRank:
         self.store.load(pos[mine], None if vel is None else vel[mine], None if mass is None else mass[mine], mine.astype(np.uint32))
         return mine
 
-    # -- phase helpers shared by both drivers ---------------------------------------------------------
-    def pack_migrants(self):
-        counts = self.store.extract_migrants(self.cuts, self.rank, self.send)
-        counts = [int(c) for c in counts]
-        counts[self.rank] = 0
-        self.stats["migrants_sent"] += sum(counts)
+    def pack(self):
+        """Route all owned particles; returns (per-destination send sizes, raw 2G counts with 'kept' zeroed)."""
+        counts = np.array(self.store.exchange_pack(self.cuts, self.rank, self.send), dtype=np.int64)
+        counts[2 * self.rank] = 0                                   # kept in place, not sent
+        self.stats["migrants_sent"] += int(counts[0::2].sum())
+        self.stats["halo_sent"] += int(counts[1::2].sum())
         return counts
 
-    def pack_halo(self, side: int) -> int:
-        nbr = self.rank - 1 if side == 0 else self.rank + 1
-        if nbr < 0 or nbr >= self.nranks:
-            return 0
-        n = self.store.extract_halo(side, self.halo_out[side])
-        self.stats["halo_sent"] += n
-        return n
+
+def _splits(table: np.ndarray, me: int):
+    """table[src, 2*dst + {0 owned, 1 ghost}] â†’ (records I send to each rank, records I receive from each rank)."""
+    G = table.shape[0]
+    send = [int(table[me, 2 * d] + table[me, 2 * d + 1]) for d in range(G)]
+    recv = [int(table[src, 2 * me] + table[src, 2 * me + 1]) for src in range(G)]
+    return send, recv
 
 
 def step_local(ranks: list[SlabRank], dt: float):
     """All ranks inside ONE process (several contexts, possibly on one GPU): the same protocol with device
     copies instead of NCCL.  Used by the single-GPU tests of the multi-GPU path."""
     G = len(ranks)
-    counts = [r.pack_migrants() for r in ranks]
+    table = np.stack([r.pack() for r in ranks])
     for r in ranks:
         r.store.synchronize()
-    offs = [np.concatenate([[0], np.cumsum(c)]) for c in counts]
+    offs = []
+    for src in range(G):
+        send, _ = _splits(table, src)
+        offs.append(np.concatenate([[0], np.cumsum(send)]))
     for dst in range(G):
         for src in range(G):
-            n = counts[src][dst]
+            n = int(offs[src][dst + 1] - offs[src][dst])
             if n:
                 tmp = ranks[src].send[offs[src][dst]: offs[src][dst] + n].to(ranks[dst].store.device).contiguous()
-                torch.cuda.synchronize() if tmp.is_cuda else None
-                ranks[dst].store.append(tmp, n, False)
+                if tmp.is_cuda:
+                    torch.cuda.synchronize()
+                ranks[dst].store.append(tmp, n, None)
                 ranks[dst].store.synchronize()
-    halo = [[r.pack_halo(0), r.pack_halo(1)] for r in ranks]
-    for r in ranks:
-        r.store.synchronize()
-    for k, r in enumerate(ranks):
-        if k > 0 and halo[k][0]:
-            tmp = r.halo_out[0][: halo[k][0]].to(ranks[k - 1].store.device).contiguous()
-            torch.cuda.synchronize() if tmp.is_cuda else None
-            ranks[k - 1].store.append(tmp, halo[k][0], True)
-            ranks[k - 1].store.synchronize()
-        if k < G - 1 and halo[k][1]:
-            tmp = r.halo_out[1][: halo[k][1]].to(ranks[k + 1].store.device).contiguous()
-            torch.cuda.synchronize() if tmp.is_cuda else None
-            ranks[k + 1].store.append(tmp, halo[k][1], True)
-            ranks[k + 1].store.synchronize()
     for r in ranks:
         r.store.step(dt)
         r.stats["steps"] += 1
@@ -191,50 +178,22 @@ def step_local(ranks: list[SlabRank], dt: float):
 
 def step_distributed(r: SlabRank, dt: float, group=None):
     """One process per GPU: the protocol over torch.distributed (NCCL on GPUs, gloo in the CPU tests).
-
-    Host synchronisations per step: one per count read-back (migrants, halo) and one per count
-    all-gather â€” the counts are gathered (not all-to-all'ed) so that every rank knows the global migrant
-    total and the payload collective can be skipped consistently when nobody moved."""
+    Two host synchronisations per step (group sizes off the device, gathered size table) and two
+    collectives (all_gather of 2G integers, all_to_all of the records)."""
     import torch.distributed as dist
 
     G, me, dev = r.nranks, r.rank, r.store.device
-    # 1. migration
-    counts = r.pack_migrants()                                   # counts[d] = records for rank d (0 for me)
-    mine = torch.tensor(counts, dtype=torch.int64, device=dev)
-    table = torch.empty((G, G), dtype=torch.int64, device=dev)
+    counts = r.pack()
+    mine = torch.from_numpy(counts).to(dev)
+    table = torch.empty((G, 2 * G), dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(table.view(-1), mine, group=group)
-    table = table.cpu().numpy()                                  # table[src, dst]
-    if table.sum() > 0:
-        c_in = [int(table[src, me]) for src in range(G)]
-        n_out, n_in = sum(counts), sum(c_in)
-        if n_in > r.recv.shape[0]:
-            raise RuntimeError(f"rank {me}: {n_in} incoming migrants exceed the exchange buffer")
-        dist.all_to_all_single(r.recv[:n_in].view(-1), r.send[:n_out].view(-1), output_split_sizes=[c * REC for c in c_in],
-                               input_split_sizes=[c * REC for c in counts], group=group)
-        r.store.append(r.recv, n_in, False)
-    # 2. halo: both faces packed, counts all-gathered, records exchanged with the adjacent ranks
-    n_send = [r.pack_halo(0), r.pack_halo(1)]
-    hs = torch.tensor(n_send, dtype=torch.int64, device=dev)
-    ht = torch.empty((G, 2), dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(ht.view(-1), hs, group=group)
-    ht = ht.cpu().numpy()                                        # ht[rank, side]
-    nbrs = [me - 1, me + 1]
-    n_recv = [int(ht[me - 1, 1]) if me > 0 else 0, int(ht[me + 1, 0]) if me < G - 1 else 0]
-    ops = []
-    for s in range(2):
-        if 0 <= nbrs[s] < G:
-            if n_recv[s] > r.halo_in[s].shape[0]:
-                raise RuntimeError(f"rank {me}: {n_recv[s]} halo records exceed the exchange buffer")
-            if n_send[s]:
-                ops.append(dist.P2POp(dist.isend, r.halo_out[s][: n_send[s]], nbrs[s], group=group))
-            if n_recv[s]:
-                ops.append(dist.P2POp(dist.irecv, r.halo_in[s][: n_recv[s]], nbrs[s], group=group))
-    for q in (dist.batch_isend_irecv(ops) if ops else []):
-        q.wait()
-    for s in range(2):
-        if n_recv[s]:
-            r.store.append(r.halo_in[s], n_recv[s], True)
-    # 3. local step
+    send, recv = _splits(table.cpu().numpy(), me)
+    n_out, n_in = sum(send), sum(recv)
+    if n_in > r.recv.shape[0]:
+        raise RuntimeError(f"rank {me}: {n_in} incoming records exceed the exchange buffer ({r.recv.shape[0]})")
+    dist.all_to_all_single(r.recv[:n_in].view(-1), r.send[:n_out].view(-1), output_split_sizes=[c * REC for c in recv],
+                           input_split_sizes=[c * REC for c in send], group=group)
+    r.store.append(r.recv, n_in, None)
     r.store.step(dt)
     r.stats["steps"] += 1
 

@@ -32,34 +32,44 @@ class NumpyStore:
         inv = np.float32(1.0) / self.nsr
         return np.floor(rec[:, self.axis] * inv).astype(np.int64)
 
-    def extract_migrants(self, cuts, me, buf):
+    def exchange_pack(self, cuts, me, buf):
+        """Same contract as sphb_slab_exchange_pack: groups [owned by r][ghosts for r] for r = 0..G-1."""
+        G = len(cuts) - 1
         rec = self.rec[~self.ghost]
-        dest = np.clip(np.searchsorted(cuts, self._cells(rec), side="right") - 1, 0, len(cuts) - 2)
-        counts = np.bincount(dest, minlength=len(cuts) - 1).astype(np.uint64)
+        cells = self._cells(rec)
+        owner = np.clip(np.searchsorted(cuts, cells, side="right") - 1, 0, G - 2 + 1)
+        L = self.layers
+        lo_edge = np.asarray(cuts)[owner].astype(np.int64)
+        hi_edge = np.asarray(cuts)[owner + 1].astype(np.int64)
+        ghost_lo = np.where((owner > 0) & (cells < lo_edge + L), owner - 1, -1)
+        ghost_hi = np.where((owner < G - 1) & (cells >= hi_edge - L), owner + 1, -1)
+        counts = np.zeros(2 * G, np.uint64)
         out = buf.numpy()
         k = 0
-        for d in range(len(cuts) - 1):
-            if d == me:
-                continue
-            sel = rec[dest == d]
-            out[k:k + len(sel)] = sel
-            k += len(sel)
-        self.rec = rec[dest == me].copy()
+        for r in range(G):
+            own = rec[owner == r]
+            counts[2 * r] = len(own)
+            if r != me:
+                out[k:k + len(own)] = own
+                k += len(own)
+            gh = rec[(ghost_lo == r) | (ghost_hi == r)].copy()
+            gh[:, 7] = (gh[:, 7].view(np.uint32) | np.uint32(0x80000000)).view(np.float32)
+            counts[2 * r + 1] = len(gh)
+            out[k:k + len(gh)] = gh
+            k += len(gh)
+        self.rec = rec[owner == me].copy()
         self.ghost = np.zeros(len(self.rec), bool)
         return counts
 
-    def extract_halo(self, side, buf):
-        rec = self.rec[~self.ghost]
-        c = self._cells(rec)
-        lo, hi = (self.own_lo, self.own_lo + self.layers) if side == 0 else (self.own_hi - self.layers, self.own_hi)
-        sel = rec[(c >= lo) & (c < hi)]
-        buf.numpy()[: len(sel)] = sel
-        return len(sel)
-
-    def append(self, buf, count, ghost):
-        if count:
-            self.rec = np.concatenate([self.rec, buf.numpy()[:count].copy()])
-            self.ghost = np.concatenate([self.ghost, np.full(count, bool(ghost))])
+    def append(self, buf, count, ghost=None):
+        if not count:
+            return
+        new = buf.numpy()[:count].copy()
+        word = new[:, 7].view(np.uint32)
+        flag = (word & np.uint32(0x80000000)) != 0 if ghost is None else np.full(count, bool(ghost))
+        new[:, 7] = (word & np.uint32(0x7FFFFFFF)).view(np.float32)
+        self.rec = np.concatenate([self.rec, new])
+        self.ghost = np.concatenate([self.ghost, flag])
 
     def ids(self, ghost):
         return np.sort(self.rec[self.ghost == ghost, 7].view(np.uint32))

@@ -40,7 +40,7 @@ def slab_run(pkg, params, pos, vel, mass, dt, steps, strict, G, axis=2, cuts=Non
     ranks = []
     for d in range(G):
         store = slab.GpuStore(pkg, n, 0, params, strict=strict)
-        ranks.append(slab.SlabRank(store, d, cuts, axis, 2, n, box_min, box_max, n))
+        ranks.append(slab.SlabRank(store, d, cuts, axis, 2, n, box_min, box_max, 3 * n))   # <= 3 records per owned particle
         ranks[-1].load_initial(pos, vel, mass, nsr)
     for _ in range(steps):
         slab.step_local(ranks, dt)
@@ -61,7 +61,7 @@ def test_dam_break_slabs_equal_single(pkg, G, strict):
     assert (got["owners"] == 1).all()
     for f in ("pos", "vel", "rho", "P", "acc"):
         assert_bits(got[f], want[f], f"G={G} strict={strict} {f}")
-    assert all(s["halo_sent"] > 0 for s in stats)
+    assert all(st["halo_sent"] > 0 for st in stats)
 
 
 def test_migration_heavy_cloud(pkg):
@@ -105,7 +105,7 @@ pos, mass, params, dt = scenes.dam_break_scene(0.02)
 n = len(pos); nsr = float(params["neighbor_search_radius"])
 cuts = slab.plan_cuts(slab.axis_cells(pos, 2, nsr), world, 2)
 store = slab.GpuStore(pkg, n, local, params, strict=True, stream=torch.cuda.current_stream().cuda_stream)
-r = slab.SlabRank(store, rank, cuts, 2, 2, n, [-0.2, 0.0, -0.4], [0.2, 0.6, 0.4], n)
+r = slab.SlabRank(store, rank, cuts, 2, 2, n, [-0.2, 0.0, -0.4], [0.2, 0.6, 0.4], 3 * n)
 r.load_initial(pos, None, mass, nsr)
 for _ in range(6):
     slab.step_distributed(r, dt)

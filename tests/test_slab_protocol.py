@@ -55,7 +55,7 @@ def test_protocol_in_process(pkg):
     n = len(pos)
     G, L = 3, 2
     cuts = slab.plan_cuts(slab.axis_cells(pos, 2, NSR), G, L)
-    ranks = [slab.SlabRank(NumpyStore(NSR, BOUNDS), d, cuts, 2, L, n, BOUNDS[0::2], BOUNDS[1::2], n) for d in range(G)]
+    ranks = [slab.SlabRank(NumpyStore(NSR, BOUNDS), d, cuts, 2, L, n, BOUNDS[0::2], BOUNDS[1::2], 3 * n) for d in range(G)]
     for r in ranks:
         r.load_initial(pos, vel, None, NSR)
     gp, gv = pos.copy(), vel.copy()
@@ -87,7 +87,7 @@ rank, world = dist.get_rank(), dist.get_world_size()
 pos, vel = T.make_cloud()
 n = len(pos)
 cuts = slab.plan_cuts(slab.axis_cells(pos, 2, T.NSR), world, 2)
-r = slab.SlabRank(NumpyStore(T.NSR, T.BOUNDS), rank, cuts, 2, 2, n, T.BOUNDS[0::2], T.BOUNDS[1::2], n)
+r = slab.SlabRank(NumpyStore(T.NSR, T.BOUNDS), rank, cuts, 2, 2, n, T.BOUNDS[0::2], T.BOUNDS[1::2], 3 * n)
 r.load_initial(pos, vel, None, T.NSR)
 gp, gv = pos.copy(), vel.copy()
 for step in range(6):
