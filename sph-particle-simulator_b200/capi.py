@@ -80,9 +80,11 @@ def load_library() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
+    import os
+    path = Path(os.environ.get("SPHB_LIB", str(LIB_PATH)))   # SPHB_LIB: alternative build of the same library (tuning runs)
+    if not path.exists():
         raise FileNotFoundError(f"{LIB_PATH} not built — run __graft_entry__.build() (sph-particle-simulator_b200/csrc/build.sh)")
-    L = C.CDLL(str(LIB_PATH))
+    L = C.CDLL(str(path))
     vp, sz, fp = C.c_void_p, C.c_size_t, C.POINTER(C.c_float)
     L.sphb_version.restype = C.c_int
     L.sphb_last_error.restype = C.c_char_p

@@ -17,6 +17,12 @@ namespace sphb {
 namespace {
 
 constexpr int kThreads = 128;
+#ifndef SPHB_FORCE_MINBLOCKS
+#define SPHB_FORCE_MINBLOCKS 1
+#endif
+#ifndef SPHB_DENSITY_MINBLOCKS
+#define SPHB_DENSITY_MINBLOCKS 1
+#endif
 
 __device__ __forceinline__ int cell_coord(float p, float inv_cell) { return __float2int_rd(__fmul_rn(p, inv_cell)); }
 
@@ -59,7 +65,7 @@ __device__ __forceinline__ void walk_runs(const GridDesc& g, const uint32_t* __r
 
 // ---- variant 0: one thread per particle, private walk -------------------------------------------------
 template <bool STRICT>
-__global__ void __launch_bounds__(kThreads) k_density_simple(PairArgs a) {
+__global__ void __launch_bounds__(kThreads, SPHB_DENSITY_MINBLOCKS) k_density_simple(PairArgs a) {
     const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
     unsigned count = 0;
     if (i < a.n) {
@@ -111,7 +117,7 @@ __global__ void __launch_bounds__(kThreads) k_density_simple(PairArgs a) {
 }
 
 template <bool STRICT>
-__global__ void __launch_bounds__(kThreads) k_force_simple(PairArgs a) {
+__global__ void __launch_bounds__(kThreads, SPHB_FORCE_MINBLOCKS) k_force_simple(PairArgs a) {
     const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= a.n) return;
     const float4 pi = a.posm[i];

@@ -341,9 +341,15 @@ void SPHEngine::step(float dt) {
     push_to_device();
     push_params();
     SPHB_CHECK(sphb_step(ctx_, dt));
+    // The reference's step() returns when the step is done and its callers time it with wall clocks
+    // (benchmarks/performance_test.cpp:118-126), so the shell synchronises by default; set_async(true) keeps the
+    // C ABI's enqueue-and-return behaviour.
+    if (!async_) SPHB_CHECK(sphb_synchronize(ctx_));
     device_ahead_ = true;
     ++step_count_;
 }
+
+void SPHEngine::set_async(bool on) { async_ = on; }
 
 // reference sph_engine.cpp:146-150
 void SPHEngine::run_steps(size_t num_steps, bool adaptive_timestep) {
@@ -421,6 +427,13 @@ void SPHEngine::compute_conservation_errors(float& mass_error, float& energy_err
     const float initial = particles_.size() * params_.particle_mass;
     mass_error = std::abs(total - initial) / initial;
     energy_error = 0.0f;
+}
+
+void SPHEngine::compute_conservation_errors(double& mass_error, double& energy_error) const {
+    float m = 0.0f, e = 0.0f;
+    compute_conservation_errors(m, e);
+    mass_error = m;
+    energy_error = e;
 }
 
 std::vector<glm::vec3> SPHEngine::get_positions() const {

@@ -156,6 +156,9 @@ public:
     void reset_performance_stats();
 
     void compute_conservation_errors(float& mass_error, float& energy_error) const;
+    // benchmarks/performance_test.cpp:157 passes doubles (which does not compile against the reference's own
+    // float& signature); this overload lets that driver build unmodified
+    void compute_conservation_errors(double& mass_error, double& energy_error) const;
     float get_total_mass() const;
     float get_total_energy() const;
 
@@ -174,6 +177,8 @@ public:
     std::vector<glm::vec3> get_accelerations() const;
     // the CFL timestep the next adaptive step would take (reference: private compute_cfl_timestep)
     float compute_cfl_timestep() const;
+    // false (default): step() returns when the GPU finished it, like the reference; true: enqueue and return
+    void set_async(bool on);
     sphb_ctx* native_handle() const { return ctx_; }
 
 private:
@@ -191,6 +196,7 @@ private:
     mutable bool device_ahead_ = false;  // device state is newer than the host AoS
     mutable PerformanceStats perf_;
     int math_mode_ = 1;
+    bool async_ = false;
 };
 
 // reference src/sph_engine.h:144-148 (never referenced by the engine; kept for source compatibility)

@@ -143,6 +143,7 @@ PYBIND11_MODULE(sph, m) {
         .def("get_pressures", [](const SPHEngine& e) { return float_array(e.get_pressures()); })
         // additions
         .def("set_math_mode", &SPHEngine::set_math_mode, py::arg("mode"))
+        .def("set_async", &SPHEngine::set_async, py::arg("on"))
         .def("get_accelerations", [](const SPHEngine& e) { return vec3_array(e.get_accelerations()); })
         .def("compute_cfl_timestep", &SPHEngine::compute_cfl_timestep);
 

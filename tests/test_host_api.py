@@ -169,3 +169,20 @@ def test_simulator_public_api_scene_and_quirks(sph, po):
     sim.step(0.001)
     assert sim.get_step_count() == 0
     ora.close()
+
+
+@pytest.mark.gpu
+def test_reference_benchmark_driver_runs_on_the_gpu_engine(tmp_path):
+    """The reference's own benchmarks/performance_test.cpp, compiled unmodified against the host shell
+    (dropin/build.sh, prebuilt in the build container), runs and writes its CSV schema."""
+    import subprocess
+    exe = ROOT / "dropin" / "_ref" / "performance_test"
+    if not exe.exists():
+        pytest.skip("dropin/_ref/performance_test not built (needs /root/reference at build time)")
+    out = subprocess.run([str(exe), "1000", "5000"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "Results for 1000 particles" in out.stdout and "Results for 5000 particles" in out.stdout
+    csv = (tmp_path / "benchmark_results.csv").read_text().splitlines()
+    assert csv[0].startswith("particles,avg_fps,min_fps,max_fps,avg_ms_frame,neighbor_search_pct") and len(csv) == 3
+    fps = float(csv[2].split(",")[1])
+    assert fps > 100.0, f"5000-particle config ran at {fps} FPS"
