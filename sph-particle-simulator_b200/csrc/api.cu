@@ -674,14 +674,32 @@ int sphb_step(sphb_ctx* c, float dt) {
     if (timing) cudaEventRecord(ev[2], st);
     launches += launch_force(pa, st);
     if (timing) cudaEventRecord(ev[3], st);
-    launches += launch_integrate(n, c->posm[c->cur], c->velid[c->cur], c->acc, ic, c->sc, st);
+    // after the clamp every position lies inside the AABB (particle.cpp:122-153), so the next step can size its
+    // cell table from the bounds without looking at the device.  When that table would be far larger than the
+    // particle count (sparse scene, e.g. a drop in a big box) the integrate kernel also reduces the bounding box
+    // of the new positions and the next step reads it back (one small synchronising copy) to build a tight table.
+    bool track_box = false;
+    if (!c->slab_on) {
+        const float bmin[3] = {c->prm.xmin, c->prm.ymin, c->prm.zmin}, bmax[3] = {c->prm.xmax, c->prm.ymax, c->prm.zmax};
+        double cells = 1.0;
+        for (int a = 0; a < 3; ++a) cells *= floor((double)(bmax[a] - bmin[a]) * (double)g.inv_cell) + 1.0;
+        track_box = cells > 8.0 * (double)n;
+    }
+    if (track_box) {
+        const int init[6] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, (int)0x80000000, (int)0x80000000, (int)0x80000000};
+        CU(c, cudaMemcpyAsync(c->d_box, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    }
+    launches += launch_integrate(n, c->posm[c->cur], c->velid[c->cur], c->acc, ic, c->sc, track_box ? c->d_box : nullptr, st);
     if (timing) cudaEventRecord(ev[4], st);
     CU(c, cudaGetLastError());
 
-    // after the clamp every position lies inside the AABB (particle.cpp:122-153)
-    c->box_min[0] = c->prm.xmin; c->box_max[0] = c->prm.xmax;
-    c->box_min[1] = c->prm.ymin; c->box_max[1] = c->prm.ymax;
-    c->box_min[2] = c->prm.zmin; c->box_max[2] = c->prm.zmax;
+    if (track_box) {
+        c->box_pending = true;
+    } else {
+        c->box_min[0] = c->prm.xmin; c->box_max[0] = c->prm.xmax;
+        c->box_min[1] = c->prm.ymin; c->box_max[1] = c->prm.ymax;
+        c->box_min[2] = c->prm.zmin; c->box_max[2] = c->prm.zmax;
+    }
     c->stepped_since_upload = true;
 
     c->step_count++;

@@ -22,7 +22,7 @@ __device__ __forceinline__ void clamp_axis(float& p, float& v, float lo, float h
 
 __global__ void __launch_bounds__(kThreads) k_integrate(size_t n, float4* __restrict__ posm, float4* __restrict__ velid,
                                                         const float4* __restrict__ acc, IntegrateConsts ic,
-                                                        DeviceScalars* sc) {
+                                                        DeviceScalars* sc, int* __restrict__ box) {
     const size_t s = (size_t)blockIdx.x * kThreads + threadIdx.x;
     const float dt = sc->dt;
     float v2 = 0.0f;
@@ -52,6 +52,38 @@ __global__ void __launch_bounds__(kThreads) k_integrate(size_t n, float4* __rest
     unsigned bits = (v2 == v2) ? __float_as_uint(v2) : 0u;
     bits = __reduce_max_sync(0xffffffffu, bits);
     if ((threadIdx.x & 31) == 0 && bits != 0u) atomicMax(&sc->max_v2_bits, bits);
+    if (box) {
+        // sparse scenes: bounding box of the new positions (ordered-int images of the floats), so the next
+        // step can size its cell table from the particles instead of the much larger AABB
+        int lo[3] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF}, hi[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
+        if (s < n) {
+            const float4 p = posm[s];
+            const float c[3] = {p.x, p.y, p.z};
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                if (fabsf(c[a]) <= 3.4028235e38f) {
+                    const int i = __float_as_int(c[a]);
+                    lo[a] = hi[a] = i >= 0 ? i : i ^ 0x7FFFFFFF;
+                }
+            }
+        }
+        __shared__ int s_lo[3][kThreads / 32], s_hi[3][kThreads / 32];
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const int l = __reduce_min_sync(0xffffffffu, lo[a]), h = __reduce_max_sync(0xffffffffu, hi[a]);
+            if (lane == 0) { s_lo[a][w] = l; s_hi[a][w] = h; }
+        }
+        __syncthreads();
+        if (threadIdx.x < 3) {   // one atomic pair per axis per CTA
+            const int a = threadIdx.x;
+            int l = s_lo[a][0], h = s_hi[a][0];
+#pragma unroll
+            for (int k = 1; k < kThreads / 32; ++k) { l = min(l, s_lo[a][k]); h = max(h, s_hi[a][k]); }
+            if (l != 0x7FFFFFFF) atomicMin(&box[a], l);
+            if (h != (int)0x80000000) atomicMax(&box[3 + a], h);
+        }
+    }
 }
 
 __global__ void k_set_dt(DeviceScalars* sc, float dt) {
@@ -92,8 +124,8 @@ int launch_cfl_probe(DeviceScalars* sc, IntegrateConsts ic, cudaStream_t st) {
 }
 
 int launch_integrate(size_t n, float4* posm, float4* velid, const float4* acc, IntegrateConsts ic, DeviceScalars* sc,
-                     cudaStream_t st) {
-    k_integrate<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(n, posm, velid, acc, ic, sc);
+                     int* d_box_or_null, cudaStream_t st) {
+    k_integrate<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(n, posm, velid, acc, ic, sc, d_box_or_null);
     return 1;
 }
 

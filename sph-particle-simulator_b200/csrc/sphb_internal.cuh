@@ -134,7 +134,7 @@ int launch_force(const PairArgs& a, cudaStream_t st);
 int launch_set_dt(DeviceScalars* sc, float dt, cudaStream_t st);
 int launch_cfl_dt(DeviceScalars* sc, IntegrateConsts ic, cudaStream_t st);
 int launch_integrate(size_t n, float4* posm, float4* velid, const float4* acc, IntegrateConsts ic, DeviceScalars* sc,
-                     cudaStream_t st);
+                     int* d_box_or_null, cudaStream_t st);
 int launch_max_speed(size_t n, const float4* velid, DeviceScalars* sc, cudaStream_t st);
 
 int launch_unpermute(size_t n, const float4* posm, const float4* velid, const float2* rho_p, const float4* acc,
