@@ -208,6 +208,12 @@ int sphb_slab_extract_halo(sphb_ctx* ctx, int side, void* d_out, size_t cap_reco
 int sphb_slab_append(sphb_ctx* ctx, const void* d_in, size_t count, int ghost);
 /* Owned particles of this context in arbitrary order: ids[k] with the matching fields (host pointers,
  * any field may be NULL); *count = number written (<= cap). */
+/* Adaptive timestep across slabs: compute_cfl_timestep (reference sph_engine.cpp:312-333) needs the global
+ * max |v|^2 and the acceleration of particle id 0.  get: this context's max |v|^2 over its owned particles, its
+ * copy of a0 and whether it advanced particle 0 in the last step (a0_fresh; cleared by the call).  set: install
+ * the globally reduced values before an adaptive sphb_step.  Both synchronise. */
+int sphb_get_cfl_state(sphb_ctx* ctx, float* max_v2, float* a0_xyz, int* a0_fresh);
+int sphb_set_cfl_state(sphb_ctx* ctx, float max_v2, const float* a0_xyz);
 int sphb_slab_download(sphb_ctx* ctx, size_t cap, uint32_t* ids, float* pos3, float* vel3, float* rho, float* pressure,
                        float* acc3, size_t* count);
 

@@ -43,7 +43,7 @@ ABI_SYMBOLS = (
     "sphb_upload_strided", "sphb_download", "sphb_download_strided", "sphb_size", "sphb_step", "sphb_run_steps",
     "sphb_get_time", "sphb_set_time", "sphb_cfl_timestep", "sphb_get_stats", "sphb_reset_stats",
     "sphb_diagnostics", "sphb_debug_dump",
-    "sphb_set_slab", "sphb_upload_ids", "sphb_slab_extract_migrants", "sphb_slab_extract_halo", "sphb_slab_append", "sphb_slab_exchange_pack",
+    "sphb_set_slab", "sphb_upload_ids", "sphb_slab_extract_migrants", "sphb_slab_extract_halo", "sphb_slab_append", "sphb_slab_exchange_pack", "sphb_get_cfl_state", "sphb_set_cfl_state",
     "sphb_slab_download",
 )
 
@@ -115,6 +115,8 @@ def load_library() -> C.CDLL:
     L.sphb_set_slab.argtypes = [vp, C.POINTER(SphbSlab)]
     L.sphb_upload_ids.argtypes = [vp, sz, vp, vp, vp, vp]
     L.sphb_slab_extract_migrants.argtypes = [vp, vp, C.c_int, C.c_int, vp, sz, vp]
+    L.sphb_get_cfl_state.argtypes = [vp, fp, fp, C.POINTER(C.c_int)]
+    L.sphb_set_cfl_state.argtypes = [vp, C.c_float, fp]
     L.sphb_slab_exchange_pack.argtypes = [vp, vp, C.c_int, C.c_int, vp, sz, vp]
     L.sphb_slab_extract_halo.argtypes = [vp, C.c_int, vp, sz, C.POINTER(C.c_uint64)]
     L.sphb_slab_append.argtypes = [vp, vp, sz, C.c_int]
@@ -321,3 +323,15 @@ class Context:
         self._ck(self.L.sphb_slab_download(self.h, cap, _ptr(out["ids"]), _ptr(out.get("pos")), _ptr(out.get("vel")),
                                            _ptr(out.get("rho")), _ptr(out.get("P")), _ptr(out.get("acc")), C.byref(n)))
         return {k: v[: n.value] for k, v in out.items()}
+
+    def get_cfl_state(self):
+        """(max |v|^2 over owned particles, a0[3], a0_fresh) — see sphb_get_cfl_state."""
+        v2 = C.c_float()
+        a0 = (C.c_float * 3)()
+        fresh = C.c_int()
+        self._ck(self.L.sphb_get_cfl_state(self.h, C.byref(v2), a0, C.byref(fresh)))
+        return np.float32(v2.value), np.array(list(a0), np.float32), bool(fresh.value)
+
+    def set_cfl_state(self, max_v2, a0):
+        arr = (C.c_float * 3)(*[float(x) for x in a0])
+        self._ck(self.L.sphb_set_cfl_state(self.h, C.c_float(float(max_v2)), arr))

@@ -1004,4 +1004,28 @@ int sphb_slab_download(sphb_ctx* c, size_t cap, uint32_t* ids, float* pos3, floa
     return SPHB_OK;
 }
 
+
+int sphb_get_cfl_state(sphb_ctx* c, float* max_v2, float* a0_xyz, int* a0_fresh) {
+    if (!c) return SPHB_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    int rc = read_scalars(c);
+    if (rc) return rc;
+    if (max_v2) memcpy(max_v2, &c->h_sc->max_v2_bits, 4);
+    if (a0_xyz) { a0_xyz[0] = c->h_sc->a0[0]; a0_xyz[1] = c->h_sc->a0[1]; a0_xyz[2] = c->h_sc->a0[2]; }
+    if (a0_fresh) *a0_fresh = c->h_sc->a0_fresh ? 1 : 0;
+    CU(c, cudaMemsetAsync(&c->sc->a0_fresh, 0, sizeof(unsigned), c->stream));
+    return SPHB_OK;
+}
+
+int sphb_set_cfl_state(sphb_ctx* c, float max_v2, const float* a0_xyz) {
+    if (!c || !a0_xyz) return SPHB_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    unsigned bits;
+    memcpy(&bits, &max_v2, 4);
+    CU(c, cudaMemcpyAsync(&c->sc->max_v2_bits, &bits, 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(&c->sc->a0[0], a0_xyz, 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return SPHB_OK;
+}
+
 }  // extern "C"

@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(kThreads) k_integrate(size_t n, float4* __rest
         posm[s] = p;
         velid[s] = v;
         v2 = __fadd_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)), __fmul_rn(v.z, v.z));
-        if (__float_as_uint(v.w) == 0u) { sc->a0[0] = a.x; sc->a0[1] = a.y; sc->a0[2] = a.z; }
+        if (__float_as_uint(v.w) == 0u) { sc->a0[0] = a.x; sc->a0[1] = a.y; sc->a0[2] = a.z; sc->a0_fresh = 1u; }
     }
     if (s == 0) sc->time = __fadd_rn(sc->time, dt);   // current_time_ += dt (sph_engine.cpp:138)
     unsigned bits = (v2 == v2) ? __float_as_uint(v2) : 0u;

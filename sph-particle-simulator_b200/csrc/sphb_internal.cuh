@@ -65,7 +65,7 @@ struct DeviceScalars {
     unsigned int error_flags;   // bit0: a particle fell outside the cell box
     double sum_rho, kinetic;    // diagnostics scratch
     unsigned int diag_max_v2_bits;
-    unsigned int pad;
+    unsigned int a0_fresh;      // set by k_integrate when it advanced particle id 0 (slab mode: who owns a0)
 };
 
 // ---- launch wrappers (each returns the number of kernels it enqueued) ---------------------------

@@ -77,6 +77,7 @@ class GpuStore:
         if stream is not None:
             self.ctx.set_stream(stream)
         self.ctx.set_params(params)
+        self.params = dict(params)
         self.capacity = capacity
 
     def configure(self, axis, own_lo, own_hi, layers, id_space, box_min, box_max):
@@ -96,6 +97,12 @@ class GpuStore:
 
     def step(self, dt):
         self.ctx.step(dt)
+
+    def cfl_state(self):
+        return self.ctx.get_cfl_state()
+
+    def set_cfl_state(self, max_v2, a0):
+        self.ctx.set_cfl_state(max_v2, a0)
 
     def synchronize(self):
         self.ctx.synchronize()
@@ -126,6 +133,7 @@ class SlabRank:
         self.send = torch.empty((exchange_capacity, REC), dtype=torch.float32, device=dev)
         self.recv = torch.empty((exchange_capacity, REC), dtype=torch.float32, device=dev)
         self.stats = {"migrants_sent": 0, "halo_sent": 0, "steps": 0}
+        self.params = getattr(store, "params", None)      # needed only for adaptive timesteps
 
     def load_initial(self, pos, vel, mass, nsr: float):
         """Every rank sees the same synthetic scene and keeps the particles of its own slab (global id = index)."""
@@ -141,6 +149,31 @@ class SlabRank:
         self.stats["migrants_sent"] += int(counts[0::2].sum())
         self.stats["halo_sent"] += int(counts[1::2].sum())
         return counts
+
+
+def cfl_timestep(params: dict, max_v2, a0) -> np.float32:
+    """SPHEngine::compute_cfl_timestep (reference sph_engine.cpp:312-333) from globally reduced inputs, in the
+    same fp32 operation order as the device kernel k_cfl_dt (so every rank derives the identical dt)."""
+    f = np.float32
+    cfl, h, ts = f(params["CFL_factor"]), f(params["smoothing_length"]), f(params["timestep"])
+    max_velocity = np.sqrt(f(max_v2))
+    dt_cfl = f(cfl * h) / f(max_velocity + f(1e-6))
+    a = f(a0[0]) * f(a0[0]) + f(a0[1]) * f(a0[1])
+    a = np.sqrt(f(f(a) + f(a0[2]) * f(a0[2])))
+    dt_force = f(cfl * np.sqrt(f(h / f(a + f(1e-6)))))
+    m = dt_cfl
+    if dt_force < m:
+        m = dt_force
+    if ts < m:
+        m = ts
+    return f(m)
+
+
+def reduce_cfl_state(states):
+    """states: [(max_v2, a0, fresh)] of every rank → (global max_v2, a0 of the rank that last advanced id 0 or None)."""
+    v2 = max(np.float32(s[0]) for s in states)
+    fresh = [s[1] for s in states if s[2]]
+    return v2, (fresh[0] if fresh else None)
 
 
 def _splits(table: np.ndarray, me: int):
@@ -171,9 +204,16 @@ def step_local(ranks: list[SlabRank], dt: float):
                     torch.cuda.synchronize()
                 ranks[dst].store.append(tmp, n, None)
                 ranks[dst].store.synchronize()
+    if dt <= 0.0:                                            # adaptive: global CFL inputs, identical dt everywhere
+        states = [r.store.cfl_state() for r in ranks]
+        v2, a0 = reduce_cfl_state(states)
+        for r, st in zip(ranks, states):
+            r.a0 = a0 if a0 is not None else getattr(r, "a0", np.zeros(3, np.float32))
+        dt = float(cfl_timestep(ranks[0].params, v2, ranks[0].a0))
     for r in ranks:
         r.store.step(dt)
         r.stats["steps"] += 1
+    return dt
 
 
 def step_distributed(r: SlabRank, dt: float, group=None):
@@ -194,8 +234,22 @@ def step_distributed(r: SlabRank, dt: float, group=None):
     dist.all_to_all_single(r.recv[:n_in].view(-1), r.send[:n_out].view(-1), output_split_sizes=[c * REC for c in recv],
                            input_split_sizes=[c * REC for c in send], group=group)
     r.store.append(r.recv, n_in, None)
+    if dt <= 0.0:                                            # adaptive: all-reduce the CFL inputs
+        v2, a0, fresh = r.store.cfl_state()
+        buf = torch.tensor([float(v2), float(a0[0]) if fresh else 0.0, float(a0[1]) if fresh else 0.0,
+                            float(a0[2]) if fresh else 0.0, 1.0 if fresh else 0.0], dtype=torch.float32, device=dev)
+        vmax = buf[:1].clone()
+        dist.all_reduce(vmax, op=dist.ReduceOp.MAX, group=group)
+        dist.all_reduce(buf[1:], op=dist.ReduceOp.SUM, group=group)     # exactly one rank is fresh: the sum IS its a0
+        host = buf.cpu().numpy()
+        if host[4] > 0:
+            r.a0 = host[1:4].astype(np.float32)
+        elif not hasattr(r, "a0"):
+            r.a0 = np.zeros(3, np.float32)
+        dt = float(cfl_timestep(r.params, np.float32(vmax.item()), r.a0))
     r.store.step(dt)
     r.stats["steps"] += 1
+    return dt
 
 
 def gather_by_id(parts: list[dict], n_total: int) -> dict:

@@ -132,3 +132,35 @@ def test_nccl_two_gpus(pkg, tmp_path):
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                           "127.0.0.1", "--master-port", "29547", str(script), str(ROOT)], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "NCCL_SLAB_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+def test_adaptive_timestep_across_slabs(pkg):
+    """dt <= 0: the CFL inputs (max |v|^2, acceleration of particle 0) are reduced across slabs; every step's
+    dt and the final state equal the single-context adaptive run bit for bit."""
+    from sph_b200 import scenes, slab
+    pos, mass, params, _ = scenes.dam_break_scene(0.02)
+    n = len(pos)
+    capi = pkg.capi
+    ctx = pkg.Context(n, 0)
+    ctx.set_option(capi.OPT_MATH_MODE, capi.MATH_STRICT)
+    ctx.set_params(params); ctx.upload(pos, None, mass)
+    want_dts = []
+    for _ in range(5):
+        want_dts.append(np.float32(ctx.cfl_timestep())); ctx.step(0.0)
+    want = ctx.download(); want_t = ctx.get_time()[0]; ctx.close()
+
+    nsr = float(params["neighbor_search_radius"])
+    cuts = slab.plan_cuts(slab.axis_cells(pos, 2, nsr), 3, 2)
+    ranks = []
+    for d in range(3):
+        store = slab.GpuStore(pkg, n, 0, params, strict=True)
+        ranks.append(slab.SlabRank(store, d, cuts, 2, 2, n, [-0.2, 0.0, -0.4], [0.2, 0.6, 0.4], 3 * n))
+        ranks[-1].load_initial(pos, None, mass, nsr)
+    got_dts = [np.float32(slab.step_local(ranks, 0.0)) for _ in range(5)]
+    assert [float(x) for x in got_dts] == [float(x) for x in want_dts]
+    merged = slab.gather_by_id([r.store.download() for r in ranks], n)
+    for f in ("pos", "vel", "rho", "acc"):
+        assert_bits(merged[f], want[f], f"adaptive slabs {f}")
+    for r in ranks:
+        assert np.float32(r.store.ctx.get_time()[0]) == np.float32(want_t)
+        r.store.close()
