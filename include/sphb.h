@@ -190,21 +190,14 @@ typedef struct sphb_slab {
 int sphb_set_slab(sphb_ctx* ctx, const sphb_slab* slab);   /* NULL: back to the whole-domain mode */
 /* like sphb_upload, with explicit global ids (slab mode: the particles this context owns) */
 int sphb_upload_ids(sphb_ctx* ctx, size_t n, const float* pos3, const float* vel3, const float* mass, const uint32_t* ids);
-/* Drop all ghosts; move every owned particle whose reference cell left [own_lo, own_hi) into d_out,
- * grouped by destination rank d (cell in [cuts[d], cuts[d+1]), nranks + 1 cuts); counts[d] = records for
- * rank d, counts[my_rank] = particles kept.  Synchronises. */
-int sphb_slab_extract_migrants(sphb_ctx* ctx, const int32_t* cuts, int nranks, int my_rank, void* d_out,
-                               size_t cap_records, uint64_t* counts);
-/* One-round exchange (what slab.py uses): drop all ghosts, then route every owned particle to the rank that
+/* One-round exchange: drop all ghosts, then route every owned particle to the rank that
  * owns its cell now AND, flagged as ghost (id bit 31), to each adjacent rank whose halo layers contain the
  * cell.  d_out receives, for r = 0..nranks-1, [records owned by r (none for r = my_rank)][ghosts for r];
  * counts[2r] / counts[2r+1] are those group sizes (counts[2*my_rank] = particles kept in place).
  * Append what arrives with sphb_slab_append(..., ghost = -1): records keep their own flag.  Synchronises. */
 int sphb_slab_exchange_pack(sphb_ctx* ctx, const int32_t* cuts, int nranks, int my_rank, void* d_out, size_t cap_records,
                             uint64_t* counts);
-/* Copy the owned particles within halo_layers cells of the lower (side 0) / upper (side 1) face into d_out. */
-int sphb_slab_extract_halo(sphb_ctx* ctx, int side, void* d_out, size_t cap_records, uint64_t* count);
-/* Append records (received migrants: ghost = 0, received halo: ghost = 1, flag taken from each record: ghost = -1). */
+/* Append records: ghost = -1 keeps each record's own flag (what the exchange delivers); 0 / 1 force owned / ghost. */
 int sphb_slab_append(sphb_ctx* ctx, const void* d_in, size_t count, int ghost);
 /* Owned particles of this context in arbitrary order: ids[k] with the matching fields (host pointers,
  * any field may be NULL); *count = number written (<= cap). */

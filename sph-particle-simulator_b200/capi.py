@@ -43,7 +43,7 @@ ABI_SYMBOLS = (
     "sphb_upload_strided", "sphb_download", "sphb_download_strided", "sphb_size", "sphb_step", "sphb_run_steps",
     "sphb_get_time", "sphb_set_time", "sphb_cfl_timestep", "sphb_get_stats", "sphb_reset_stats",
     "sphb_diagnostics", "sphb_debug_dump",
-    "sphb_set_slab", "sphb_upload_ids", "sphb_slab_extract_migrants", "sphb_slab_extract_halo", "sphb_slab_append", "sphb_slab_exchange_pack", "sphb_get_cfl_state", "sphb_set_cfl_state",
+    "sphb_set_slab", "sphb_upload_ids", "sphb_slab_append", "sphb_slab_exchange_pack", "sphb_get_cfl_state", "sphb_set_cfl_state",
     "sphb_slab_download",
 )
 
@@ -114,11 +114,9 @@ def load_library() -> C.CDLL:
     L.sphb_debug_dump.argtypes = [vp, vp, vp, vp]
     L.sphb_set_slab.argtypes = [vp, C.POINTER(SphbSlab)]
     L.sphb_upload_ids.argtypes = [vp, sz, vp, vp, vp, vp]
-    L.sphb_slab_extract_migrants.argtypes = [vp, vp, C.c_int, C.c_int, vp, sz, vp]
     L.sphb_get_cfl_state.argtypes = [vp, fp, fp, C.POINTER(C.c_int)]
     L.sphb_set_cfl_state.argtypes = [vp, C.c_float, fp]
     L.sphb_slab_exchange_pack.argtypes = [vp, vp, C.c_int, C.c_int, vp, sz, vp]
-    L.sphb_slab_extract_halo.argtypes = [vp, C.c_int, vp, sz, C.POINTER(C.c_uint64)]
     L.sphb_slab_append.argtypes = [vp, vp, sz, C.c_int]
     L.sphb_slab_download.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, C.POINTER(sz)]
     _lib = L
@@ -286,14 +284,6 @@ class Context:
         ids = np.ascontiguousarray(ids, np.uint32).reshape(n)
         self._ck(self.L.sphb_upload_ids(self.h, n, _ptr(pos), _ptr(vel), _ptr(mass), _ptr(ids)))
 
-    def slab_extract_migrants(self, cuts, my_rank: int, d_out_ptr: int, cap_records: int) -> np.ndarray:
-        cuts = np.ascontiguousarray(cuts, np.int32)
-        nranks = cuts.shape[0] - 1
-        counts = np.zeros(nranks, np.uint64)
-        self._ck(self.L.sphb_slab_extract_migrants(self.h, _ptr(cuts), nranks, int(my_rank), C.c_void_p(d_out_ptr), int(cap_records),
-                                                   _ptr(counts)))
-        return counts
-
     def slab_exchange_pack(self, cuts, my_rank: int, d_out_ptr: int, cap_records: int) -> np.ndarray:
         cuts = np.ascontiguousarray(cuts, np.int32)
         nranks = cuts.shape[0] - 1
@@ -301,11 +291,6 @@ class Context:
         self._ck(self.L.sphb_slab_exchange_pack(self.h, _ptr(cuts), nranks, int(my_rank), C.c_void_p(d_out_ptr), int(cap_records),
                                                 _ptr(counts)))
         return counts
-
-    def slab_extract_halo(self, side: int, d_out_ptr: int, cap_records: int) -> int:
-        n = C.c_uint64()
-        self._ck(self.L.sphb_slab_extract_halo(self.h, int(side), C.c_void_p(d_out_ptr), int(cap_records), C.byref(n)))
-        return n.value
 
     def slab_append(self, d_in_ptr: int, count: int, ghost: bool):
         flag = -1 if ghost is None else (1 if ghost else 0)     # None: records carry their own ghost flag

@@ -861,41 +861,6 @@ int sphb_upload_ids(sphb_ctx* c, size_t n, const float* pos3, const float* vel3,
     return after_upload(c, n);
 }
 
-int sphb_slab_extract_migrants(sphb_ctx* c, const int32_t* cuts, int nranks, int my_rank, void* d_out, size_t cap_records,
-                               uint64_t* counts) {
-    if (!c || !cuts || !counts) return SPHB_E_INVALID;
-    if (!c->slab_on) return fail(c, SPHB_E_INVALID, "sphb_set_slab first");
-    if (nranks < 1 || nranks > kMaxRanks || my_rank < 0 || my_rank >= nranks) return fail(c, SPHB_E_INVALID, "bad rank layout");
-    CU(c, cudaSetDevice(c->device));
-    SlabCuts sc;
-    sc.nranks = nranks;
-    for (int d = 0; d <= nranks; ++d) sc.cuts[d] = cuts[d];
-    const float ref_inv = 1.0f / c->prm.neighbor_search_radius;
-    const int in = c->cur, out = c->cur ^ 1;
-    unsigned int h[kMaxRanks];
-    CU(c, cudaMemsetAsync(c->d_counts, 0, (kMaxRanks + 1) * sizeof(unsigned int), c->stream));
-    c->stats.kernel_launches += launch_slab_count(c->n, c->posm[in], c->velid[in], sc, c->slab.axis, ref_inv, c->d_counts, c->stream);
-    CU(c, cudaMemcpyAsync(h, c->d_counts, nranks * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
-    SlabOffsets off;
-    size_t total = 0;
-    for (int d = 0; d < nranks; ++d) {
-        off.start[d] = (unsigned int)total;
-        if (d != my_rank) total += h[d];
-        counts[d] = h[d];
-    }
-    if (total > cap_records) return fail(c, SPHB_E_CAPACITY, "%zu migrants exceed the exchange buffer (%zu records)", total, cap_records);
-    if (total > 0 && !d_out) return fail(c, SPHB_E_INVALID, "d_out is NULL");
-    CU(c, cudaMemsetAsync(c->d_counts, 0, (kMaxRanks + 1) * sizeof(unsigned int), c->stream));
-    c->stats.kernel_launches += launch_slab_split(c->n, c->posm[in], c->velid[in], sc, c->slab.axis, ref_inv, my_rank, c->posm[out],
-                                                  c->velid[out], static_cast<float4*>(d_out), off, c->d_counts, c->stream);
-    CU(c, cudaGetLastError());
-    c->cur = out;
-    c->n = h[my_rank];
-    c->stepped_since_upload = false;   // device order no longer matches the per-slot outputs of the last step
-    return SPHB_OK;
-}
-
 int sphb_slab_exchange_pack(sphb_ctx* c, const int32_t* cuts, int nranks, int my_rank, void* d_out, size_t cap_records,
                             uint64_t* counts) {
     if (!c || !cuts || !counts) return SPHB_E_INVALID;
@@ -930,25 +895,6 @@ int sphb_slab_exchange_pack(sphb_ctx* c, const int32_t* cuts, int nranks, int my
     c->cur = out;
     c->n = h[2 * my_rank];
     c->stepped_since_upload = false;
-    return SPHB_OK;
-}
-
-int sphb_slab_extract_halo(sphb_ctx* c, int side, void* d_out, size_t cap_records, uint64_t* count) {
-    if (!c || !count) return SPHB_E_INVALID;
-    if (!c->slab_on) return fail(c, SPHB_E_INVALID, "sphb_set_slab first");
-    CU(c, cudaSetDevice(c->device));
-    const int L = c->slab.halo_layers;
-    const int lo = side == 0 ? c->slab.own_lo : c->slab.own_hi - L;
-    const int hi = side == 0 ? c->slab.own_lo + L : c->slab.own_hi;
-    const float ref_inv = 1.0f / c->prm.neighbor_search_radius;
-    unsigned int h = 0;
-    CU(c, cudaMemsetAsync(c->d_counts, 0, sizeof(unsigned int), c->stream));
-    c->stats.kernel_launches += launch_slab_halo(c->n, c->posm[c->cur], c->velid[c->cur], c->slab.axis, ref_inv, lo, hi,
-                                                 static_cast<float4*>(d_out), cap_records, c->d_counts, c->stream);
-    CU(c, cudaMemcpyAsync(&h, c->d_counts, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
-    if (h > cap_records) return fail(c, SPHB_E_CAPACITY, "%u halo particles exceed the exchange buffer (%zu records)", h, cap_records);
-    *count = h;
     return SPHB_OK;
 }
 

@@ -16,7 +16,19 @@ namespace sphb {
 
 namespace {
 
-constexpr int kThreads = 128;
+#ifndef SPHB_PAIR_THREADS
+#define SPHB_PAIR_THREADS 128
+#endif
+#ifndef SPHB_FORCE_UNROLL
+#define SPHB_FORCE_UNROLL 4
+#endif
+#ifndef SPHB_DENSITY_UNROLL
+#define SPHB_DENSITY_UNROLL 4
+#endif
+#define SPHB_STR2(x) #x
+#define SPHB_STR(x) SPHB_STR2(x)
+#define SPHB_UNROLL(n) _Pragma(SPHB_STR(unroll n))
+constexpr int kThreads = SPHB_PAIR_THREADS;
 #ifndef SPHB_FORCE_MINBLOCKS
 #define SPHB_FORCE_MINBLOCKS 1
 #endif
@@ -81,6 +93,7 @@ __global__ void __launch_bounds__(kThreads, SPHB_DENSITY_MINBLOCKS) k_density_si
         const float r2 = a.k.r2;
         const float inv_h = a.k.inv_h, sig6 = a.k.sigma * (1.0f / 6.0f);
         walk_runs(a.grid, a.cell_start, a.walk_radius, cx, cy, cz, [&](uint32_t b, uint32_t e) {
+            SPHB_UNROLL(SPHB_DENSITY_UNROLL)
             for (uint32_t j = b; j < e; ++j) {
                 const float4 pj = __ldg(&a.posm[j]);
                 const float dx = __fsub_rn(pi.x, pj.x), dy = __fsub_rn(pi.y, pj.y), dz = __fsub_rn(pi.z, pj.z);
@@ -131,6 +144,7 @@ __global__ void __launch_bounds__(kThreads, SPHB_FORCE_MINBLOCKS) k_force_simple
     const float r2 = a.k.r2;
     const float4* __restrict__ ja = STRICT ? a.posm : a.fa;
     walk_runs(a.grid, a.cell_start, a.walk_radius, cx, cy, cz, [&](uint32_t b, uint32_t e) {
+        SPHB_UNROLL(SPHB_FORCE_UNROLL)
         for (uint32_t j = b; j < e; ++j) {
             const float4 pj = __ldg(&ja[j]);
             const float rx = __fsub_rn(pi.x, pj.x), ry = __fsub_rn(pi.y, pj.y), rz = __fsub_rn(pi.z, pj.z);

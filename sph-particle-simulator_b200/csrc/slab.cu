@@ -46,65 +46,6 @@ __device__ __forceinline__ unsigned grouped_slot(int key, unsigned int* counters
     return base + __popc(peers & ((1u << lane) - 1u));
 }
 
-__global__ void __launch_bounds__(kThreads) k_slab_count(size_t n, const float4* __restrict__ posm,
-                                                         const float4* __restrict__ velid, SlabCuts sc, int axis,
-                                                         float ref_inv_cell, unsigned int* __restrict__ counts) {
-    const size_t s = (size_t)blockIdx.x * kThreads + threadIdx.x;
-    int key = -1;
-    if (s < n && !(__float_as_uint(velid[s].w) & kGhostBit)) key = dest_of(sc, axis_cell(posm[s], axis, ref_inv_cell));
-    const unsigned peers = __match_any_sync(kFull, key);
-    if (key >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&counts[key], __popc(peers));
-}
-
-// kept particles → (posm_out, velid_out) compacted; migrants → records at rec + 2 * (offsets[dest] + slot)
-__global__ void __launch_bounds__(kThreads) k_slab_split(size_t n, const float4* __restrict__ posm,
-                                                         const float4* __restrict__ velid, SlabCuts sc, int axis,
-                                                         float ref_inv_cell, int me, float4* __restrict__ posm_out,
-                                                         float4* __restrict__ velid_out, float4* __restrict__ rec,
-                                                         SlabOffsets off, unsigned int* __restrict__ cursors) {
-    const size_t s = (size_t)blockIdx.x * kThreads + threadIdx.x;
-    int key = -1;
-    float4 p, v;
-    if (s < n) {
-        v = velid[s];
-        if (!(__float_as_uint(v.w) & kGhostBit)) {
-            p = posm[s];
-            key = dest_of(sc, axis_cell(p, axis, ref_inv_cell));
-        }
-    }
-    const unsigned slot = grouped_slot(key, cursors);
-    if (key < 0) return;
-    if (key == me) {
-        posm_out[slot] = p;
-        velid_out[slot] = v;
-    } else {
-        const size_t r = (size_t)off.start[key] + slot;
-        rec[2 * r] = p;
-        rec[2 * r + 1] = v;
-    }
-}
-
-__global__ void __launch_bounds__(kThreads) k_slab_halo(size_t n, const float4* __restrict__ posm,
-                                                        const float4* __restrict__ velid, int axis, float ref_inv_cell,
-                                                        int lo, int hi, float4* __restrict__ rec, size_t cap,
-                                                        unsigned int* __restrict__ cursor) {
-    const size_t s = (size_t)blockIdx.x * kThreads + threadIdx.x;
-    int key = -1;
-    float4 p, v;
-    if (s < n) {
-        v = velid[s];
-        if (!(__float_as_uint(v.w) & kGhostBit)) {
-            p = posm[s];
-            const int c = axis_cell(p, axis, ref_inv_cell);
-            if (c >= lo && c < hi) key = 0;
-        }
-    }
-    const unsigned slot = grouped_slot(key, cursor);
-    if (key < 0 || slot >= cap) return;
-    rec[2 * (size_t)slot] = p;
-    rec[2 * (size_t)slot + 1] = v;
-}
-
 __global__ void __launch_bounds__(kThreads) k_slab_append(size_t count, const float4* __restrict__ rec, unsigned flag,
                                                           float4* __restrict__ posm, float4* __restrict__ velid) {
     const size_t k = (size_t)blockIdx.x * kThreads + threadIdx.x;
@@ -222,29 +163,6 @@ __global__ void __launch_bounds__(kThreads) k_slab_append_asis(size_t count, con
 }
 
 }  // namespace
-
-int launch_slab_count(size_t n, const float4* posm, const float4* velid, const SlabCuts& sc, int axis, float ref_inv_cell,
-                      unsigned int* counts, cudaStream_t st) {
-    if (n == 0) return 0;
-    k_slab_count<<<blocks_for(n), kThreads, 0, st>>>(n, posm, velid, sc, axis, ref_inv_cell, counts);
-    return 1;
-}
-
-int launch_slab_split(size_t n, const float4* posm, const float4* velid, const SlabCuts& sc, int axis, float ref_inv_cell,
-                      int me, float4* posm_out, float4* velid_out, float4* rec, const SlabOffsets& off, unsigned int* cursors,
-                      cudaStream_t st) {
-    if (n == 0) return 0;
-    k_slab_split<<<blocks_for(n), kThreads, 0, st>>>(n, posm, velid, sc, axis, ref_inv_cell, me, posm_out, velid_out, rec, off,
-                                                      cursors);
-    return 1;
-}
-
-int launch_slab_halo(size_t n, const float4* posm, const float4* velid, int axis, float ref_inv_cell, int lo, int hi,
-                     float4* rec, size_t cap, unsigned int* cursor, cudaStream_t st) {
-    if (n == 0) return 0;
-    k_slab_halo<<<blocks_for(n), kThreads, 0, st>>>(n, posm, velid, axis, ref_inv_cell, lo, hi, rec, cap, cursor);
-    return 1;
-}
 
 int launch_slab_append(size_t count, const float4* rec, bool ghost, float4* posm, float4* velid, cudaStream_t st) {
     if (count == 0) return 0;

@@ -146,15 +146,7 @@ int launch_diagnostics(size_t n, const float4* posm, const float4* velid, const 
 // ---- slab decomposition (slab.cu) ----------------------------------------------------------------
 constexpr int kMaxRanks = 64;
 struct SlabCuts { int nranks; int cuts[kMaxRanks + 1]; };       // rank d owns reference cells [cuts[d], cuts[d+1])
-struct SlabOffsets { unsigned int start[kMaxRanks]; };           // record offset of each destination group
 struct ExchangeOffsets { unsigned int start[2 * kMaxRanks]; };   // one-round exchange: key 2r = owned by r, 2r+1 = ghost for r
-int launch_slab_count(size_t n, const float4* posm, const float4* velid, const SlabCuts& sc, int axis, float ref_inv_cell,
-                      unsigned int* counts, cudaStream_t st);
-int launch_slab_split(size_t n, const float4* posm, const float4* velid, const SlabCuts& sc, int axis, float ref_inv_cell,
-                      int me, float4* posm_out, float4* velid_out, float4* rec, const SlabOffsets& off, unsigned int* cursors,
-                      cudaStream_t st);
-int launch_slab_halo(size_t n, const float4* posm, const float4* velid, int axis, float ref_inv_cell, int lo, int hi,
-                     float4* rec, size_t cap, unsigned int* cursor, cudaStream_t st);
 int launch_exchange_count(size_t n, const float4* posm, const float4* velid, const SlabCuts& sc, int axis, float ref_inv_cell,
                           int layers, unsigned int* counts, cudaStream_t st);
 int launch_exchange_split(size_t n, const float4* posm, const float4* velid, const SlabCuts& sc, int axis, float ref_inv_cell,
