@@ -541,6 +541,7 @@ int sphb_upload_strided(sphb_ctx* c, size_t n, const void* base, size_t stride, 
 
 int sphb_download(sphb_ctx* c, float* pos3, float* vel3, float* rho, float* pressure, float* acc3) {
     if (!c) return SPHB_E_INVALID;
+    if (c->slab_on) return fail(c, SPHB_E_INVALID, "slab mode: ids are global, use sphb_slab_download");
     CU(c, cudaSetDevice(c->device));
     const size_t n = c->n;
     if (n == 0) return SPHB_OK;
@@ -787,6 +788,7 @@ int sphb_diagnostics(sphb_ctx* c, double* sum_density, double* kinetic, float* m
 
 int sphb_debug_dump(sphb_ctx* c, uint64_t* keys, uint32_t* perm, uint32_t* nbr_count) {
     if (!c) return SPHB_E_INVALID;
+    if (c->slab_on) return fail(c, SPHB_E_INVALID, "sphb_debug_dump is not available in slab mode (ids are global)");
     if (!c->debug_capture || !c->refkeys[0]) return fail(c, SPHB_E_INVALID, "enable SPHB_OPT_DEBUG_CAPTURE before the step");
     if (!c->stepped_since_upload) return fail(c, SPHB_E_INVALID, "no step has run since the last upload");
     CU(c, cudaSetDevice(c->device));

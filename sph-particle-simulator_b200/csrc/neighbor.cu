@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(kThreads) k_diagnostics(size_t n, const float4
     unsigned vbits = 0;
     for (size_t s = (size_t)blockIdx.x * kThreads + threadIdx.x; s < n; s += (size_t)gridDim.x * kThreads) {
         float4 v = velid[s];
+        if (__float_as_uint(v.w) & 0x80000000u) continue;   // slab mode: halo copies belong to another context
         float m = posm[s].w;
         float v2 = __fadd_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)), __fmul_rn(v.z, v.z));
         rho += (double)rho_p[s].x;

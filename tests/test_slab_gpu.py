@@ -164,3 +164,32 @@ def test_adaptive_timestep_across_slabs(pkg):
     for r in ranks:
         assert np.float32(r.store.ctx.get_time()[0]) == np.float32(want_t)
         r.store.close()
+
+
+def test_slab_mode_guards_and_diagnostics(pkg):
+    """Dense-by-id getters are refused in slab mode; diagnostics sum owned particles only, so the slabs' sums add
+    up to the single-context values."""
+    from sph_b200 import scenes, slab
+    pos, mass, params, dt = scenes.dam_break_scene(0.02)
+    n = len(pos)
+    ctx = pkg.Context(n, 0); ctx.set_params(params); ctx.upload(pos, None, mass)
+    for _ in range(2):
+        ctx.step(dt)
+    want = ctx.diagnostics(); ctx.close()
+    nsr = float(params["neighbor_search_radius"])
+    cuts = slab.plan_cuts(slab.axis_cells(pos, 2, nsr), 2, 2)
+    ranks = []
+    for d in range(2):
+        store = slab.GpuStore(pkg, n, 0, params)
+        ranks.append(slab.SlabRank(store, d, cuts, 2, 2, n, [-0.2, 0.0, -0.4], [0.2, 0.6, 0.4], 3 * n))
+        ranks[-1].load_initial(pos, None, mass, nsr)
+    for _ in range(2):
+        slab.step_local(ranks, dt)
+    with pytest.raises(pkg.SphbError):
+        ranks[0].store.ctx.download()
+    got = [r.store.ctx.diagnostics() for r in ranks]
+    assert abs(sum(g[0] for g in got) - want[0]) <= 1e-9 * abs(want[0])
+    assert abs(sum(g[1] for g in got) - want[1]) <= 1e-9 * abs(want[1]) + 1e-15
+    assert max(g[2] for g in got) == want[2]
+    for r in ranks:
+        r.store.close()
