@@ -109,8 +109,16 @@ def dist_env():
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the reference's own CPU code on the host cores
 # ------------------------------------------------------------------------------------------------
+def _use_all_host_cores():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU reference must use the box's cores.
+    Has to run before libgomp initialises (i.e. before the oracle library is loaded)."""
+    if "TORCHELASTIC_RUN_ID" in os.environ or os.environ.get("OMP_NUM_THREADS") in (None, "", "1"):
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+
+
 def cpu_reference_run(scene_name: str, steps: int, warmup: int):
     """Time the reference CPU implementation (oracle/_ref fast build; else the C port) on `scene_name`."""
+    _use_all_host_cores()
     po = graft.load_oracle()
     pkg = graft.load_package()
     from sph_b200 import scenes
@@ -349,7 +357,7 @@ def run_ours(args):
 
     # ---- CPU baseline: the reference's own code on this box's host cores, bounded sample ---------
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:      # contract: CPU baseline on rank 0 at N = 1 only
         try:
             r = cpu_reference_run(args.cpu_scene or "dam_break_347k", 3, 1)
             cpu = {"value": round(r["value"], 6), "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
