@@ -74,6 +74,8 @@ struct sphb_ctx {
 
     bool slab_on = false;
     sphb_slab slab{};
+    void* sort_scratch = nullptr;       // one-sweep radix sort: global histograms, look-back status words, tickets
+    int sort_impl = 1;                  // 1 = one-sweep (default), 0 = multi-kernel (SPHB_SORT=legacy)
     unsigned int* d_counts = nullptr;   // 2 * kMaxRanks + 1 counters / cursors
 
     uint64_t step_count = 0;
@@ -267,7 +269,7 @@ void free_all(sphb_ctx* c) {
     cudaFree(c->pp2); cudaFree(c->fa2); cudaFree(c->fb2);
     cudaFree(c->rho_p); cudaFree(c->fa); cudaFree(c->fb); cudaFree(c->acc); cudaFree(c->nbr_count);
     cudaFree(c->sb.counts); cudaFree(c->sb.block_sums); cudaFree(c->cell_start);
-    cudaFree(c->sc); cudaFree(c->d_stage); cudaFree(c->d_box); cudaFree(c->d_counts);
+    cudaFree(c->sc); cudaFree(c->d_stage); cudaFree(c->d_box); cudaFree(c->d_counts); cudaFree(c->sort_scratch);
     if (c->h_sc) cudaFreeHost(c->h_sc);
     if (c->h_bounce) cudaFreeHost(c->h_bounce);
     for (auto& set : c->ev_pool) for (auto& e : set.e) if (e) cudaEventDestroy(e);
@@ -376,6 +378,8 @@ int sphb_create(sphb_ctx** out, size_t capacity, int device) {
     CUC(cudaMallocHost(&c->h_sc, sizeof(DeviceScalars)));
     memset(c->h_sc, 0, sizeof(DeviceScalars));
     CUC(cudaMalloc(&c->d_box, 6 * sizeof(int)));
+    CUC(cudaMalloc(&c->sort_scratch, onesweep_scratch_bytes(cap, 64)));
+    if (const char* e = std::getenv("SPHB_SORT")) c->sort_impl = (strcmp(e, "legacy") == 0) ? 0 : 1;
     CUC(cudaMalloc(&c->d_counts, (2 * kMaxRanks + 1) * sizeof(unsigned int)));
 #undef CUC
     *out = c;
@@ -632,7 +636,8 @@ int sphb_step(sphb_ctx* c, float dt) {
     launches += launch_cell_keys(n, c->posm[in], c->velid[in], g, c->sb.keys[0], c->sb.vals[0],
                                  c->debug_capture ? c->refkeys[in] : nullptr, dbg_ref_sort ? c->dbg_keys[0] : nullptr, gc, c->sc, st);
     int sorted = 0;
-    launches += launch_radix_sort(c->sb, n, g.id_bits + g.cell_bits, &sorted, st);
+    launches += c->sort_impl ? launch_radix_sort_onesweep(c->sb, n, g.id_bits + g.cell_bits, &sorted, c->sort_scratch, st)
+                             : launch_radix_sort(c->sb, n, g.id_bits + g.cell_bits, &sorted, st);
     launches += launch_cell_table(n, c->sb.keys[sorted], g, c->cell_start, c->sb.block_sums, st);
     launches += launch_reorder(n, c->sb.vals[sorted], c->posm[in], c->velid[in], c->debug_capture ? c->refkeys[in] : nullptr,
                                c->posm[outb], c->velid[outb], c->debug_capture ? c->refkeys[outb] : nullptr,
@@ -644,7 +649,8 @@ int sphb_step(sphb_ctx* c, float dt) {
         SortBuffers ds = c->sb;
         ds.keys[0] = c->dbg_keys[0]; ds.keys[1] = c->dbg_keys[1];   // vals buffers are free again after the reorder
         int o = 0;
-        launches += launch_radix_sort(ds, n, gc.id_bits + gc.cell_bits, &o, st);
+        launches += c->sort_impl ? launch_radix_sort_onesweep(ds, n, gc.id_bits + gc.cell_bits, &o, c->sort_scratch, st)
+                                 : launch_radix_sort(ds, n, gc.id_bits + gc.cell_bits, &o, st);
         c->dbg_sorted = o;
         c->dbg_id_bits = gc.id_bits;
     }

@@ -233,6 +233,154 @@ __global__ void __launch_bounds__(kSortThreads) k_radix_scatter(const uint64_t* 
     }
 }
 
+// ---- single-pass-per-digit radix sort ("onesweep": global digit histograms up front, then one scatter kernel
+// per 8-bit digit whose tiles resolve their global offsets by decoupled look-back over a status table) ----------
+//
+// Per pass this reads the pairs once (12 B) and writes them once (12 B) with ONE launch, instead of
+// hist + 3-kernel scan + scatter (32 B, 5 launches) of the multi-kernel path above.  Tiles take their index from
+// an atomic ticket, so a tile only ever waits for tiles that already started — the look-back cannot deadlock.
+constexpr int kMaxPasses = 8;
+constexpr unsigned long long kFlagLocal = 1ull << 62;       // status word: [63:62] flag, [61:0] count
+constexpr unsigned long long kFlagIncl = 2ull << 62;
+constexpr unsigned long long kCountMask = (1ull << 62) - 1ull;
+
+struct PassPlan {
+    int npasses;
+    int shift[kMaxPasses];
+    uint32_t mask[kMaxPasses];
+};
+
+__global__ void __launch_bounds__(kSortThreads) k_onesweep_hist(const uint64_t* __restrict__ keys, size_t n, PassPlan plan,
+                                                                unsigned long long* __restrict__ ghist) {
+    __shared__ uint32_t s_hist[kMaxPasses][256];
+    for (int i = threadIdx.x; i < kMaxPasses * 256; i += kSortThreads) (&s_hist[0][0])[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    for (size_t base = (size_t)blockIdx.x * kSortTile; base < n; base += (size_t)gridDim.x * kSortTile) {
+#pragma unroll
+        for (int k = 0; k < kSortItems; ++k) {
+            const size_t e = base + (size_t)k * kSortThreads + threadIdx.x;
+            const bool valid = e < n;
+            const uint64_t key = valid ? keys[e] : 0ull;
+            for (int p = 0; p < plan.npasses; ++p) {
+                const uint32_t digit = valid ? (uint32_t)(key >> plan.shift[p]) & plan.mask[p] : 0xFFFFFFFFu;
+                const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+                if (valid && lane == __ffs(peers) - 1) atomicAdd(&s_hist[p][digit], __popc(peers));
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < plan.npasses * 256; i += kSortThreads) {
+        const uint32_t v = (&s_hist[0][0])[i];
+        if (v) atomicAdd(&ghist[i], (unsigned long long)v);
+    }
+}
+
+__global__ void __launch_bounds__(kSortThreads) k_onesweep_pass(const uint64_t* __restrict__ keys_in,
+                                                                const uint32_t* __restrict__ vals_in,
+                                                                uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                                                                const unsigned long long* __restrict__ ghist,
+                                                                volatile unsigned long long* status, unsigned int* ticket,
+                                                                size_t n, int shift, uint32_t mask) {
+    __shared__ uint64_t s_keys[kSortTile];
+    __shared__ uint32_t s_vals[kSortTile];
+    __shared__ uint32_t s_warp_cnt[kSortWarps][256];
+    __shared__ uint32_t s_tile_off[256];
+    __shared__ unsigned long long s_gbase[256];
+    __shared__ uint32_t s_scan[kSortWarps];
+    __shared__ unsigned int s_tile;
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int i = tid; i < kSortWarps * 256; i += kSortThreads) (&s_warp_cnt[0][0])[i] = 0;
+    __syncthreads();
+    const unsigned int tile = s_tile;
+    const size_t tile_base = (size_t)tile * kSortTile;
+
+    uint64_t key[kSortItems];
+    uint32_t val[kSortItems], lrank[kSortItems], dig[kSortItems];
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        const size_t e = tile_base + (size_t)w * (32 * kSortItems) + (size_t)k * 32 + lane;
+        const bool valid = e < n;
+        key[k] = valid ? keys_in[e] : ~0ull;
+        val[k] = valid ? (vals_in ? vals_in[e] : (uint32_t)e) : 0u;   // first pass: the payload is the slot itself
+        const uint32_t digit = valid ? (uint32_t)(key[k] >> shift) & mask : 255u;
+        dig[k] = digit;
+        const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+        const uint32_t below = __popc(peers & ((1u << lane) - 1u));
+        const int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (lane == leader) {
+            old = s_warp_cnt[w][digit];
+            s_warp_cnt[w][digit] = old + __popc(peers);
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        lrank[k] = old + below;
+        __syncwarp();
+    }
+    __syncthreads();
+
+    const size_t remaining = n - tile_base;
+    const uint32_t nvalid = remaining < (size_t)kSortTile ? (uint32_t)remaining : (uint32_t)kSortTile;
+    {   // thread d owns digit d
+        const int d = tid;
+        uint32_t run = 0;
+#pragma unroll
+        for (int ww = 0; ww < kSortWarps; ++ww) {
+            const uint32_t t = s_warp_cnt[ww][d];
+            s_warp_cnt[ww][d] = run;
+            run += t;
+        }
+        // padding of the last tile was ranked into digit 255: it must not be published
+        const uint32_t pad = (d == 255) ? (uint32_t)kSortTile - nvalid : 0u;
+        const unsigned long long cnt = run - pad;
+        volatile unsigned long long* my = status + (size_t)tile * 256 + d;
+        if (tile == 0) *my = kFlagIncl | cnt; else *my = kFlagLocal | cnt;
+        // exclusive prefix of this digit over all earlier tiles: decoupled look-back
+        unsigned long long excl = 0;
+        if (tile > 0) {
+            long long t = (long long)tile - 1;
+            for (;;) {
+                unsigned long long v;
+                do { v = status[(size_t)t * 256 + d]; } while ((v >> 62) == 0ull);
+                excl += v & kCountMask;
+                if ((v >> 62) == 2ull || t == 0) break;
+                --t;
+            }
+            *my = kFlagIncl | (excl + cnt);
+        }
+        uint32_t total;
+        const uint32_t ex = block_exclusive<false, kSortThreads>(run, s_scan, &total);
+        s_tile_off[d] = ex;
+        __syncthreads();   // s_scan is reused by the second block scan
+        // global base of digit d = number of keys with a smaller digit (exclusive scan of the global histogram;
+        // every prefix is <= n < 2^31) + keys of this digit in earlier tiles
+        const uint32_t dbase = block_exclusive<false, kSortThreads>((uint32_t)ghist[d], s_scan, &total);
+        s_gbase[d] = (unsigned long long)dbase + excl - ex;
+    }
+    __syncthreads();
+
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        const uint32_t pos = s_tile_off[dig[k]] + s_warp_cnt[w][dig[k]] + lrank[k];
+        s_keys[pos] = key[k];
+        s_vals[pos] = val[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        const uint32_t pos = (uint32_t)k * kSortThreads + tid;
+        if (pos < nvalid) {
+            const uint64_t kk = s_keys[pos];
+            const uint32_t d = (uint32_t)(kk >> shift) & mask;
+            const size_t g = (size_t)(s_gbase[d] + pos);
+            keys_out[g] = kk;
+            vals_out[g] = s_vals[pos];
+        }
+    }
+}
+
 }  // namespace
 
 int launch_scan_sum_exclusive(uint32_t* data, size_t n, uint32_t* block_sums, cudaStream_t st) {
@@ -255,6 +403,45 @@ int launch_radix_sort(const SortBuffers& sb, size_t n, int bits, int* out_buf, c
         k_radix_scatter<<<ntiles, kSortThreads, 0, st>>>(sb.keys[cur], sb.vals[cur], sb.keys[cur ^ 1], sb.vals[cur ^ 1],
                                                         sb.counts, n, shift, mask, ntiles);
         launches += 1;
+        cur ^= 1;
+    }
+    *out_buf = cur;
+    return launches;
+}
+
+// One-sweep variant.  scratch: (npasses * 256 + npasses * ntiles * 256) u64 + npasses u32 tickets, zeroed here.
+size_t onesweep_scratch_bytes(size_t n_max, int bits_max) {
+    const size_t ntiles = (n_max + kSortTile - 1) / kSortTile;
+    const size_t passes = (size_t)((bits_max + 7) / 8);
+    return (passes * 256 + passes * ntiles * 256) * sizeof(unsigned long long) + kMaxPasses * sizeof(unsigned int) + 64;
+}
+
+int launch_radix_sort_onesweep(const SortBuffers& sb, size_t n, int bits, int* out_buf, void* scratch, cudaStream_t st) {
+    *out_buf = 0;
+    if (n == 0) return 0;
+    PassPlan plan;
+    plan.npasses = (bits + 7) / 8;
+    if (plan.npasses > kMaxPasses) plan.npasses = kMaxPasses;
+    for (int p = 0; p < plan.npasses; ++p) {
+        const int nb = bits - 8 * p < 8 ? bits - 8 * p : 8;
+        plan.shift[p] = 8 * p;
+        plan.mask[p] = (1u << nb) - 1u;
+    }
+    const uint32_t ntiles = (uint32_t)((n + kSortTile - 1) / kSortTile);
+    unsigned long long* ghist = static_cast<unsigned long long*>(scratch);
+    unsigned long long* status = ghist + (size_t)plan.npasses * 256;
+    unsigned int* tickets = reinterpret_cast<unsigned int*>(status + (size_t)plan.npasses * ntiles * 256);
+    const size_t zero_bytes = ((size_t)plan.npasses * 256 + (size_t)plan.npasses * ntiles * 256) * sizeof(unsigned long long) +
+                              kMaxPasses * sizeof(unsigned int);
+    cudaMemsetAsync(scratch, 0, zero_bytes, st);
+    unsigned hb = ntiles < (unsigned)(kSMs * 4) ? ntiles : (unsigned)(kSMs * 4);
+    k_onesweep_hist<<<hb, kSortThreads, 0, st>>>(sb.keys[0], n, plan, ghist);
+    int cur = 0, launches = 1;
+    for (int p = 0; p < plan.npasses; ++p) {
+        k_onesweep_pass<<<ntiles, kSortThreads, 0, st>>>(sb.keys[cur], p == 0 ? nullptr : sb.vals[cur], sb.keys[cur ^ 1], sb.vals[cur ^ 1],
+                                                        ghist + (size_t)p * 256, status + (size_t)p * ntiles * 256, tickets + p, n,
+                                                        plan.shift[p], plan.mask[p]);
+        ++launches;
         cur ^= 1;
     }
     *out_buf = cur;

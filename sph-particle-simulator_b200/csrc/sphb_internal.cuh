@@ -84,6 +84,10 @@ constexpr int kScanTile = 4096;   // elements per CTA of the device-wide scan
 // LSD radix sort of (key, val) pairs by the low `bits` bits of key, 8 bits per pass, stable.
 // Input in buffers [0]; returns the index (0/1) of the buffer pair holding the result in *out_buf.
 int launch_radix_sort(const SortBuffers& sb, size_t n, int bits, int* out_buf, cudaStream_t st);
+// Same contract, one scatter kernel per digit with decoupled look-back; the first pass generates vals = slot itself
+// (the caller need not fill vals[0]).  scratch must hold onesweep_scratch_bytes(n_max, bits_max).
+size_t onesweep_scratch_bytes(size_t n_max, int bits_max);
+int launch_radix_sort_onesweep(const SortBuffers& sb, size_t n, int bits, int* out_buf, void* scratch, cudaStream_t st);
 
 // out[i] = sum(in[0..i-1]) (exclusive) or out[i] = max(in[0..i]) (inclusive); in == out allowed.
 int launch_scan_sum_exclusive(uint32_t* data, size_t n, uint32_t* block_sums, cudaStream_t st);
