@@ -22,7 +22,7 @@ __device__ __forceinline__ void block_max_v2(float v2, DeviceScalars* sc) {
     // std::max(max_velocity, velocity) drops it (sph_engine.cpp:318).
     unsigned bits = (v2 == v2) ? __float_as_uint(v2) : 0u;
     bits = __reduce_max_sync(0xffffffffu, bits);
-    if ((threadIdx.x & 31) == 0 && bits != 0u) atomicMax(&sc->max_v2_bits, bits);
+    if ((threadIdx.x & 31) == 0 && bits > *(volatile unsigned int*)&sc->max_v2_bits) atomicMax(&sc->max_v2_bits, bits);
 }
 
 __global__ void __launch_bounds__(kThreads) k_pack_upload(size_t n, const float* __restrict__ pos3,

@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(kThreads, SPHB_DENSITY_MINBLOCKS) k_density_si
         if (a.nbr_count) a.nbr_count[i] = count;
     }
     count = __reduce_max_sync(0xffffffffu, count);
-    if ((threadIdx.x & 31) == 0) atomicMax(&a.sc->max_neighbors, count);
+    if ((threadIdx.x & 31) == 0 && count > *(volatile unsigned int*)&a.sc->max_neighbors) atomicMax(&a.sc->max_neighbors, count);
 }
 
 template <bool STRICT>
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(kThreads) k_density_packed(PairArgs a) {
         if (a.nbr_count) a.nbr_count[i] = count;
     }
     count = __reduce_max_sync(0xffffffffu, count);
-    if ((threadIdx.x & 31) == 0) atomicMax(&a.sc->max_neighbors, count);
+    if ((threadIdx.x & 31) == 0 && count > *(volatile unsigned int*)&a.sc->max_neighbors) atomicMax(&a.sc->max_neighbors, count);
 }
 
 template <int R_UNUSED = 0>
