@@ -186,3 +186,17 @@ def test_reference_benchmark_driver_runs_on_the_gpu_engine(tmp_path):
     assert csv[0].startswith("particles,avg_fps,min_fps,max_fps,avg_ms_frame,neighbor_search_pct") and len(csv) == 3
     fps = float(csv[2].split(",")[1])
     assert fps > 100.0, f"5000-particle config ran at {fps} FPS"
+
+
+@pytest.mark.gpu
+def test_headless_dam_break_example(tmp_path):
+    """examples/dam_break_headless.py: the reference example's parameters, loop and CSV columns on the GPU engine
+    (BASELINE.json configs[0]: capacity 20 000 → 20 000 wall particles, 0 fluid)."""
+    import subprocess
+    out = subprocess.run([sys.executable, str(ROOT / "examples" / "dam_break_headless.py"), "10000", "0.012", str(tmp_path / "d.csv")],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+    assert "Simulation initialized with 20000 particles" in out.stdout
+    rows = (tmp_path / "d.csv").read_text().splitlines()
+    assert rows[0] == "time,particles,mass_error,energy,total_energy,avg_density,max_velocity" and len(rows) >= 2
+    assert rows[1].split(",")[1] == "20000"
