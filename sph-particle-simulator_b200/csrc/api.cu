@@ -71,6 +71,7 @@ struct sphb_ctx {
     bool box_pending = false;  // box must be read back from the device (after an upload)
     int* d_box = nullptr;      // 6 ordered-int encoded floats
     bool stepped_since_upload = false;
+    bool box_tracking = false;   // the last step's integrate kernel reduced the particle bounding box into d_box
 
     bool slab_on = false;
     sphb_slab slab{};
@@ -474,6 +475,7 @@ int sphb_size(const sphb_ctx* c, size_t* n) {
 }
 
 static int after_upload(sphb_ctx* c, size_t n) {
+    c->box_tracking = false;
     c->n = n;
     c->cur = 0;
     c->box_pending = n > 0;
@@ -605,7 +607,7 @@ int sphb_step(sphb_ctx* c, float dt) {
     CU(c, cudaSetDevice(c->device));
     int rc = fetch_box(c);
     if (rc) return rc;
-    if (c->slab_on) {
+    if (c->slab_on && !c->box_tracking) {
         for (int a = 0; a < 3; ++a) { c->box_min[a] = c->slab.box_min[a]; c->box_max[a] = c->slab.box_max[a]; }
     }
     // strict mode keeps the reference's cell size so the device layout IS the reference order; fast mode
@@ -686,11 +688,18 @@ int sphb_step(sphb_ctx* c, float dt) {
     // particle count (sparse scene, e.g. a drop in a big box) the integrate kernel also reduces the bounding box
     // of the new positions and the next step reads it back (one small synchronising copy) to build a tight table.
     bool track_box = false;
-    if (!c->slab_on) {
+    {
         const float bmin[3] = {c->prm.xmin, c->prm.ymin, c->prm.zmin}, bmax[3] = {c->prm.xmax, c->prm.ymax, c->prm.zmax};
         double cells = 1.0;
-        for (int a = 0; a < 3; ++a) cells *= floor((double)(bmax[a] - bmin[a]) * (double)g.inv_cell) + 1.0;
-        track_box = cells > 8.0 * (double)n;
+        for (int a = 0; a < 3; ++a) {
+            double ext = floor((double)(bmax[a] - bmin[a]) * (double)g.inv_cell) + 1.0;
+            if (c->slab_on && a == c->slab.axis) {   // only the slab and its ghost layers can be populated on this axis
+                const double slab_ext = (double)refine * ((double)c->slab.own_hi - (double)c->slab.own_lo + 2.0 * c->slab.halo_layers);
+                if (slab_ext < ext) ext = slab_ext;
+            }
+            cells *= ext;
+        }
+        track_box = cells > 8.0 * (double)n;   // slab mode: sphb_slab_append adds the boxes of arriving records
     }
     if (track_box) {
         const int init[6] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, (int)0x80000000, (int)0x80000000, (int)0x80000000};
@@ -700,9 +709,10 @@ int sphb_step(sphb_ctx* c, float dt) {
     if (timing) cudaEventRecord(ev[4], st);
     CU(c, cudaGetLastError());
 
+    c->box_tracking = track_box;
     if (track_box) {
         c->box_pending = true;
-    } else {
+    } else if (!c->slab_on) {
         c->box_min[0] = c->prm.xmin; c->box_max[0] = c->prm.xmax;
         c->box_min[1] = c->prm.ymin; c->box_max[1] = c->prm.ymax;
         c->box_min[2] = c->prm.zmin; c->box_max[2] = c->prm.zmax;
@@ -918,6 +928,7 @@ int sphb_slab_append(sphb_ctx* c, const void* d_in, size_t count, int ghost) {
     else
         c->stats.kernel_launches += launch_slab_append(count, static_cast<const float4*>(d_in), ghost != 0, c->posm[c->cur] + c->n,
                                                        c->velid[c->cur] + c->n, c->stream);
+    if (c->box_tracking) c->stats.kernel_launches += launch_bbox(count, c->posm[c->cur] + c->n, c->d_box, c->stream);
     CU(c, cudaGetLastError());
     c->n += count;
     c->stepped_since_upload = false;
