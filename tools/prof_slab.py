@@ -15,6 +15,7 @@ r.load_initial(pos, None, mass, nsr)
 dev = store.device
 def sync(): torch.cuda.synchronize()
 T = {k: 0.0 for k in ("pack", "gather", "a2a", "append", "step")}
+store.ctx.set_option(pkg.capi.OPT_STAGE_TIMING, 1)
 for it in range(13):
     sync(); dist.barrier(); t0 = time.perf_counter()
     counts = r.pack(); sync(); t1 = time.perf_counter()
@@ -27,8 +28,12 @@ for it in range(13):
     sync(); t3 = time.perf_counter()
     store.append(r.recv, n_in, None); sync(); t4 = time.perf_counter()
     store.step(dt); sync(); t5 = time.perf_counter()
+    if it == 2:
+        store.ctx.reset_stats()
     if it >= 3:
         for k, v in zip(T, (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)): T[k] += v
 if rank in (0, world // 2):
-    print(rank, {k: round(1e3 * v / 10, 3) for k, v in T.items()}, "n_in", n_in, "size", store.size, flush=True)
+    st = store.ctx.stats()
+    print(rank, {k: round(1e3 * v / 10, 3) for k, v in T.items()}, "n_in", n_in, "size", store.size,
+          {k: round(1e3 * st[k] / st["steps"], 3) for k in ("neighbor_search_time", "density_computation_time", "force_computation_time", "integration_time")}, flush=True)
 dist.destroy_process_group()
