@@ -86,14 +86,21 @@ enum {
     SPHB_OPT_STAGE_TIMING = 3,
     /* 1 = keep per-particle cell keys and neighbour counts of every step for sphb_debug_dump (default 0) */
     SPHB_OPT_DEBUG_CAPTURE = 4,
-    /* pair kernel variant: 0 = scalar per-thread walk (default), 1 = packed-f32x2 walk (fast mode only;
-     * measured slower on B200 — kept selectable) */
+    /* pair kernel variant (fast mode; strict always runs 0): 2 = the density pass hands the accepted-neighbour
+     * sets to the force pass as per-column bitmasks, so the radius test runs once per step (default);
+     * 0 = tested per-thread walk in both passes; 1 = packed-f32x2 walk (measured slower on B200 — kept
+     * selectable).  All variants find identical neighbour sets. */
     SPHB_OPT_PAIR_KERNEL = 5,
     /* fast mode only: the device sorts on an internal grid of cell size neighbor_search_radius / f and
      * walks (2 f + 1)^3 cells, which cuts the candidates per particle (27 r^3 -> 15.6 r^3 at f = 2).  The
      * reference's 63-bit keys, its permutation and the neighbour sets are unaffected (1..4, default 2;
      * strict mode always uses 1 so that its layout and summation order are the reference's). */
-    SPHB_OPT_GRID_REFINE = 6
+    SPHB_OPT_GRID_REFINE = 6,
+    /* fast mode, pair kernel 2: physical axis (0 = x, 1 = y, 2 = z) that is most significant in the device's
+     * cell order (default 0).  In slab mode the slab axis is used, so that ghost layers are contiguous in the
+     * sorted arrays.  Only the fp32 summation ORDER depends on it (results agree within the fast-mode
+     * tolerances; identical layouts give bit-identical results). */
+    SPHB_OPT_LAYOUT_MAJOR = 7
 };
 
 /* ---- lifetime ---------------------------------------------------------------------------------

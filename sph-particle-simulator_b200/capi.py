@@ -33,6 +33,7 @@ OPT_STAGE_TIMING = 3
 OPT_DEBUG_CAPTURE = 4
 OPT_PAIR_KERNEL = 5
 OPT_GRID_REFINE = 6
+OPT_LAYOUT_MAJOR = 7
 MATH_STRICT = 0
 MATH_FAST = 1
 

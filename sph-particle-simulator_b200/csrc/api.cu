@@ -38,7 +38,8 @@ struct sphb_ctx {
     int walk_radius = 1;
     int stage_timing = 0;
     int debug_capture = 0;
-    int pair_kernel = 0;
+    int pair_kernel = 2;     // fast mode: 2 = bitmask hand-off density -> force (default), 0 = tested walk twice, 1 = packed f32x2
+    int layout_major = 0;    // fast-mode layout: physical axis that is most significant in the cell order (slab mode: the slab axis)
     int grid_refine = 2;     // internal cell = neighbor_search_radius / grid_refine (fast mode; strict always 1)
 
     float4* posm[2] = {nullptr, nullptr};
@@ -51,6 +52,8 @@ struct sphb_ctx {
     float4* fa2 = nullptr;
     float4* fb2 = nullptr;
     float4* acc = nullptr;
+    uint2* masks = nullptr;      // variant 2: (kMaskCols + 1) rows of mask_stride accepted-neighbour masks
+    size_t mask_stride = 0;
     uint32_t* nbr_count = nullptr;
     uint64_t* refkeys[2] = {nullptr, nullptr};
     uint64_t* dbg_keys[2] = {nullptr, nullptr};   // reference-order composite keys (debug capture with a refined grid)
@@ -175,7 +178,9 @@ int host_cell(float p, float inv_cell) {
     return (int)f;
 }
 
-int make_grid(sphb_ctx* c, GridDesc* g, int refine) {
+// layout_major < 0: the reference layout (x, y, z key order, masked-key ranks).  layout_major = a: fast-mode layout
+// with physical axis a most significant and monotone ranks (see GridDesc).
+int make_grid(sphb_ctx* c, GridDesc* g, int refine, int layout_major = -1) {
     const float cell = c->prm.neighbor_search_radius;
     if (!(cell > 0.0f)) return fail(c, SPHB_E_INVALID, "neighbor_search_radius must be > 0 (got %g)", (double)cell);
     g->ref_inv_cell = 1.0f / cell;  // SpatialHash::set_cell_size, reference spatial_hash.h:63-66
@@ -204,6 +209,17 @@ int make_grid(sphb_ctx* c, GridDesc* g, int refine) {
         if (ncells > kMaxCells)
             return fail(c, SPHB_E_GRID, "dense cell table would need more than %llu cells (box / neighbor_search_radius too large)",
                         (unsigned long long)kMaxCells);
+    }
+    g->monotone = layout_major >= 0 ? 1 : 0;
+    g->perm[0] = 0; g->perm[1] = 1; g->perm[2] = 2;
+    if (layout_major == 1) { g->perm[0] = 1; g->perm[1] = 0; g->perm[2] = 2; }        // (y, x, z)
+    else if (layout_major == 2) { g->perm[0] = 2; g->perm[1] = 0; g->perm[2] = 1; }   // (z, x, y)
+    if (g->perm[0] != 0) {   // the loop above filled the fields by physical axis: bring them into key order
+        GridDesc t = *g;
+        for (int k = 0; k < 3; ++k) {
+            const int a = g->perm[k];
+            g->lo[k] = t.lo[a]; g->hi[k] = t.hi[a]; g->ext[k] = t.ext[a]; g->pos_lo[k] = t.pos_lo[a]; g->npos[k] = t.npos[a];
+        }
     }
     g->ncells = (uint32_t)ncells;
     g->id_bits = bits_for(c->slab_on ? (c->slab.id_space > 1 ? c->slab.id_space : 2) : (c->capacity > 1 ? c->capacity : 2));
@@ -267,7 +283,7 @@ void free_all(sphb_ctx* c) {
         cudaFree(c->posm[i]); cudaFree(c->velid[i]); cudaFree(c->refkeys[i]); cudaFree(c->dbg_keys[i]);
         cudaFree(c->sb.keys[i]); cudaFree(c->sb.vals[i]);
     }
-    cudaFree(c->pp2); cudaFree(c->fa2); cudaFree(c->fb2);
+    cudaFree(c->pp2); cudaFree(c->fa2); cudaFree(c->fb2); cudaFree(c->masks);
     cudaFree(c->rho_p); cudaFree(c->fa); cudaFree(c->fb); cudaFree(c->acc); cudaFree(c->nbr_count);
     cudaFree(c->sb.counts); cudaFree(c->sb.block_sums); cudaFree(c->cell_start);
     cudaFree(c->sc); cudaFree(c->d_stage); cudaFree(c->d_box); cudaFree(c->d_counts); cudaFree(c->sort_scratch);
@@ -415,12 +431,16 @@ int sphb_set_option(sphb_ctx* c, int option, int64_t value) {
             if (c->debug_capture) { cudaSetDevice(c->device); return ensure_debug(c); }
             return SPHB_OK;
         case SPHB_OPT_PAIR_KERNEL:
-            if (value < 0 || value > 1) return fail(c, SPHB_E_INVALID, "pair kernel variant must be 0 or 1");
+            if (value < 0 || value > 2) return fail(c, SPHB_E_INVALID, "pair kernel variant must be 0, 1 or 2");
             c->pair_kernel = (int)value;
             return SPHB_OK;
         case SPHB_OPT_GRID_REFINE:
             if (value < 1 || value > 4) return fail(c, SPHB_E_INVALID, "grid refine must be 1..4");
             c->grid_refine = (int)value;
+            return SPHB_OK;
+        case SPHB_OPT_LAYOUT_MAJOR:
+            if (value < 0 || value > 2) return fail(c, SPHB_E_INVALID, "layout major axis must be 0..2");
+            c->layout_major = (int)value;
             return SPHB_OK;
         default:
             return fail(c, SPHB_E_INVALID, "unknown option %d", option);
@@ -436,6 +456,7 @@ int sphb_get_option(const sphb_ctx* c, int option, int64_t* value) {
         case SPHB_OPT_DEBUG_CAPTURE: *value = c->debug_capture; return SPHB_OK;
         case SPHB_OPT_PAIR_KERNEL: *value = c->pair_kernel; return SPHB_OK;
         case SPHB_OPT_GRID_REFINE: *value = c->grid_refine; return SPHB_OK;
+        case SPHB_OPT_LAYOUT_MAJOR: *value = c->layout_major; return SPHB_OK;
         default: return SPHB_E_INVALID;
     }
 }
@@ -613,15 +634,28 @@ int sphb_step(sphb_ctx* c, float dt) {
     // strict mode keeps the reference's cell size so the device layout IS the reference order; fast mode
     // may sort on a finer grid (fewer candidates per particle) and walk refine x as many cells per axis
     int refine = (c->math_mode == 0) ? 1 : c->grid_refine;
+    // pair-kernel variant 2 (bitmask hand-off) needs the 5 x 5 column walk and uses the fast-mode layout
+    int variant = (c->math_mode == 0) ? 0 : c->pair_kernel;
+    if (variant == 2 && c->walk_radius * refine != kMaskRadius) variant = 0;
+    int layout = (variant == 2) ? (c->slab_on ? c->slab.axis : c->layout_major) : -1;
     GridDesc g, gc;
-    rc = make_grid(c, &g, refine);
-    if (rc == SPHB_E_GRID && refine > 1) { refine = 1; rc = make_grid(c, &g, 1); }   // refined table too large: coarse grid
+    rc = make_grid(c, &g, refine, layout);
+    if (rc == SPHB_E_GRID && refine > 1) {   // refined table too large: coarse grid, tested walk
+        refine = 1; layout = -1;
+        if (variant == 2) variant = 0;
+        rc = make_grid(c, &g, 1);
+    }
     if (rc) return rc;
     gc = g;
-    const bool dbg_ref_sort = c->debug_capture && refine > 1 && !c->slab_on;
+    const bool dbg_ref_sort = c->debug_capture && (refine > 1 || layout >= 0) && !c->slab_on;
     if (dbg_ref_sort) { rc = make_grid(c, &gc, 1); if (rc) return rc; }
     rc = ensure_cell_table(c, g);
     if (rc) return rc;
+    if (variant == 2 && !c->masks) {
+        const size_t cap = c->capacity ? c->capacity : 1;
+        c->mask_stride = (cap + 31) & ~(size_t)31;
+        CU(c, cudaMalloc(&c->masks, (size_t)(kMaskCols + 1) * c->mask_stride * sizeof(uint2)));
+    }
     if (c->debug_capture) { rc = ensure_debug(c); if (rc) return rc; }
 
     cudaStream_t st = c->stream;
@@ -643,7 +677,7 @@ int sphb_step(sphb_ctx* c, float dt) {
     launches += launch_cell_table(n, c->sb.keys[sorted], g, c->cell_start, c->sb.block_sums, st);
     launches += launch_reorder(n, c->sb.vals[sorted], c->posm[in], c->velid[in], c->debug_capture ? c->refkeys[in] : nullptr,
                                c->posm[outb], c->velid[outb], c->debug_capture ? c->refkeys[outb] : nullptr,
-                               (c->pair_kernel == 1 && c->math_mode == 1) ? c->pp2 : nullptr, st);
+                               variant == 1 ? c->pp2 : nullptr, st);
     c->cur = outb;
     if (timing) cudaEventRecord(ev[1], st);
     c->dbg_sorted = -1;
@@ -669,13 +703,15 @@ int sphb_step(sphb_ctx* c, float dt) {
     pa.fa2 = c->fa2;
     pa.fb2 = c->fb2;
     pa.acc = c->acc;
+    pa.masks = c->masks;
+    pa.mask_stride = c->mask_stride;
     pa.nbr_count = c->debug_capture ? c->nbr_count : nullptr;
     pa.sc = c->sc;
     pa.grid = g;
     pa.k = make_pair_consts(c->prm);
     pa.walk_radius = c->walk_radius * refine;
     pa.strict = c->math_mode == 0;
-    pa.variant = c->pair_kernel;
+    pa.variant = variant;
     pa.slab_axis = c->slab_on ? c->slab.axis : -1;
     pa.rho_lo = c->slab_on ? c->slab.own_lo - 1 : 0;
     pa.rho_hi = c->slab_on ? c->slab.own_hi + 1 : 0;

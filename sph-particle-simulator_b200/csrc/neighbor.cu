@@ -46,13 +46,14 @@ __global__ void __launch_bounds__(kThreads) k_pack_upload(size_t n, const float*
 }
 
 __device__ __forceinline__ uint32_t dense_cell(const GridDesc& g, const float4& p, bool* outside) {
-    int c[3] = {cell_coord(p.x, g.inv_cell), cell_coord(p.y, g.inv_cell), cell_coord(p.z, g.inv_cell)};
     uint32_t cell = 0;
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        if (c[a] < g.lo[a]) { c[a] = g.lo[a]; *outside = true; }
-        if (c[a] > g.hi[a]) { c[a] = g.hi[a]; *outside = true; }
-        cell = cell * (uint32_t)g.ext[a] + (uint32_t)grid_rank(g, a, c[a]);
+    for (int k = 0; k < 3; ++k) {
+        const int a = g.perm[k];
+        int c = cell_coord(a == 0 ? p.x : (a == 1 ? p.y : p.z), g.inv_cell);
+        if (c < g.lo[k]) { c = g.lo[k]; *outside = true; }
+        if (c > g.hi[k]) { c = g.hi[k]; *outside = true; }
+        cell = cell * (uint32_t)g.ext[k] + (uint32_t)grid_rank(g, k, c);
     }
     return cell;
 }

@@ -36,19 +36,6 @@ constexpr int kThreads = SPHB_PAIR_THREADS;
 #define SPHB_DENSITY_MINBLOCKS 1
 #endif
 
-__device__ __forceinline__ int cell_coord(float p, float inv_cell) { return __float2int_rd(__fmul_rn(p, inv_cell)); }
-
-__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
-
-// slab mode: is the density of this particle needed here (owned or first halo layer)?
-__device__ __forceinline__ bool wants_density(const PairArgs& a, const float4& p) {
-    if (a.slab_axis < 0) return true;
-    const float c = a.slab_axis == 0 ? p.x : (a.slab_axis == 1 ? p.y : p.z);
-    const int cell = cell_coord(c, a.grid.ref_inv_cell);
-    return cell >= a.rho_lo && cell < a.rho_hi;
-}
-__device__ __forceinline__ bool is_ghost(const float4& velid) { return (__float_as_uint(velid.w) & 0x80000000u) != 0u; }
-
 // Calls body(begin, end) for every contiguous slot run of the neighbourhood of cell (cx, cy, cz),
 // in the reference's visiting order.
 template <typename Body>
@@ -327,6 +314,7 @@ __global__ void __launch_bounds__(kThreads) k_force_packed(PairArgs a) {
 
 int launch_density(const PairArgs& a, cudaStream_t st) {
     if (a.n == 0) return 0;
+    if (a.variant == 2 && !a.strict) return launch_density_mask(a, st);
     const unsigned nb = (unsigned)((a.n + kThreads - 1) / kThreads);
     if (a.variant == 0) {
         if (a.strict) k_density_simple<true><<<nb, kThreads, 0, st>>>(a);
@@ -340,6 +328,7 @@ int launch_density(const PairArgs& a, cudaStream_t st) {
 
 int launch_force(const PairArgs& a, cudaStream_t st) {
     if (a.n == 0) return 0;
+    if (a.variant == 2 && !a.strict) return launch_force_mask(a, st);
     const unsigned nb = (unsigned)((a.n + kThreads - 1) / kThreads);
     if (a.variant == 0) {
         if (a.strict) k_force_simple<true><<<nb, kThreads, 0, st>>>(a);

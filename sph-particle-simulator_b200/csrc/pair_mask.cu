@@ -1,0 +1,210 @@
+// Pair kernels, variant 2 (fast math, default): the density pass hands its accepted-neighbour sets to the
+// force pass as per-column bitmasks, so the radius test runs ONCE per step instead of twice.
+//
+// Why: both pair passes are instruction-issue bound (profiles/: ~86 % / 73 % issue-active, <1 % DRAM), and
+// ~1 000 candidates are tested per particle and pass to find ~270 neighbours.  In the one-thread-per-particle
+// walk the test costs ~12 warp-instructions per candidate and the divergent "accepted" branch is entered
+// whenever ANY lane accepts.  Here
+//   * k_density_mask walks the (2R+1)^2 cell columns (each ONE contiguous run of the sorted arrays — the
+//     fast-mode layout uses monotone cell ranks, see GridDesc), evaluates the density exactly like variant 0,
+//     and additionally records, per column, which candidates passed the reference's exact radius test
+//     (spatial_hash.h:70-73) as a 64-bit mask.  Masks are stored column-major (masks[col][slot]) so that a warp
+//     writes one fully coalesced 256-byte row per column — the per-lane scattered stores that sank the
+//     neighbour-LIST hand-off do not occur;
+//   * k_force_mask reads the 25 masks of its particle back (coalesced), and for every set bit evaluates the pair
+//     directly — no distance test, no rejected candidates; the per-column loop trip count is the popcount of
+//     the mask, so a warp runs max-over-lanes(popcount) iterations of pure pair arithmetic.
+// A column holding more than 64 candidates (collapsed states) sets the particle's overflow flag; the force pass
+// then walks that particle with the tested loop of variant 0, so results never depend on the mask capacity.
+//
+// Reference: SPHEngine::update_neighbor_lists' query + compute_densities + compute_pressures + compute_forces
+// (src/sph_engine.cpp:335-353, 203-244); the bitmask is this design's stand-in for neighbor_lists_[i].
+#include "pair_math.cuh"
+
+namespace sphb {
+
+namespace {
+
+constexpr int kThreads = 128;
+constexpr int R = kMaskRadius;
+
+struct CellPos {
+    int c0, c1, c2;
+};
+
+__device__ __forceinline__ CellPos key_order_cell(const GridDesc& g, const float4& p) {
+    CellPos c;
+    c.c0 = clampi(cell_coord(pick_axis(p, g.perm[0]), g.inv_cell), g.lo[0], g.hi[0]);
+    c.c1 = clampi(cell_coord(pick_axis(p, g.perm[1]), g.inv_cell), g.lo[1], g.hi[1]);
+    c.c2 = clampi(cell_coord(pick_axis(p, g.perm[2]), g.inv_cell), g.lo[2], g.hi[2]);
+    return c;
+}
+
+// Calls body(col, valid, b, e) for the (2R+1)^2 columns around cell c in walk order; [b, e) is the slot run of
+// the column's 2R+1 cells (monotone ranks: always one run).  Invalid columns (outside the cell box) get b = e = 0.
+template <typename Body>
+__device__ __forceinline__ void walk_columns(const GridDesc& g, const uint32_t* __restrict__ cell_start, const CellPos& c,
+                                             Body&& body) {
+    const int za = max(c.c2 - R, g.lo[2]) - g.lo[2];
+    const int zb = min(c.c2 + R, g.hi[2]) - g.lo[2] + 1;
+    int col = 0;
+    for (int d0 = -R; d0 <= R; ++d0) {
+        const int x0 = c.c0 + d0;
+        const bool ok0 = x0 >= g.lo[0] && x0 <= g.hi[0];
+        const uint32_t base0 = (uint32_t)(x0 - g.lo[0]) * (uint32_t)g.ext[1];
+        for (int d1 = -R; d1 <= R; ++d1, ++col) {
+            const int x1 = c.c1 + d1;
+            if (ok0 && x1 >= g.lo[1] && x1 <= g.hi[1]) {
+                const uint32_t base = (base0 + (uint32_t)(x1 - g.lo[1])) * (uint32_t)g.ext[2];
+                body(col, true, __ldg(&cell_start[base + za]), __ldg(&cell_start[base + zb]));
+            } else {
+                body(col, false, 0u, 0u);
+            }
+        }
+    }
+}
+
+template <bool SLAB>
+__global__ void __launch_bounds__(kThreads) k_density_mask(PairArgs a) {
+    const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    unsigned count = 0;
+    if (i < a.n) {
+        const float4 pi = a.posm[i];
+        if (!SLAB || wants_density(a, pi)) {
+            const CellPos c = key_order_cell(a.grid, pi);
+            const float r2 = a.k.r2;
+            const float inv_h = a.k.inv_h;
+            float rho = 0.0f;   // the self pair (d2 = 0) stays in the loop: the polynomial gives sigma * 4/6 there
+            unsigned ovf = 0;
+            uint2* __restrict__ mrow = a.masks + i;
+            const size_t stride = a.mask_stride;
+            // test + density contribution of slot j; returns whether j is a neighbour (exact reference test)
+            auto visit = [&](uint32_t j) -> bool {
+                const float4 pj = __ldg(&a.posm[j]);
+                const float dx = __fsub_rn(pi.x, pj.x), dy = __fsub_rn(pi.y, pj.y), dz = __fsub_rn(pi.z, pj.z);
+                const float d2 = dist2_exact(dx, dy, dz);
+                const bool in = d2 <= r2;
+                if (in) {
+                    const float q = fast_sqrt(d2) * inv_h;
+                    const float t2 = fmaxf(2.0f - q, 0.0f), t1 = fmaxf(1.0f - q, 0.0f);
+                    rho += pj.w * (t2 * t2 * t2 - 4.0f * (t1 * t1 * t1));
+                }
+                return in;
+            };
+            walk_columns(a.grid, a.cell_start, c, [&](int col, bool valid, uint32_t b, uint32_t e) {
+                uint32_t mlo = 0, mhi = 0;
+                if (valid) {
+                    uint32_t j = b;
+                    const uint32_t e1 = min(e, b + 32u);
+                    uint32_t bit = 1u;
+#pragma unroll 4
+                    for (; j < e1; ++j, bit += bit)
+                        if (visit(j)) mlo |= bit;
+                    if (j < e) {
+                        const uint32_t e2 = min(e, b + 64u);
+                        bit = 1u;
+#pragma unroll 4
+                        for (; j < e2; ++j, bit += bit)
+                            if (visit(j)) mhi |= bit;
+                        if (j < e) {   // more than 64 candidates in this column: no mask for them
+                            ovf = 1u;
+                            for (; j < e; ++j)
+                                if (visit(j)) ++count;
+                        }
+                    }
+                    count += __popc(mlo) + __popc(mhi);
+                }
+                mrow[(size_t)col * stride] = make_uint2(mlo, mhi);
+            });
+            mrow[(size_t)kMaskCols * stride] = make_uint2(ovf, count);
+            rho *= a.k.sigma * (1.0f / 6.0f);
+            const float P = a.k.gas_constant * (rho - a.k.rest_density);
+            a.rho_p[i] = make_float2(rho, P);
+            const float4 v = a.velid[i];
+            const float A = pi.w / (2.0f * rho);
+            a.fa[i] = make_float4(pi.x, pi.y, pi.z, A);
+            a.fb[i] = make_float4(v.x, v.y, v.z, A * P);
+            if (a.nbr_count) a.nbr_count[i] = count;
+        }
+    }
+    count = __reduce_max_sync(0xffffffffu, count);
+    if ((threadIdx.x & 31) == 0 && count > *(volatile unsigned int*)&a.sc->max_neighbors) atomicMax(&a.sc->max_neighbors, count);
+}
+
+template <bool SLAB>
+__global__ void __launch_bounds__(kThreads) k_force_mask(PairArgs a) {
+    const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= a.n) return;
+    const float4 vi = a.velid[i];
+    if (SLAB && is_ghost(vi)) return;   // slab mode: halo copies are never advanced here
+    const float4 pi = a.posm[i];
+    const float P_i = a.rho_p[i].y;
+    const CellPos c = key_order_cell(a.grid, pi);
+    ForceAccum f = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    const uint2* __restrict__ mrow = a.masks + i;
+    const size_t stride = a.mask_stride;
+    const unsigned ovf = mrow[(size_t)kMaskCols * stride].x;
+    // pair j -> i without a distance test (j was accepted by the density pass)
+    auto pair = [&](uint32_t j) {
+        const float4 pj = __ldg(&a.fa[j]);
+        const float4 vj = __ldg(&a.fb[j]);
+        const float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
+        const float d2 = rx * rx + ry * ry + rz * rz;
+        force_pair_fast(a.k, f, rx, ry, rz, d2, vj.x - vi.x, vj.y - vi.y, vj.z - vi.z, P_i, pj.w, vj.w);
+    };
+    if (!ovf) {
+        walk_columns(a.grid, a.cell_start, c, [&](int col, bool valid, uint32_t b, uint32_t e) {
+            if (!valid) return;
+            const uint2 m = mrow[(size_t)col * stride];
+            uint32_t w = m.x;
+            while (w) {
+                const int k = 31 - __clz(w);
+                w ^= 1u << k;
+                pair(b + (uint32_t)k);
+            }
+            w = m.y;
+            while (w) {
+                const int k = 31 - __clz(w);
+                w ^= 1u << k;
+                pair(b + 32u + (uint32_t)k);
+            }
+        });
+    } else {
+        const float r2 = a.k.r2;
+        walk_columns(a.grid, a.cell_start, c, [&](int col, bool valid, uint32_t b, uint32_t e) {
+            for (uint32_t j = b; j < e; ++j) {
+                // positions from posm: in slab mode fa/fb are only written where the density was evaluated (owned +
+                // first halo layer), which covers every ACCEPTED j of an owned particle but not every candidate
+                const float4 pj = __ldg(&a.posm[j]);
+                const float rx = __fsub_rn(pi.x, pj.x), ry = __fsub_rn(pi.y, pj.y), rz = __fsub_rn(pi.z, pj.z);
+                const float d2 = dist2_exact(rx, ry, rz);
+                if (d2 <= r2) {
+                    const float A_j = __ldg(&a.fa[j].w);
+                    const float4 vj = __ldg(&a.fb[j]);
+                    force_pair_fast(a.k, f, rx, ry, rz, d2, vj.x - vi.x, vj.y - vi.y, vj.z - vi.z, P_i, A_j, vj.w);
+                }
+            }
+        });
+    }
+    a.acc[i] = accel_fast(a.k, f, pi.w);
+}
+
+}  // namespace
+
+int launch_density_mask(const PairArgs& a, cudaStream_t st) {
+    if (a.n == 0) return 0;
+    const unsigned nb = (unsigned)((a.n + kThreads - 1) / kThreads);
+    if (a.slab_axis >= 0) k_density_mask<true><<<nb, kThreads, 0, st>>>(a);
+    else k_density_mask<false><<<nb, kThreads, 0, st>>>(a);
+    return 1;
+}
+
+int launch_force_mask(const PairArgs& a, cudaStream_t st) {
+    if (a.n == 0) return 0;
+    const unsigned nb = (unsigned)((a.n + kThreads - 1) / kThreads);
+    if (a.slab_axis >= 0) k_force_mask<true><<<nb, kThreads, 0, st>>>(a);
+    else k_force_mask<false><<<nb, kThreads, 0, st>>>(a);
+    return 1;
+}
+
+}  // namespace sphb

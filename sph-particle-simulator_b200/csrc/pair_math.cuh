@@ -19,6 +19,18 @@
 
 namespace sphb {
 
+__device__ __forceinline__ int cell_coord(float p, float inv_cell) { return __float2int_rd(__fmul_rn(p, inv_cell)); }
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+__device__ __forceinline__ float pick_axis(const float4& p, int axis) { return axis == 0 ? p.x : (axis == 1 ? p.y : p.z); }
+
+// slab mode: is the density of this particle needed here (owned or first halo layer)?
+__device__ __forceinline__ bool wants_density(const PairArgs& a, const float4& p) {
+    if (a.slab_axis < 0) return true;
+    const int cell = cell_coord(pick_axis(p, a.slab_axis), a.grid.ref_inv_cell);
+    return cell >= a.rho_lo && cell < a.rho_hi;
+}
+__device__ __forceinline__ bool is_ghost(const float4& velid) { return (__float_as_uint(velid.w) & 0x80000000u) != 0u; }
+
 // dot(d, d) <= r2 exactly as SpatialHash::within_radius_squared (reference spatial_hash.h:70-73):
 // (dx*dx + dy*dy) + dz*dz with every product and sum rounded separately.
 __device__ __forceinline__ float dist2_exact(float dx, float dy, float dz) {

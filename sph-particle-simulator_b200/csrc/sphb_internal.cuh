@@ -18,6 +18,14 @@ constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs; grids of the persistent ker
 // that order inside the bounding cell box [lo, hi], so the dense linear cell index
 //     cell = (rank_x * ext_y + rank_y) * ext_z + rank_z
 // is strictly monotone in the reference key and a sort by it yields the reference-key order.
+//
+// The per-axis fields are indexed by KEY POSITION k (0 = most significant, 2 = fastest-varying = the axis the
+// contiguous cell columns run along); perm[k] is the physical axis (0 = x, 1 = y, 2 = z) at that position.
+// Strict mode and the reference-order debug keys use the identity permutation with the masked-key rank
+// (monotone = 0).  The fast-mode layout is free to differ from the reference order (the reference-order
+// permutation is then produced by a separate debug sort): it uses monotone ranks (rank = c - lo, so a cell
+// column is ONE contiguous run) and, in slab mode, puts the slab axis first so that the ghost layers are
+// contiguous blocks of the sorted arrays (whole warps of ghosts exit the force pass at once).
 struct GridDesc {
     float inv_cell;        // 1 / (internal cell size) — internal cell = neighbor_search_radius / refine
     float ref_inv_cell;    // 1 / neighbor_search_radius: the reference's hash cell (spatial_hash.h:63-66), for the 63-bit keys
@@ -25,13 +33,16 @@ struct GridDesc {
     int pos_lo[3];         // max(lo, 0)
     int npos[3];           // number of non-negative cells on the axis
     int ext[3];            // hi - lo + 1
+    int perm[3];           // physical axis at key position k
+    int monotone;          // 1: rank = c - lo ; 0: the reference's masked-key order (non-negative cells first)
     uint32_t ncells;
     int id_bits;           // bits of the particle id inside the composite sort key
     int cell_bits;
 };
 
-__host__ __device__ inline int grid_rank(const GridDesc& g, int axis, int c) {
-    return c >= 0 ? c - g.pos_lo[axis] : c - g.lo[axis] + g.npos[axis];
+__host__ __device__ inline int grid_rank(const GridDesc& g, int k, int c) {
+    if (g.monotone) return c - g.lo[k];
+    return c >= 0 ? c - g.pos_lo[k] : c - g.lo[k] + g.npos[k];
 }
 
 // ---- physics constants, precomputed on the host in the reference's own fp32 expression order ----
@@ -120,6 +131,11 @@ struct PairArgs {
     float4* fa2;               // x, y, z, A' = (sigma/h) m / (2 rho)
     float4* fb2;               // vx, vy, vz, B' = A' P
     float4* acc;               // ax, ay, az, (unused)
+    // variant 2: accepted-neighbour bitmasks handed from the density pass to the force pass, column-major:
+    // masks[col * mask_stride + slot], col = 0 .. kMaskCols-1 are the (2R+1)^2 cell columns in walk order (bit k =
+    // k-th candidate of the column run), col = kMaskCols is {overflow flag, 0}
+    uint2* masks;
+    size_t mask_stride;
     uint32_t* nbr_count;       // optional, per sorted slot
     DeviceScalars* sc;
     GridDesc grid;
@@ -134,6 +150,10 @@ struct PairArgs {
 };
 int launch_density(const PairArgs& a, cudaStream_t st);
 int launch_force(const PairArgs& a, cudaStream_t st);
+constexpr int kMaskRadius = 2;                                           // variant 2 walks (2*2+1)^2 columns of 5 cells
+constexpr int kMaskCols = (2 * kMaskRadius + 1) * (2 * kMaskRadius + 1);
+int launch_density_mask(const PairArgs& a, cudaStream_t st);
+int launch_force_mask(const PairArgs& a, cudaStream_t st);
 
 int launch_set_dt(DeviceScalars* sc, float dt, cudaStream_t st);
 int launch_cfl_dt(DeviceScalars* sc, IntegrateConsts ic, cudaStream_t st);

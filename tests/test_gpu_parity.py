@@ -65,7 +65,7 @@ def test_strict_bit_exact_vs_reference_golden(pkg, name, variant):
     ctx.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("name", ["micro_pair", "micro_coincident", "micro_lattice27", "cloud600", "cloud600_truncated_support",
                                   "cloud600_wide_cell", "dam_break_13k_tame"])
 def test_fast_mode_single_step_tolerance(pkg, name, variant):
@@ -241,7 +241,7 @@ def test_full_size_properties_1M(pkg):
     pos, mass, prm, dt = scenes.make_scene("dam_break_1M")
     n = pos.shape[0]
     res = {}
-    for name, strict, variant in (("s0", True, 0), ("s1", True, 1), ("f1", False, 1)):
+    for name, strict, variant in (("s0", True, 0), ("s1", True, 1), ("f1", False, 1), ("f2", False, 2)):
         ctx = make_ctx(pkg, n, prm, strict=strict, OPT_PAIR_KERNEL=variant)
         ctx.upload(pos, None, mass)
         ctx.step(dt)
@@ -258,9 +258,11 @@ def test_full_size_properties_1M(pkg):
         same = sk[1:] == sk[:-1]
         assert (perm[1:][same] > perm[:-1][same]).all(), "sort not stable (ids not ascending inside a cell)"
         assert (cnt >= 1).all() and int((cnt.astype(np.int64) - 1).sum()) % 2 == 0, "neighbour relation not symmetric"
-    assert_bits(res["f1"][0][1]["nbr_count"], res["s1"][0][1]["nbr_count"], "fast vs strict counts (step 1)")
-    assert_bits(res["f1"][0][1]["perm"], res["s1"][0][1]["perm"], "fast vs strict perm (step 1)")
-    assert_bits(res["f1"][0][1]["keys"], res["s1"][0][1]["keys"], "fast vs strict keys (step 1)")
+    for fv in ("f1", "f2"):   # f2 = the default fast path (bitmask hand-off, monotone layout)
+        assert_bits(res[fv][0][1]["nbr_count"], res["s1"][0][1]["nbr_count"], f"{fv} vs strict counts (step 1)")
+        assert_bits(res[fv][0][1]["perm"], res["s1"][0][1]["perm"], f"{fv} vs strict perm (step 1)")
+        assert_bits(res[fv][0][1]["keys"], res["s1"][0][1]["keys"], f"{fv} vs strict keys (step 1)")
+    check_fast(res["f2"][0][0], res["s1"][0][0], 0.8, "1M fast (variant 2) vs strict, step 1")
     for f in ("rho", "P", "acc", "pos", "vel"):
         assert_bits(res["s0"][1][f], res["s1"][1][f], f"pair-kernel variants differ in strict mode: {f}")
     check_fast(res["f1"][0][0], res["s1"][0][0], 0.8, "1M fast vs strict, step 1")

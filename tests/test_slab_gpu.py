@@ -16,10 +16,13 @@ pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parent.parent
 
 
-def single_run(pkg, params, pos, vel, mass, dt, steps, strict):
+def single_run(pkg, params, pos, vel, mass, dt, steps, strict, layout_major=2):
     capi = pkg.capi
     ctx = pkg.Context(len(pos), 0)
     ctx.set_option(capi.OPT_MATH_MODE, capi.MATH_STRICT if strict else capi.MATH_FAST)
+    # fast mode: a slab context orders its cells with the slab axis most significant; the single context is given
+    # the same layout so that the fp32 summation orders (and therefore the bits) agree.  Strict mode ignores it.
+    ctx.set_option(capi.OPT_LAYOUT_MAJOR, layout_major)
     ctx.set_params(params)
     ctx.upload(pos, vel, mass)
     for _ in range(steps):
