@@ -54,6 +54,7 @@ struct sphb_ctx {
     float4* acc = nullptr;
     uint2* masks = nullptr;      // variant 2: (kMaskCols + 1) rows of mask_stride accepted-neighbour masks
     size_t mask_stride = 0;
+    ForceRec* fab = nullptr;     // variant 2: 32-byte force-pass records
     uint32_t* nbr_count = nullptr;
     uint64_t* refkeys[2] = {nullptr, nullptr};
     uint64_t* dbg_keys[2] = {nullptr, nullptr};   // reference-order composite keys (debug capture with a refined grid)
@@ -283,7 +284,7 @@ void free_all(sphb_ctx* c) {
         cudaFree(c->posm[i]); cudaFree(c->velid[i]); cudaFree(c->refkeys[i]); cudaFree(c->dbg_keys[i]);
         cudaFree(c->sb.keys[i]); cudaFree(c->sb.vals[i]);
     }
-    cudaFree(c->pp2); cudaFree(c->fa2); cudaFree(c->fb2); cudaFree(c->masks);
+    cudaFree(c->pp2); cudaFree(c->fa2); cudaFree(c->fb2); cudaFree(c->masks); cudaFree(c->fab);
     cudaFree(c->rho_p); cudaFree(c->fa); cudaFree(c->fb); cudaFree(c->acc); cudaFree(c->nbr_count);
     cudaFree(c->sb.counts); cudaFree(c->sb.block_sums); cudaFree(c->cell_start);
     cudaFree(c->sc); cudaFree(c->d_stage); cudaFree(c->d_box); cudaFree(c->d_counts); cudaFree(c->sort_scratch);
@@ -655,6 +656,7 @@ int sphb_step(sphb_ctx* c, float dt) {
         const size_t cap = c->capacity ? c->capacity : 1;
         c->mask_stride = (cap + 31) & ~(size_t)31;
         CU(c, cudaMalloc(&c->masks, (size_t)(kMaskCols + 1) * c->mask_stride * sizeof(uint2)));
+        CU(c, cudaMalloc(&c->fab, cap * sizeof(ForceRec)));
     }
     if (c->debug_capture) { rc = ensure_debug(c); if (rc) return rc; }
 
@@ -705,6 +707,7 @@ int sphb_step(sphb_ctx* c, float dt) {
     pa.acc = c->acc;
     pa.masks = c->masks;
     pa.mask_stride = c->mask_stride;
+    pa.fab = c->fab;
     pa.nbr_count = c->debug_capture ? c->nbr_count : nullptr;
     pa.sc = c->sc;
     pa.grid = g;

@@ -122,14 +122,28 @@ __global__ void __launch_bounds__(kThreads) k_density_mask(PairArgs a) {
             a.rho_p[i] = make_float2(rho, P);
             const float4 v = a.velid[i];
             const float A = pi.w / (2.0f * rho);
-            a.fa[i] = make_float4(pi.x, pi.y, pi.z, A);
-            a.fb[i] = make_float4(v.x, v.y, v.z, A * P);
+            float4* rec = reinterpret_cast<float4*>(a.fab + i);
+            rec[0] = make_float4(pi.x, pi.y, pi.z, A);
+            rec[1] = make_float4(v.x, v.y, v.z, A * P);
             if (a.nbr_count) a.nbr_count[i] = count;
         }
     }
     count = __reduce_max_sync(0xffffffffu, count);
     if ((threadIdx.x & 31) == 0 && count > *(volatile unsigned int*)&a.sc->max_neighbors) atomicMax(&a.sc->max_neighbors, count);
 }
+
+// 32-byte force-pass record of one particle, fetched with ONE 256-bit load (LDG.E.256, sm_100)
+__device__ __forceinline__ ForceRec load_rec(const ForceRec* __restrict__ p) {
+    ForceRec r;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.A), "=f"(r.vx), "=f"(r.vy), "=f"(r.vz), "=f"(r.B)
+        : "l"(p));
+    return r;
+}
+
+#ifndef SPHB_FORCE_PIPE
+#define SPHB_FORCE_PIPE 0
+#endif
 
 template <bool SLAB>
 __global__ void __launch_bounds__(kThreads) k_force_mask(PairArgs a) {
@@ -140,48 +154,77 @@ __global__ void __launch_bounds__(kThreads) k_force_mask(PairArgs a) {
     const float4 pi = a.posm[i];
     const float P_i = a.rho_p[i].y;
     const CellPos c = key_order_cell(a.grid, pi);
+    const GridDesc& g = a.grid;
     ForceAccum f = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
     const uint2* __restrict__ mrow = a.masks + i;
     const size_t stride = a.mask_stride;
     const unsigned ovf = mrow[(size_t)kMaskCols * stride].x;
     // pair j -> i without a distance test (j was accepted by the density pass)
-    auto pair = [&](uint32_t j) {
-        const float4 pj = __ldg(&a.fa[j]);
-        const float4 vj = __ldg(&a.fb[j]);
-        const float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
+    auto eval = [&](const ForceRec& q) {
+        const float rx = pi.x - q.x, ry = pi.y - q.y, rz = pi.z - q.z;
         const float d2 = rx * rx + ry * ry + rz * rz;
-        force_pair_fast(a.k, f, rx, ry, rz, d2, vj.x - vi.x, vj.y - vi.y, vj.z - vi.z, P_i, pj.w, vj.w);
+        force_pair_fast(a.k, f, rx, ry, rz, d2, q.vx - vi.x, q.vy - vi.y, q.vz - vi.z, P_i, q.A, q.B);
     };
     if (!ovf) {
-        walk_columns(a.grid, a.cell_start, c, [&](int col, bool valid, uint32_t b, uint32_t e) {
-            if (!valid) return;
-            const uint2 m = mrow[(size_t)col * stride];
-            uint32_t w = m.x;
-            while (w) {
-                const int k = 31 - __clz(w);
-                w ^= 1u << k;
-                pair(b + (uint32_t)k);
+        // The 25 columns are consumed as 13 groups {column k, its point mirror 24 - k}: a lane close to one side of
+        // its cell has many neighbours in the columns on that side and few in the mirrored ones, so the SUM over a
+        // mirror pair is nearly the same for all lanes of a warp.  Inside a group every lane pops its own bits as
+        // one flat stream (column k, then 24 - k), so the warp runs max-over-lanes(sum) iterations per group:
+        // ~300 per particle instead of ~450 with one lock-step loop per mask word (lattice, h = 2 dx).
+        const int za = max(c.c2 - R, g.lo[2]) - g.lo[2];
+        const int r0 = c.c0 - g.lo[0], r1 = c.c1 - g.lo[1];
+        int d0 = -R, d1 = -R;
+#pragma unroll 1
+        for (int k = 0; k <= kMaskCols / 2; ++k) {
+            const uint2 mA = mrow[(size_t)k * stride];
+            uint2 mB = make_uint2(0u, 0u);
+            if (k < kMaskCols / 2) mB = mrow[(size_t)(kMaskCols - 1 - k) * stride];
+            // masks of columns outside the cell box are zero (written by the density pass), so a base is only
+            // looked up for columns that exist
+            uint32_t bA = 0, bB = 0;
+            if (mA.x | mA.y) bA = __ldg(&a.cell_start[((uint32_t)(r0 + d0) * (uint32_t)g.ext[1] + (uint32_t)(r1 + d1)) * (uint32_t)g.ext[2] + za]);
+            if (mB.x | mB.y) bB = __ldg(&a.cell_start[((uint32_t)(r0 - d0) * (uint32_t)g.ext[1] + (uint32_t)(r1 - d1)) * (uint32_t)g.ext[2] + za]);
+            if (++d1 > R) { d1 = -R; ++d0; }
+            uint32_t lo = mA.x, hi = mA.y, base = bA;
+            uint32_t lo2 = mB.x, hi2 = mB.y;
+            if ((lo | hi) == 0u) { lo = lo2; hi = hi2; base = bB; lo2 = 0u; hi2 = 0u; }
+            // pops the highest set bit of hi:lo and returns its slot
+            auto pop = [&]() -> uint32_t {
+                const bool up = hi != 0u;
+                uint32_t w = up ? hi : lo;
+                const int b = 31 - __clz(w);
+                w ^= 1u << b;
+                if (up) hi = w; else lo = w;
+                const uint32_t j = base + (uint32_t)b + (up ? 32u : 0u);
+                if ((lo | hi) == 0u) { lo = lo2; hi = hi2; base = bB; lo2 = 0u; hi2 = 0u; }
+                return j;
+            };
+#if SPHB_FORCE_PIPE
+            bool have = (lo | hi) != 0u;
+            ForceRec nxt;
+            if (have) nxt = load_rec(a.fab + pop());
+            while (have) {
+                const ForceRec cur = nxt;
+                have = (lo | hi) != 0u;
+                if (have) nxt = load_rec(a.fab + pop());
+                eval(cur);
             }
-            w = m.y;
-            while (w) {
-                const int k = 31 - __clz(w);
-                w ^= 1u << k;
-                pair(b + 32u + (uint32_t)k);
-            }
-        });
+#else
+            while (lo | hi) eval(load_rec(a.fab + pop()));
+#endif
+        }
     } else {
         const float r2 = a.k.r2;
         walk_columns(a.grid, a.cell_start, c, [&](int col, bool valid, uint32_t b, uint32_t e) {
             for (uint32_t j = b; j < e; ++j) {
-                // positions from posm: in slab mode fa/fb are only written where the density was evaluated (owned +
+                // positions from posm: in slab mode fab is only written where the density was evaluated (owned +
                 // first halo layer), which covers every ACCEPTED j of an owned particle but not every candidate
                 const float4 pj = __ldg(&a.posm[j]);
                 const float rx = __fsub_rn(pi.x, pj.x), ry = __fsub_rn(pi.y, pj.y), rz = __fsub_rn(pi.z, pj.z);
                 const float d2 = dist2_exact(rx, ry, rz);
                 if (d2 <= r2) {
-                    const float A_j = __ldg(&a.fa[j].w);
-                    const float4 vj = __ldg(&a.fb[j]);
-                    force_pair_fast(a.k, f, rx, ry, rz, d2, vj.x - vi.x, vj.y - vi.y, vj.z - vi.z, P_i, A_j, vj.w);
+                    const ForceRec q = load_rec(a.fab + j);
+                    force_pair_fast(a.k, f, rx, ry, rz, d2, q.vx - vi.x, q.vy - vi.y, q.vz - vi.z, P_i, q.A, q.B);
                 }
             }
         });

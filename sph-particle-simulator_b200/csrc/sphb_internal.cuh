@@ -117,6 +117,12 @@ int launch_reorder(size_t n, const uint32_t* sorted_vals, const float4* posm_in,
                    const uint64_t* refkeys_in, float4* posm_out, float4* velid_out, uint64_t* refkeys_out, float4* pp2_out,
                    cudaStream_t st);
 
+// variant 2: everything the force pass needs from a neighbour, in one 32-byte record (A = m / (2 rho), B = A * P)
+struct __align__(32) ForceRec {
+    float x, y, z, A;
+    float vx, vy, vz, B;
+};
+
 struct PairArgs {
     size_t n;
     const float4* posm;        // x, y, z, mass   (cell-sorted)
@@ -136,6 +142,7 @@ struct PairArgs {
     // k-th candidate of the column run), col = kMaskCols is {overflow flag, 0}
     uint2* masks;
     size_t mask_stride;
+    ForceRec* fab;             // variant 2: force-pass records, written by the density pass
     uint32_t* nbr_count;       // optional, per sorted slot
     DeviceScalars* sc;
     GridDesc grid;
