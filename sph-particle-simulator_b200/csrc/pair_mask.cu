@@ -27,6 +27,9 @@ namespace {
 
 constexpr int kThreads = 128;
 constexpr int R = kMaskRadius;
+#ifndef SPHB_DENSITY_F32X2
+#define SPHB_DENSITY_F32X2 1
+#endif
 
 struct CellPos {
     int c0, c1, c2;
@@ -64,8 +67,11 @@ __device__ __forceinline__ void walk_columns(const GridDesc& g, const uint32_t* 
     }
 }
 
+#ifndef SPHB_DMASK_MINBLOCKS
+#define SPHB_DMASK_MINBLOCKS 1
+#endif
 template <bool SLAB>
-__global__ void __launch_bounds__(kThreads) k_density_mask(PairArgs a) {
+__global__ void __launch_bounds__(kThreads, SPHB_DMASK_MINBLOCKS) k_density_mask(PairArgs a) {
     const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
     unsigned count = 0;
     if (i < a.n) {
@@ -78,16 +84,37 @@ __global__ void __launch_bounds__(kThreads) k_density_mask(PairArgs a) {
             unsigned ovf = 0;
             uint2* __restrict__ mrow = a.masks + i;
             const size_t stride = a.mask_stride;
+            const float2 pxy = make_float2(pi.x, pi.y);
+            const float2 nz2 = make_float2(a.k.neg_zero, a.k.neg_zero);
+            const float2 ninv_h2 = make_float2(-inv_h, -inv_h);
             // test + density contribution of slot j; returns whether j is a neighbour (exact reference test)
             auto visit = [&](uint32_t j) -> bool {
                 const float4 pj = __ldg(&a.posm[j]);
+#if SPHB_DENSITY_F32X2
+                // (x, y) of a float4 load sit in an aligned register pair: one FADD2 + one FFMA2 (exact squares as
+                // fma(d, d, -0), see pair.cu) replace two FADDs + two FMULs; every rounding is the reference's
+                const float2 dxy = __fadd2_rn(pxy, make_float2(-pj.x, -pj.y));
+                const float2 sq = __ffma2_rn(dxy, dxy, nz2);
+                const float dz = __fsub_rn(pi.z, pj.z);
+                const float d2 = __fadd_rn(__fadd_rn(sq.x, sq.y), __fmul_rn(dz, dz));
+#else
                 const float dx = __fsub_rn(pi.x, pj.x), dy = __fsub_rn(pi.y, pj.y), dz = __fsub_rn(pi.z, pj.z);
                 const float d2 = dist2_exact(dx, dy, dz);
+#endif
                 const bool in = d2 <= r2;
                 if (in) {
+#if SPHB_DENSITY_F32X2 >= 2
+                    // (2 - q, 1 - q) -> clamp -> cubes as packed pairs
+                    const float s = fast_sqrt(d2);
+                    float2 t = __ffma2_rn(make_float2(s, s), ninv_h2, make_float2(2.0f, 1.0f));
+                    t.x = fmaxf(t.x, 0.0f); t.y = fmaxf(t.y, 0.0f);
+                    const float2 t3 = __fmul2_rn(__fmul2_rn(t, t), t);
+                    rho += pj.w * (t3.x - 4.0f * t3.y);
+#else
                     const float q = fast_sqrt(d2) * inv_h;
                     const float t2 = fmaxf(2.0f - q, 0.0f), t1 = fmaxf(1.0f - q, 0.0f);
                     rho += pj.w * (t2 * t2 * t2 - 4.0f * (t1 * t1 * t1));
+#endif
                 }
                 return in;
             };

@@ -176,6 +176,7 @@ def test_slab_mode_guards_and_diagnostics(pkg):
     pos, mass, params, dt = scenes.dam_break_scene(0.02)
     n = len(pos)
     ctx = pkg.Context(n, 0); ctx.set_params(params); ctx.upload(pos, None, mass)
+    ctx.set_option(pkg.capi.OPT_LAYOUT_MAJOR, 2)      # the slab contexts below order their cells z-major (fast mode)
     for _ in range(2):
         ctx.step(dt)
     want = ctx.diagnostics(); ctx.close()
