@@ -204,6 +204,14 @@ int sphb_upload_ids(sphb_ctx* ctx, size_t n, const float* pos3, const float* vel
  * Append what arrives with sphb_slab_append(..., ghost = -1): records keep their own flag.  Synchronises. */
 int sphb_slab_exchange_pack(sphb_ctx* ctx, const int32_t* cuts, int nranks, int my_rank, void* d_out, size_t cap_records,
                             uint64_t* counts);
+/* The same exchange in two phases, for ONE host synchronisation per step: _count only enqueues the routing count
+ * and copies this rank's 2*nranks group sizes (uint32) to the DEVICE buffer d_counts on the context's stream — the
+ * caller all-gathers them on the device and reads the gathered table back once; _split then takes this rank's row
+ * of that table from the host and moves the records exactly like sphb_slab_exchange_pack.  Nothing may touch the
+ * context between the two calls. */
+int sphb_slab_exchange_count(sphb_ctx* ctx, const int32_t* cuts, int nranks, int my_rank, uint32_t* d_counts);
+int sphb_slab_exchange_split(sphb_ctx* ctx, const int32_t* cuts, int nranks, int my_rank, const uint32_t* counts, void* d_out,
+                             size_t cap_records);
 /* Append records: ghost = -1 keeps each record's own flag (what the exchange delivers); 0 / 1 force owned / ghost. */
 int sphb_slab_append(sphb_ctx* ctx, const void* d_in, size_t count, int ghost);
 /* Owned particles of this context in arbitrary order: ids[k] with the matching fields (host pointers,

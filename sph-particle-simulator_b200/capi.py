@@ -44,7 +44,8 @@ ABI_SYMBOLS = (
     "sphb_upload_strided", "sphb_download", "sphb_download_strided", "sphb_size", "sphb_step", "sphb_run_steps",
     "sphb_get_time", "sphb_set_time", "sphb_cfl_timestep", "sphb_get_stats", "sphb_reset_stats",
     "sphb_diagnostics", "sphb_debug_dump",
-    "sphb_set_slab", "sphb_upload_ids", "sphb_slab_append", "sphb_slab_exchange_pack", "sphb_get_cfl_state", "sphb_set_cfl_state",
+    "sphb_set_slab", "sphb_upload_ids", "sphb_slab_append", "sphb_slab_exchange_pack", "sphb_slab_exchange_count",
+    "sphb_slab_exchange_split", "sphb_get_cfl_state", "sphb_set_cfl_state",
     "sphb_slab_download",
 )
 
@@ -118,6 +119,8 @@ def load_library() -> C.CDLL:
     L.sphb_get_cfl_state.argtypes = [vp, fp, fp, C.POINTER(C.c_int)]
     L.sphb_set_cfl_state.argtypes = [vp, C.c_float, fp]
     L.sphb_slab_exchange_pack.argtypes = [vp, vp, C.c_int, C.c_int, vp, sz, vp]
+    L.sphb_slab_exchange_count.argtypes = [vp, vp, C.c_int, C.c_int, vp]
+    L.sphb_slab_exchange_split.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, sz]
     L.sphb_slab_append.argtypes = [vp, vp, sz, C.c_int]
     L.sphb_slab_download.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, C.POINTER(sz)]
     _lib = L
@@ -292,6 +295,18 @@ class Context:
         self._ck(self.L.sphb_slab_exchange_pack(self.h, _ptr(cuts), nranks, int(my_rank), C.c_void_p(d_out_ptr), int(cap_records),
                                                 _ptr(counts)))
         return counts
+
+    def slab_exchange_count(self, cuts, my_rank: int, d_counts_ptr: int):
+        """Phase 1 (asynchronous): this rank's 2*nranks group sizes (uint32) land in the device buffer d_counts_ptr."""
+        cuts = np.ascontiguousarray(cuts, np.int32)
+        self._ck(self.L.sphb_slab_exchange_count(self.h, _ptr(cuts), cuts.shape[0] - 1, int(my_rank), C.c_void_p(d_counts_ptr)))
+
+    def slab_exchange_split(self, cuts, my_rank: int, counts, d_out_ptr: int, cap_records: int):
+        """Phase 2: move the records, given this rank's group sizes (host array, as gathered from phase 1)."""
+        cuts = np.ascontiguousarray(cuts, np.int32)
+        counts = np.ascontiguousarray(counts, np.uint32)
+        self._ck(self.L.sphb_slab_exchange_split(self.h, _ptr(cuts), cuts.shape[0] - 1, int(my_rank), _ptr(counts),
+                                                 C.c_void_p(d_out_ptr), int(cap_records)))
 
     def slab_append(self, d_in_ptr: int, count: int, ghost: bool):
         flag = -1 if ghost is None else (1 if ghost else 0)     # None: records carry their own ghost flag

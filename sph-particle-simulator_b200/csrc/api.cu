@@ -918,8 +918,70 @@ int sphb_upload_ids(sphb_ctx* c, size_t n, const float* pos3, const float* vel3,
     return after_upload(c, n);
 }
 
+static int exchange_count_impl(sphb_ctx* c, const int32_t* cuts, int nranks, int my_rank, SlabCuts* sc) {
+    if (!c->slab_on) return fail(c, SPHB_E_INVALID, "sphb_set_slab first");
+    if (nranks < 1 || nranks > kMaxRanks || my_rank < 0 || my_rank >= nranks) return fail(c, SPHB_E_INVALID, "bad rank layout");
+    CU(c, cudaSetDevice(c->device));
+    sc->nranks = nranks;
+    for (int d = 0; d <= nranks; ++d) sc->cuts[d] = cuts[d];
+    const float ref_inv = 1.0f / c->prm.neighbor_search_radius;
+    CU(c, cudaMemsetAsync(c->d_counts, 0, (2 * kMaxRanks + 1) * sizeof(unsigned int), c->stream));
+    c->stats.kernel_launches += launch_exchange_count(c->n, c->posm[c->cur], c->velid[c->cur], *sc, c->slab.axis, ref_inv,
+                                                      c->slab.halo_layers, c->d_counts, c->stream);
+    return SPHB_OK;
+}
+
+// h[k]: group sizes of this rank (k = 2r: owned by rank r, 2r+1: ghosts for rank r)
+static int exchange_split_impl(sphb_ctx* c, const SlabCuts& sc, int my_rank, const unsigned int* h, void* d_out, size_t cap_records) {
+    const int nranks = sc.nranks;
+    const float ref_inv = 1.0f / c->prm.neighbor_search_radius;
+    const int in = c->cur, out = c->cur ^ 1;
+    ExchangeOffsets off;
+    size_t total = 0, all = 0;
+    for (int k = 0; k < 2 * nranks; ++k) {
+        off.start[k] = (unsigned int)total;
+        if (k != 2 * my_rank) total += h[k];      // key 2*me = particles kept in place
+        if ((k & 1) == 0) all += h[k];
+    }
+    // the context also holds last step's ghosts, which the exchange drops: owned <= n
+    if (all > c->n) return fail(c, SPHB_E_INVALID, "exchange counts cover %zu particles, the context holds only %zu", all, c->n);
+    if (total > cap_records) return fail(c, SPHB_E_CAPACITY, "%zu exchange records exceed the buffer (%zu records)", total, cap_records);
+    if (total > 0 && !d_out) return fail(c, SPHB_E_INVALID, "d_out is NULL");
+    CU(c, cudaMemsetAsync(c->d_counts, 0, (2 * kMaxRanks + 1) * sizeof(unsigned int), c->stream));
+    c->stats.kernel_launches += launch_exchange_split(c->n, c->posm[in], c->velid[in], sc, c->slab.axis, ref_inv, c->slab.halo_layers,
+                                                      my_rank, c->posm[out], c->velid[out], static_cast<float4*>(d_out), off,
+                                                      c->d_counts, c->stream);
+    CU(c, cudaGetLastError());
+    c->cur = out;
+    c->n = h[2 * my_rank];
+    c->stepped_since_upload = false;
+    return SPHB_OK;
+}
+
 int sphb_slab_exchange_pack(sphb_ctx* c, const int32_t* cuts, int nranks, int my_rank, void* d_out, size_t cap_records,
                             uint64_t* counts) {
+    if (!c || !cuts || !counts) return SPHB_E_INVALID;
+    SlabCuts sc;
+    int rc = exchange_count_impl(c, cuts, nranks, my_rank, &sc);
+    if (rc) return rc;
+    unsigned int h[2 * kMaxRanks];
+    CU(c, cudaMemcpyAsync(h, c->d_counts, 2 * nranks * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 2 * nranks; ++k) counts[k] = h[k];
+    return exchange_split_impl(c, sc, my_rank, h, d_out, cap_records);
+}
+
+int sphb_slab_exchange_count(sphb_ctx* c, const int32_t* cuts, int nranks, int my_rank, uint32_t* d_counts) {
+    if (!c || !cuts || !d_counts) return SPHB_E_INVALID;
+    SlabCuts sc;
+    int rc = exchange_count_impl(c, cuts, nranks, my_rank, &sc);
+    if (rc) return rc;
+    CU(c, cudaMemcpyAsync(d_counts, c->d_counts, 2 * nranks * sizeof(unsigned int), cudaMemcpyDeviceToDevice, c->stream));
+    return SPHB_OK;
+}
+
+int sphb_slab_exchange_split(sphb_ctx* c, const int32_t* cuts, int nranks, int my_rank, const uint32_t* counts, void* d_out,
+                             size_t cap_records) {
     if (!c || !cuts || !counts) return SPHB_E_INVALID;
     if (!c->slab_on) return fail(c, SPHB_E_INVALID, "sphb_set_slab first");
     if (nranks < 1 || nranks > kMaxRanks || my_rank < 0 || my_rank >= nranks) return fail(c, SPHB_E_INVALID, "bad rank layout");
@@ -927,32 +989,7 @@ int sphb_slab_exchange_pack(sphb_ctx* c, const int32_t* cuts, int nranks, int my
     SlabCuts sc;
     sc.nranks = nranks;
     for (int d = 0; d <= nranks; ++d) sc.cuts[d] = cuts[d];
-    const float ref_inv = 1.0f / c->prm.neighbor_search_radius;
-    const int in = c->cur, out = c->cur ^ 1;
-    const int L = c->slab.halo_layers;
-    unsigned int h[2 * kMaxRanks];
-    CU(c, cudaMemsetAsync(c->d_counts, 0, (2 * kMaxRanks + 1) * sizeof(unsigned int), c->stream));
-    c->stats.kernel_launches += launch_exchange_count(c->n, c->posm[in], c->velid[in], sc, c->slab.axis, ref_inv, L, c->d_counts, c->stream);
-    CU(c, cudaMemcpyAsync(h, c->d_counts, 2 * nranks * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
-    ExchangeOffsets off;
-    size_t total = 0;
-    for (int k = 0; k < 2 * nranks; ++k) {
-        off.start[k] = (unsigned int)total;
-        if (k != 2 * my_rank) total += h[k];      // key 2*me = particles kept in place
-        counts[k] = h[k];
-    }
-    if (total > cap_records) return fail(c, SPHB_E_CAPACITY, "%zu exchange records exceed the buffer (%zu records)", total, cap_records);
-    if (total > 0 && !d_out) return fail(c, SPHB_E_INVALID, "d_out is NULL");
-    CU(c, cudaMemsetAsync(c->d_counts, 0, (2 * kMaxRanks + 1) * sizeof(unsigned int), c->stream));
-    c->stats.kernel_launches += launch_exchange_split(c->n, c->posm[in], c->velid[in], sc, c->slab.axis, ref_inv, L, my_rank,
-                                                      c->posm[out], c->velid[out], static_cast<float4*>(d_out), off, c->d_counts,
-                                                      c->stream);
-    CU(c, cudaGetLastError());
-    c->cur = out;
-    c->n = h[2 * my_rank];
-    c->stepped_since_upload = false;
-    return SPHB_OK;
+    return exchange_split_impl(c, sc, my_rank, counts, d_out, cap_records);
 }
 
 int sphb_slab_append(sphb_ctx* c, const void* d_in, size_t count, int ghost) {

@@ -90,6 +90,14 @@ class GpuStore:
         """counts[2r] = records owned by rank r (kept in place for r = me), counts[2r+1] = ghosts for rank r."""
         return self.ctx.slab_exchange_pack(cuts, me, buf.data_ptr(), buf.shape[0])
 
+    def exchange_count(self, cuts, me, d_counts: torch.Tensor):
+        """Two-phase form, phase 1 (no host synchronisation): group sizes -> int32 device tensor."""
+        self.ctx.slab_exchange_count(cuts, me, d_counts.data_ptr())
+
+    def exchange_split(self, cuts, me, counts, buf: torch.Tensor):
+        """Phase 2: move the records given this rank's group sizes (host)."""
+        self.ctx.slab_exchange_split(cuts, me, counts, buf.data_ptr(), buf.shape[0])
+
     def append(self, buf: torch.Tensor, count: int, ghost=None):
         """ghost=None: each record carries its own ghost flag (id bit 31)."""
         if count:
@@ -132,6 +140,12 @@ class SlabRank:
         dev = store.device
         self.send = torch.empty((exchange_capacity, REC), dtype=torch.float32, device=dev)
         self.recv = torch.empty((exchange_capacity, REC), dtype=torch.float32, device=dev)
+        # two-phase exchange: my group sizes, the gathered table and its pinned host mirror
+        self.d_counts = torch.zeros(2 * self.nranks, dtype=torch.int32, device=dev)
+        self.d_table = torch.zeros((self.nranks, 2 * self.nranks), dtype=torch.int32, device=dev)
+        self.h_table = torch.zeros((self.nranks, 2 * self.nranks), dtype=torch.int32)
+        if dev.type == "cuda":
+            self.h_table = self.h_table.pin_memory()
         self.stats = {"migrants_sent": 0, "halo_sent": 0, "steps": 0}
         self.params = getattr(store, "params", None)      # needed only for adaptive timesteps
 
@@ -218,16 +232,31 @@ def step_local(ranks: list[SlabRank], dt: float):
 
 def step_distributed(r: SlabRank, dt: float, group=None):
     """One process per GPU: the protocol over torch.distributed (NCCL on GPUs, gloo in the CPU tests).
-    Two host synchronisations per step (group sizes off the device, gathered size table) and two
-    collectives (all_gather of 2G integers, all_to_all of the records)."""
+    One host synchronisation per step (the gathered table of group sizes) and two collectives (all_gather of 2G
+    integers, all_to_all of the records)."""
     import torch.distributed as dist
 
     G, me, dev = r.nranks, r.rank, r.store.device
-    counts = r.pack()
-    mine = torch.from_numpy(counts).to(dev)
-    table = torch.empty((G, 2 * G), dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(table.view(-1), mine, group=group)
-    send, recv = _splits(table.cpu().numpy(), me)
+    if hasattr(r.store, "exchange_count"):
+        # ONE host synchronisation: the routing count, the all-gather of the group sizes and the copy of the
+        # gathered table to pinned memory are enqueued back to back; the host then waits once, and everything
+        # after it (record split, all_to_all, append, the local step) is enqueued without further waiting
+        r.store.exchange_count(r.cuts, me, r.d_counts)
+        dist.all_gather_into_tensor(r.d_table.view(-1), r.d_counts, group=group)
+        r.h_table.copy_(r.d_table, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        table = r.h_table.numpy().astype(np.int64)
+        r.store.exchange_split(r.cuts, me, table[me], r.send)
+        table[me, 2 * me] = 0                                        # kept in place, not sent
+        r.stats["migrants_sent"] += int(table[me, 0::2].sum())
+        r.stats["halo_sent"] += int(table[me, 1::2].sum())
+    else:                                                            # stores without the two-phase form (CPU test double)
+        counts = r.pack()
+        mine = torch.from_numpy(counts).to(dev)
+        table = torch.empty((G, 2 * G), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(table.view(-1), mine, group=group)
+        table = table.cpu().numpy()
+    send, recv = _splits(table, me)
     n_out, n_in = sum(send), sum(recv)
     if n_in > r.recv.shape[0]:
         raise RuntimeError(f"rank {me}: {n_in} incoming records exceed the exchange buffer ({r.recv.shape[0]})")
