@@ -397,7 +397,7 @@ def main():
     ap.add_argument("--cpu-scene", default=None)
     ap.add_argument("--math", default="fast", choices=["fast", "strict"])
     ap.add_argument("--pair-kernel", type=int, default=2)
-    ap.add_argument("--refine", type=int, default=2)
+    ap.add_argument("--refine", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     args = ap.parse_args()

@@ -40,7 +40,7 @@ struct sphb_ctx {
     int debug_capture = 0;
     int pair_kernel = 2;     // fast mode: 2 = bitmask hand-off density -> force (default), 0 = tested walk twice, 1 = packed f32x2
     int layout_major = 0;    // fast-mode layout: physical axis that is most significant in the cell order (slab mode: the slab axis)
-    int grid_refine = 2;     // internal cell = neighbor_search_radius / grid_refine (fast mode; strict always 1)
+    int grid_refine = 4;     // internal cell = neighbor_search_radius / grid_refine (fast mode; strict always 1)
 
     float4* posm[2] = {nullptr, nullptr};
     float4* velid[2] = {nullptr, nullptr};
@@ -52,7 +52,8 @@ struct sphb_ctx {
     float4* fa2 = nullptr;
     float4* fb2 = nullptr;
     float4* acc = nullptr;
-    uint2* masks = nullptr;      // variant 2: (kMaskCols + 1) rows of mask_stride accepted-neighbour masks
+    void* masks = nullptr;       // variant 2: (mask_cols(R) + 1) rows of mask_stride accepted-neighbour masks
+    size_t mask_bytes = 0;
     size_t mask_stride = 0;
     ForceRec* fab = nullptr;     // variant 2: 32-byte force-pass records
     uint32_t* nbr_count = nullptr;
@@ -186,6 +187,11 @@ int make_grid(sphb_ctx* c, GridDesc* g, int refine, int layout_major = -1) {
     if (!(cell > 0.0f)) return fail(c, SPHB_E_INVALID, "neighbor_search_radius must be > 0 (got %g)", (double)cell);
     g->ref_inv_cell = 1.0f / cell;  // SpatialHash::set_cell_size, reference spatial_hash.h:63-66
     g->inv_cell = g->ref_inv_cell * (float)refine;
+    // Refined (internal) grids use cells 0.1 % LARGER than neighbor_search_radius / refine: two particles exactly
+    // neighbor_search_radius apart (the q = 2 ties of lattice scenes) then differ by strictly less than `refine`
+    // in p * inv_cell, so fp32 rounding of that product can never put them refine + 1 cells apart and outside the
+    // (2 refine + 1)-cell walk.  The reference guards the same tie with a second ring of cells (spatial_hash.cpp:35).
+    if (refine > 1) g->inv_cell *= 0.9990234375f;   // 1 - 2^-10
     uint64_t ncells = 1;
     for (int a = 0; a < 3; ++a) {
         int lo = host_cell(c->box_min[a], g->inv_cell), hi = host_cell(c->box_max[a], g->inv_cell);
@@ -635,16 +641,17 @@ int sphb_step(sphb_ctx* c, float dt) {
     // strict mode keeps the reference's cell size so the device layout IS the reference order; fast mode
     // may sort on a finer grid (fewer candidates per particle) and walk refine x as many cells per axis
     int refine = (c->math_mode == 0) ? 1 : c->grid_refine;
-    // pair-kernel variant 2 (bitmask hand-off) needs the 5 x 5 column walk and uses the fast-mode layout
-    int variant = (c->math_mode == 0) ? 0 : c->pair_kernel;
-    if (variant == 2 && c->walk_radius * refine != kMaskRadius) variant = 0;
-    int layout = (variant == 2) ? (c->slab_on ? c->slab.axis : c->layout_major) : -1;
+    // pair-kernel variant 2 (bitmask hand-off) walks R = walk_radius * refine cells per axis, R in [2, 4], and uses
+    // the fast-mode layout.  A refined cell table that would be too large falls back to coarser grids.
+    int variant = 0, layout = -1;
     GridDesc g, gc;
-    rc = make_grid(c, &g, refine, layout);
-    if (rc == SPHB_E_GRID && refine > 1) {   // refined table too large: coarse grid, tested walk
-        refine = 1; layout = -1;
-        if (variant == 2) variant = 0;
-        rc = make_grid(c, &g, 1);
+    for (;; --refine) {
+        variant = (c->math_mode == 0) ? 0 : c->pair_kernel;
+        const int Rw = c->walk_radius * refine;
+        if (variant == 2 && (Rw < kMaskMinRadius || Rw > kMaskMaxRadius)) variant = 0;
+        layout = (variant == 2) ? (c->slab_on ? c->slab.axis : c->layout_major) : -1;
+        rc = make_grid(c, &g, refine, layout);
+        if (rc != SPHB_E_GRID || refine == 1) break;
     }
     if (rc) return rc;
     gc = g;
@@ -652,11 +659,17 @@ int sphb_step(sphb_ctx* c, float dt) {
     if (dbg_ref_sort) { rc = make_grid(c, &gc, 1); if (rc) return rc; }
     rc = ensure_cell_table(c, g);
     if (rc) return rc;
-    if (variant == 2 && !c->masks) {
+    if (variant == 2) {
         const size_t cap = c->capacity ? c->capacity : 1;
+        const int Rw = c->walk_radius * refine;
         c->mask_stride = (cap + 31) & ~(size_t)31;
-        CU(c, cudaMalloc(&c->masks, (size_t)(kMaskCols + 1) * c->mask_stride * sizeof(uint2)));
-        CU(c, cudaMalloc(&c->fab, cap * sizeof(ForceRec)));
+        const size_t need = (size_t)(mask_cols(Rw) + 1) * c->mask_stride * sizeof(uint32_t) * mask_words(Rw);
+        if (need > c->mask_bytes) {
+            if (c->masks) { CU(c, cudaStreamSynchronize(c->stream)); cudaFree(c->masks); c->masks = nullptr; c->mask_bytes = 0; }
+            CU(c, cudaMalloc(&c->masks, need));
+            c->mask_bytes = need;
+        }
+        if (!c->fab) CU(c, cudaMalloc(&c->fab, cap * sizeof(ForceRec)));
     }
     if (c->debug_capture) { rc = ensure_debug(c); if (rc) return rc; }
 

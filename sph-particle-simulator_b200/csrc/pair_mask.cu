@@ -14,8 +14,9 @@
 //   * k_force_mask reads the 25 masks of its particle back (coalesced), and for every set bit evaluates the pair
 //     directly — no distance test, no rejected candidates; the per-column loop trip count is the popcount of
 //     the mask, so a warp runs max-over-lanes(popcount) iterations of pure pair arithmetic.
-// A column holding more than 64 candidates (collapsed states) sets the particle's overflow flag; the force pass
-// then walks that particle with the tested loop of variant 0, so results never depend on the mask capacity.
+// A column holding more candidates than its mask has bits (collapsed states, coincident wall layers) sets the
+// particle's overflow flag; the force pass then walks the candidates BEYOND the mask of each column with the tested
+// loop of variant 0, so results never depend on the mask capacity.
 //
 // Reference: SPHEngine::update_neighbor_lists' query + compute_densities + compute_pressures + compute_forces
 // (src/sph_engine.cpp:335-353, 203-244); the bitmask is this design's stand-in for neighbor_lists_[i].
@@ -26,10 +27,10 @@ namespace sphb {
 namespace {
 
 constexpr int kThreads = 128;
-constexpr int R = kMaskRadius;
 #ifndef SPHB_DENSITY_F32X2
 #define SPHB_DENSITY_F32X2 1
 #endif
+
 
 struct CellPos {
     int c0, c1, c2;
@@ -45,7 +46,7 @@ __device__ __forceinline__ CellPos key_order_cell(const GridDesc& g, const float
 
 // Calls body(col, valid, b, e) for the (2R+1)^2 columns around cell c in walk order; [b, e) is the slot run of
 // the column's 2R+1 cells (monotone ranks: always one run).  Invalid columns (outside the cell box) get b = e = 0.
-template <typename Body>
+template <int R, typename Body>
 __device__ __forceinline__ void walk_columns(const GridDesc& g, const uint32_t* __restrict__ cell_start, const CellPos& c,
                                              Body&& body) {
     const int za = max(c.c2 - R, g.lo[2]) - g.lo[2];
@@ -70,8 +71,20 @@ __device__ __forceinline__ void walk_columns(const GridDesc& g, const uint32_t* 
 #ifndef SPHB_DMASK_MINBLOCKS
 #define SPHB_DMASK_MINBLOCKS 1
 #endif
-template <bool SLAB>
+// mask storage: W = 1 -> one uint32 per (column, particle), W = 2 -> one uint2
+template <int W> struct MaskStore;
+template <> struct MaskStore<1> {
+    static __device__ __forceinline__ void put(void* base, size_t idx, uint32_t lo, uint32_t) { static_cast<uint32_t*>(base)[idx] = lo; }
+    static __device__ __forceinline__ uint2 get(const void* base, size_t idx) { return make_uint2(static_cast<const uint32_t*>(base)[idx], 0u); }
+};
+template <> struct MaskStore<2> {
+    static __device__ __forceinline__ void put(void* base, size_t idx, uint32_t lo, uint32_t hi) { static_cast<uint2*>(base)[idx] = make_uint2(lo, hi); }
+    static __device__ __forceinline__ uint2 get(const void* base, size_t idx) { return static_cast<const uint2*>(base)[idx]; }
+};
+
+template <bool SLAB, int R, int W>
 __global__ void __launch_bounds__(kThreads, SPHB_DMASK_MINBLOCKS) k_density_mask(PairArgs a) {
+    constexpr int kMaskCols = (2 * R + 1) * (2 * R + 1);
     const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
     unsigned count = 0;
     if (i < a.n) {
@@ -82,11 +95,9 @@ __global__ void __launch_bounds__(kThreads, SPHB_DMASK_MINBLOCKS) k_density_mask
             const float inv_h = a.k.inv_h;
             float rho = 0.0f;   // the self pair (d2 = 0) stays in the loop: the polynomial gives sigma * 4/6 there
             unsigned ovf = 0;
-            uint2* __restrict__ mrow = a.masks + i;
             const size_t stride = a.mask_stride;
             const float2 pxy = make_float2(pi.x, pi.y);
             const float2 nz2 = make_float2(a.k.neg_zero, a.k.neg_zero);
-            const float2 ninv_h2 = make_float2(-inv_h, -inv_h);
             // test + density contribution of slot j; returns whether j is a neighbour (exact reference test)
             auto visit = [&](uint32_t j) -> bool {
                 const float4 pj = __ldg(&a.posm[j]);
@@ -103,22 +114,13 @@ __global__ void __launch_bounds__(kThreads, SPHB_DMASK_MINBLOCKS) k_density_mask
 #endif
                 const bool in = d2 <= r2;
                 if (in) {
-#if SPHB_DENSITY_F32X2 >= 2
-                    // (2 - q, 1 - q) -> clamp -> cubes as packed pairs
-                    const float s = fast_sqrt(d2);
-                    float2 t = __ffma2_rn(make_float2(s, s), ninv_h2, make_float2(2.0f, 1.0f));
-                    t.x = fmaxf(t.x, 0.0f); t.y = fmaxf(t.y, 0.0f);
-                    const float2 t3 = __fmul2_rn(__fmul2_rn(t, t), t);
-                    rho += pj.w * (t3.x - 4.0f * t3.y);
-#else
                     const float q = fast_sqrt(d2) * inv_h;
                     const float t2 = fmaxf(2.0f - q, 0.0f), t1 = fmaxf(1.0f - q, 0.0f);
                     rho += pj.w * (t2 * t2 * t2 - 4.0f * (t1 * t1 * t1));
-#endif
                 }
                 return in;
             };
-            walk_columns(a.grid, a.cell_start, c, [&](int col, bool valid, uint32_t b, uint32_t e) {
+            walk_columns<R>(a.grid, a.cell_start, c, [&](int col, bool valid, uint32_t b, uint32_t e) {
                 uint32_t mlo = 0, mhi = 0;
                 if (valid) {
                     uint32_t j = b;
@@ -128,12 +130,14 @@ __global__ void __launch_bounds__(kThreads, SPHB_DMASK_MINBLOCKS) k_density_mask
                     for (; j < e1; ++j, bit += bit)
                         if (visit(j)) mlo |= bit;
                     if (j < e) {
-                        const uint32_t e2 = min(e, b + 64u);
-                        bit = 1u;
+                        if (W == 2) {
+                            const uint32_t e2 = min(e, b + 64u);
+                            bit = 1u;
 #pragma unroll 4
-                        for (; j < e2; ++j, bit += bit)
-                            if (visit(j)) mhi |= bit;
-                        if (j < e) {   // more than 64 candidates in this column: no mask for them
+                            for (; j < e2; ++j, bit += bit)
+                                if (visit(j)) mhi |= bit;
+                        }
+                        if (j < e) {   // more than 32 W candidates in this column: no mask for them
                             ovf = 1u;
                             for (; j < e; ++j)
                                 if (visit(j)) ++count;
@@ -141,9 +145,9 @@ __global__ void __launch_bounds__(kThreads, SPHB_DMASK_MINBLOCKS) k_density_mask
                     }
                     count += __popc(mlo) + __popc(mhi);
                 }
-                mrow[(size_t)col * stride] = make_uint2(mlo, mhi);
+                MaskStore<W>::put(a.masks, (size_t)col * stride + i, mlo, mhi);
             });
-            mrow[(size_t)kMaskCols * stride] = make_uint2(ovf, count);
+            MaskStore<W>::put(a.masks, (size_t)kMaskCols * stride + i, ovf, count);
             rho *= a.k.sigma * (1.0f / 6.0f);
             const float P = a.k.gas_constant * (rho - a.k.rest_density);
             a.rho_p[i] = make_float2(rho, P);
@@ -172,8 +176,9 @@ __device__ __forceinline__ ForceRec load_rec(const ForceRec* __restrict__ p) {
 #define SPHB_FORCE_PIPE 0
 #endif
 
-template <bool SLAB>
+template <bool SLAB, int R, int W>
 __global__ void __launch_bounds__(kThreads) k_force_mask(PairArgs a) {
+    constexpr int kMaskCols = (2 * R + 1) * (2 * R + 1);
     const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= a.n) return;
     const float4 vi = a.velid[i];
@@ -183,29 +188,28 @@ __global__ void __launch_bounds__(kThreads) k_force_mask(PairArgs a) {
     const CellPos c = key_order_cell(a.grid, pi);
     const GridDesc& g = a.grid;
     ForceAccum f = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-    const uint2* __restrict__ mrow = a.masks + i;
     const size_t stride = a.mask_stride;
-    const unsigned ovf = mrow[(size_t)kMaskCols * stride].x;
+    const unsigned ovf = MaskStore<W>::get(a.masks, (size_t)kMaskCols * stride + i).x;
     // pair j -> i without a distance test (j was accepted by the density pass)
     auto eval = [&](const ForceRec& q) {
         const float rx = pi.x - q.x, ry = pi.y - q.y, rz = pi.z - q.z;
         const float d2 = rx * rx + ry * ry + rz * rz;
         force_pair_fast(a.k, f, rx, ry, rz, d2, q.vx - vi.x, q.vy - vi.y, q.vz - vi.z, P_i, q.A, q.B);
     };
-    if (!ovf) {
-        // The 25 columns are consumed as 13 groups {column k, its point mirror 24 - k}: a lane close to one side of
+    {
+        // The (2R+1)^2 columns are consumed as groups {column k, its point mirror 24 - k}: a lane close to one side of
         // its cell has many neighbours in the columns on that side and few in the mirrored ones, so the SUM over a
         // mirror pair is nearly the same for all lanes of a warp.  Inside a group every lane pops its own bits as
-        // one flat stream (column k, then 24 - k), so the warp runs max-over-lanes(sum) iterations per group:
-        // ~300 per particle instead of ~450 with one lock-step loop per mask word (lattice, h = 2 dx).
+        // one flat stream (column k, then its mirror), so the warp runs max-over-lanes(sum) iterations per group:
+        // at R = 2 ~300 per particle instead of ~450 with one lock-step loop per mask word (lattice, h = 2 dx).
         const int za = max(c.c2 - R, g.lo[2]) - g.lo[2];
         const int r0 = c.c0 - g.lo[0], r1 = c.c1 - g.lo[1];
         int d0 = -R, d1 = -R;
 #pragma unroll 1
         for (int k = 0; k <= kMaskCols / 2; ++k) {
-            const uint2 mA = mrow[(size_t)k * stride];
+            const uint2 mA = MaskStore<W>::get(a.masks, (size_t)k * stride + i);
             uint2 mB = make_uint2(0u, 0u);
-            if (k < kMaskCols / 2) mB = mrow[(size_t)(kMaskCols - 1 - k) * stride];
+            if (k < kMaskCols / 2) mB = MaskStore<W>::get(a.masks, (size_t)(kMaskCols - 1 - k) * stride + i);
             // masks of columns outside the cell box are zero (written by the density pass), so a base is only
             // looked up for columns that exist
             uint32_t bA = 0, bB = 0;
@@ -215,15 +219,23 @@ __global__ void __launch_bounds__(kThreads) k_force_mask(PairArgs a) {
             uint32_t lo = mA.x, hi = mA.y, base = bA;
             uint32_t lo2 = mB.x, hi2 = mB.y;
             if ((lo | hi) == 0u) { lo = lo2; hi = hi2; base = bB; lo2 = 0u; hi2 = 0u; }
-            // pops the highest set bit of hi:lo and returns its slot
+            // pops the highest set bit of hi:lo and returns its slot (W == 1: hi is identically 0 and folds away)
             auto pop = [&]() -> uint32_t {
-                const bool up = hi != 0u;
-                uint32_t w = up ? hi : lo;
-                const int b = 31 - __clz(w);
-                w ^= 1u << b;
-                if (up) hi = w; else lo = w;
-                const uint32_t j = base + (uint32_t)b + (up ? 32u : 0u);
-                if ((lo | hi) == 0u) { lo = lo2; hi = hi2; base = bB; lo2 = 0u; hi2 = 0u; }
+                uint32_t j;
+                if (W == 2) {
+                    const bool up = hi != 0u;
+                    uint32_t w = up ? hi : lo;
+                    const int b = 31 - __clz(w);
+                    w ^= 1u << b;
+                    if (up) hi = w; else lo = w;
+                    j = base + (uint32_t)b + (up ? 32u : 0u);
+                    if ((lo | hi) == 0u) { lo = lo2; hi = hi2; base = bB; lo2 = 0u; hi2 = 0u; }
+                } else {
+                    const int b = 31 - __clz(lo);
+                    lo ^= 1u << b;
+                    j = base + (uint32_t)b;
+                    if (lo == 0u) { lo = lo2; base = bB; lo2 = 0u; }
+                }
                 return j;
             };
 #if SPHB_FORCE_PIPE
@@ -240,10 +252,13 @@ __global__ void __launch_bounds__(kThreads) k_force_mask(PairArgs a) {
             while (lo | hi) eval(load_rec(a.fab + pop()));
 #endif
         }
-    } else {
+    }
+    if (ovf) {
+        // some column of this particle holds more candidates than its mask has bits (collapsed states, coincident
+        // wall layers): the candidates beyond the mask are walked with the exact radius test, like variant 0
         const float r2 = a.k.r2;
-        walk_columns(a.grid, a.cell_start, c, [&](int col, bool valid, uint32_t b, uint32_t e) {
-            for (uint32_t j = b; j < e; ++j) {
+        walk_columns<R>(a.grid, a.cell_start, c, [&](int col, bool valid, uint32_t b, uint32_t e) {
+            for (uint32_t j = b + 32u * W; j < e; ++j) {
                 // positions from posm: in slab mode fab is only written where the density was evaluated (owned +
                 // first halo layer), which covers every ACCEPTED j of an owned particle but not every candidate
                 const float4 pj = __ldg(&a.posm[j]);
@@ -261,19 +276,37 @@ __global__ void __launch_bounds__(kThreads) k_force_mask(PairArgs a) {
 
 }  // namespace
 
+static_assert(SPHB_MASK_W4 == mask_words(4), "mask_words() and the kernels disagree");
+
 int launch_density_mask(const PairArgs& a, cudaStream_t st) {
     if (a.n == 0) return 0;
     const unsigned nb = (unsigned)((a.n + kThreads - 1) / kThreads);
-    if (a.slab_axis >= 0) k_density_mask<true><<<nb, kThreads, 0, st>>>(a);
-    else k_density_mask<false><<<nb, kThreads, 0, st>>>(a);
+    const bool slab = a.slab_axis >= 0;
+#define SPHB_LAUNCH_D(RR, WW)                                                 \
+    if (slab) k_density_mask<true, RR, WW><<<nb, kThreads, 0, st>>>(a);       \
+    else k_density_mask<false, RR, WW><<<nb, kThreads, 0, st>>>(a)
+    switch (a.walk_radius) {
+        case 2: SPHB_LAUNCH_D(2, 2); break;
+        case 3: SPHB_LAUNCH_D(3, 2); break;
+        default: SPHB_LAUNCH_D(4, SPHB_MASK_W4); break;
+    }
+#undef SPHB_LAUNCH_D
     return 1;
 }
 
 int launch_force_mask(const PairArgs& a, cudaStream_t st) {
     if (a.n == 0) return 0;
     const unsigned nb = (unsigned)((a.n + kThreads - 1) / kThreads);
-    if (a.slab_axis >= 0) k_force_mask<true><<<nb, kThreads, 0, st>>>(a);
-    else k_force_mask<false><<<nb, kThreads, 0, st>>>(a);
+    const bool slab = a.slab_axis >= 0;
+#define SPHB_LAUNCH_F(RR, WW)                                                 \
+    if (slab) k_force_mask<true, RR, WW><<<nb, kThreads, 0, st>>>(a);         \
+    else k_force_mask<false, RR, WW><<<nb, kThreads, 0, st>>>(a)
+    switch (a.walk_radius) {
+        case 2: SPHB_LAUNCH_F(2, 2); break;
+        case 3: SPHB_LAUNCH_F(3, 2); break;
+        default: SPHB_LAUNCH_F(4, SPHB_MASK_W4); break;
+    }
+#undef SPHB_LAUNCH_F
     return 1;
 }
 

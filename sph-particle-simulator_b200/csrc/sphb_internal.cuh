@@ -138,9 +138,9 @@ struct PairArgs {
     float4* fb2;               // vx, vy, vz, B' = A' P
     float4* acc;               // ax, ay, az, (unused)
     // variant 2: accepted-neighbour bitmasks handed from the density pass to the force pass, column-major:
-    // masks[col * mask_stride + slot], col = 0 .. kMaskCols-1 are the (2R+1)^2 cell columns in walk order (bit k =
-    // k-th candidate of the column run), col = kMaskCols is {overflow flag, 0}
-    uint2* masks;
+    // masks[col * mask_stride + slot], col = 0 .. mask_cols(R)-1 are the (2R+1)^2 cell columns in walk order (bit k =
+    // k-th candidate of the column run), col = mask_cols(R) is {overflow flag, neighbour count}
+    void* masks;               // uint2 per (column, particle) for R <= 3, uint32 for R = 4 (mask_words())
     size_t mask_stride;
     ForceRec* fab;             // variant 2: force-pass records, written by the density pass
     uint32_t* nbr_count;       // optional, per sorted slot
@@ -157,8 +157,13 @@ struct PairArgs {
 };
 int launch_density(const PairArgs& a, cudaStream_t st);
 int launch_force(const PairArgs& a, cudaStream_t st);
-constexpr int kMaskRadius = 2;                                           // variant 2 walks (2*2+1)^2 columns of 5 cells
-constexpr int kMaskCols = (2 * kMaskRadius + 1) * (2 * kMaskRadius + 1);
+// variant 2 walks (2R+1)^2 columns of 2R+1 cells, R = walk_radius * grid_refine in [kMaskMinRadius, kMaskMaxRadius]
+constexpr int kMaskMinRadius = 2, kMaskMaxRadius = 4;
+constexpr int mask_cols(int R) { return (2 * R + 1) * (2 * R + 1); }
+#ifndef SPHB_MASK_W4
+#define SPHB_MASK_W4 1
+#endif
+constexpr int mask_words(int R) { return R >= 4 ? SPHB_MASK_W4 : 2; }   // 32-bit words per column mask (a column holds ~(2R+1)/R^3 of a coarse cell)
 int launch_density_mask(const PairArgs& a, cudaStream_t st);
 int launch_force_mask(const PairArgs& a, cudaStream_t st);
 

@@ -298,3 +298,51 @@ def test_sparse_fluid_drop_multi_step(pkg, po):
     assert rel_err(fast["rho"], want["rho"]) <= 6 * TOL_RHO
     assert np.abs(fast["pos"].astype(np.float64) - want["pos"]).max() <= 6 * TOL_POS * 2.0
     ora.close(); cs.close(); cf.close()
+
+
+@pytest.mark.parametrize("refine", [1, 2, 3, 4])
+@pytest.mark.parametrize("name", ["cloud600", "cloud600_truncated_support", "dam_break_13k_tame"])
+def test_fast_mode_grid_refinements(pkg, name, refine):
+    """Default fast path (bitmask hand-off) on every internal grid: refine 2/3 use 64-bit column masks, refine 4 32-bit
+    ones, refine 1 falls back to the tested walk.  Neighbour sets must not depend on the grid; fields stay in the gates."""
+    g = load_golden(name)
+    prm = params_from(g["params"])
+    n = g["pos"].shape[0]
+    ctx = make_ctx(pkg, n, prm, strict=False, OPT_PAIR_KERNEL=2, OPT_GRID_REFINE=refine)
+    ctx.upload(g["pos"], g["vel"], g["mass"])
+    k0 = golden_steps(g)[0]
+    for k in range(k0 + 1):
+        ctx.step(float(g["dts"][k]))
+    d = ctx.debug_dump()
+    if k0 == 0:
+        assert_bits(d["perm"], stable_perm(g["s0_keys"]), f"{name} refine {refine} permutation")
+        assert_bits(d["nbr_count"], g["s0_counts"], f"{name} refine {refine} counts")
+    got = ctx.download()
+    want = {f: g[f"s{k0}_{f}"] for f in ("rho", "P", "acc", "pos", "vel")}
+    L = float(max(prm["xmax"] - prm["xmin"], prm["ymax"] - prm["ymin"], prm["zmax"] - prm["zmin"]))
+    check_fast(got, want, L, f"{name} refine {refine}")
+    ctx.close()
+
+
+@pytest.mark.parametrize("refine", [2, 4])
+def test_fast_mode_mask_overflow_falls_back(pkg, po, refine):
+    """A collapsed state: far more candidates per cell column than a column mask holds (64 / 32 bits).  Those particles
+    take the tested walk in the force pass; counts stay bit-exact and the fields stay inside the gates.  Half of the
+    cloud is dilute, so both paths run inside the same warps."""
+    rng = np.random.default_rng(11)
+    prm = dict(pkg.DEFAULT_PARAMS)
+    prm.update(smoothing_length=0.05, neighbor_search_radius=0.1, gas_constant=1e-3, viscosity=1e-6, particle_mass=1e-4,
+               xmin=-1.0, xmax=1.0, ymin=-1.0, ymax=1.0, zmin=-1.0, zmax=1.0)
+    dense = rng.uniform(-0.06, 0.06, size=(3000, 3))
+    dilute = rng.uniform(-0.9, 0.9, size=(3000, 3))
+    pos = np.concatenate([dense, dilute]).astype(np.float32)
+    vel = rng.normal(0, 0.1, size=pos.shape).astype(np.float32)
+    mass = np.full(len(pos), prm["particle_mass"], np.float32)
+    ora = po.Engine("port", len(pos)); ora.initialize(prm); ora.add_particles(pos, vel, mass)
+    ctx = make_ctx(pkg, len(pos), prm, strict=False, OPT_PAIR_KERNEL=2, OPT_GRID_REFINE=refine)
+    ctx.upload(pos, vel, mass)
+    ora.step(1e-4); ctx.step(1e-4)
+    assert_bits(ctx.debug_dump()["nbr_count"], ora.neighbor_counts(), "overflow counts")
+    assert ora.neighbor_counts().max() > 2000
+    check_fast(ctx.download(), ora.state(), 2.0, f"overflow refine {refine}")
+    ctx.close(); ora.close()
