@@ -687,10 +687,11 @@ int sphb_step(sphb_ctx* c, float dt) {
     launches += launch_cell_keys(n, c->posm[in], c->velid[in], g, c->sb.keys[0], c->sb.vals[0],
                                  c->debug_capture ? c->refkeys[in] : nullptr, dbg_ref_sort ? c->dbg_keys[0] : nullptr, gc, c->sc, st);
     int sorted = 0;
-    launches += c->sort_impl ? launch_radix_sort_onesweep(c->sb, n, g.id_bits + g.cell_bits, &sorted, c->sort_scratch, st)
+    // one-sweep: by the cell field only — k_reorder restores the id order inside each cell
+    launches += c->sort_impl ? launch_radix_sort_onesweep(c->sb, n, g.id_bits, g.cell_bits, &sorted, c->sort_scratch, st)
                              : launch_radix_sort(c->sb, n, g.id_bits + g.cell_bits, &sorted, st);
     launches += launch_cell_table(n, c->sb.keys[sorted], g, c->cell_start, c->sb.block_sums, st);
-    launches += launch_reorder(n, c->sb.vals[sorted], c->posm[in], c->velid[in], c->debug_capture ? c->refkeys[in] : nullptr,
+    launches += launch_reorder(n, c->sb.keys[sorted], g.id_bits, c->cell_start, c->sb.vals[sorted], c->posm[in], c->velid[in], c->debug_capture ? c->refkeys[in] : nullptr,
                                c->posm[outb], c->velid[outb], c->debug_capture ? c->refkeys[outb] : nullptr,
                                variant == 1 ? c->pp2 : nullptr, st);
     c->cur = outb;
@@ -700,7 +701,7 @@ int sphb_step(sphb_ctx* c, float dt) {
         SortBuffers ds = c->sb;
         ds.keys[0] = c->dbg_keys[0]; ds.keys[1] = c->dbg_keys[1];   // vals buffers are free again after the reorder
         int o = 0;
-        launches += c->sort_impl ? launch_radix_sort_onesweep(ds, n, gc.id_bits + gc.cell_bits, &o, c->sort_scratch, st)
+        launches += c->sort_impl ? launch_radix_sort_onesweep(ds, n, 0, gc.id_bits + gc.cell_bits, &o, c->sort_scratch, st)
                                  : launch_radix_sort(ds, n, gc.id_bits + gc.cell_bits, &o, st);
         c->dbg_sorted = o;
         c->dbg_id_bits = gc.id_bits;

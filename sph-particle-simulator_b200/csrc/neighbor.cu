@@ -94,14 +94,28 @@ __global__ void __launch_bounds__(kThreads) k_cell_ends(size_t n, const uint64_t
     if (c != cn) cell_start[c + 1] = (uint32_t)(s + 1);
 }
 
-__global__ void __launch_bounds__(kThreads) k_reorder(size_t n, const uint32_t* __restrict__ sorted_vals,
+// The radix sort orders by CELL only (half the digit passes of a (cell, id) sort); the id order inside a cell — the
+// order of the reference's per-cell vectors (spatial_hash.cpp:19-24), which fixes the summation order — is restored
+// here: a particle's final slot is cell_start[cell] + (number of particles of its cell with a smaller key).  Cells
+// hold ~1 (refined fast grid) to ~64 (strict) particles; collapsed cells cost occupancy^2 reads, the same order as the
+// pair passes themselves.
+__global__ void __launch_bounds__(kThreads) k_reorder(size_t n, const uint64_t* __restrict__ sorted_keys, int id_bits,
+                                                      const uint32_t* __restrict__ cell_start,
+                                                      const uint32_t* __restrict__ sorted_vals,
                                                       const float4* __restrict__ posm_in, const float4* __restrict__ velid_in,
                                                       const uint64_t* __restrict__ refkeys_in, float4* __restrict__ posm_out,
                                                       float4* __restrict__ velid_out, uint64_t* __restrict__ refkeys_out,
                                                       float4* __restrict__ pp2_out) {
-    size_t s = (size_t)blockIdx.x * kThreads + threadIdx.x;
-    if (s >= n) return;
-    uint32_t src = sorted_vals[s];
+    size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    if (t >= n) return;
+    const uint32_t src = sorted_vals[t];
+    const uint64_t key = sorted_keys[t];
+    const uint32_t cell = (uint32_t)(key >> id_bits);
+    const uint32_t cs = cell_start[cell], ce = cell_start[cell + 1];
+    uint32_t rank = 0;
+    if (ce - cs > 1u)
+        for (uint32_t u = cs; u < ce; ++u) rank += (__ldg(&sorted_keys[u]) < key) ? 1u : 0u;
+    const size_t s = (size_t)cs + rank;
     const float4 p = posm_in[src];
     posm_out[s] = p;
     velid_out[s] = velid_in[src];
@@ -250,11 +264,11 @@ int launch_cell_table(size_t n, const uint64_t* sorted_keys, GridDesc g, uint32_
     return 1 + launch_scan_max_inclusive(cell_start, (size_t)g.ncells + 1, block_sums, st);
 }
 
-int launch_reorder(size_t n, const uint32_t* sorted_vals, const float4* posm_in, const float4* velid_in,
-                   const uint64_t* refkeys_in, float4* posm_out, float4* velid_out, uint64_t* refkeys_out, float4* pp2_out,
-                   cudaStream_t st) {
-    k_reorder<<<blocks_for(n, kThreads), kThreads, 0, st>>>(n, sorted_vals, posm_in, velid_in, refkeys_in, posm_out,
-                                                             velid_out, refkeys_out, pp2_out);
+int launch_reorder(size_t n, const uint64_t* sorted_keys, int id_bits, const uint32_t* cell_start, const uint32_t* sorted_vals,
+                   const float4* posm_in, const float4* velid_in, const uint64_t* refkeys_in, float4* posm_out, float4* velid_out,
+                   uint64_t* refkeys_out, float4* pp2_out, cudaStream_t st) {
+    k_reorder<<<blocks_for(n, kThreads), kThreads, 0, st>>>(n, sorted_keys, id_bits, cell_start, sorted_vals, posm_in, velid_in,
+                                                             refkeys_in, posm_out, velid_out, refkeys_out, pp2_out);
     return 1;
 }
 

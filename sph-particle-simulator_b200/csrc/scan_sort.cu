@@ -430,7 +430,8 @@ size_t onesweep_scratch_bytes(size_t n_max, int bits_max) {
     return (passes * 256 + passes * ntiles * 256) * sizeof(unsigned long long) + kMaxPasses * sizeof(unsigned int) + 64;
 }
 
-int launch_radix_sort_onesweep(const SortBuffers& sb, size_t n, int bits, int* out_buf, void* scratch, cudaStream_t st) {
+int launch_radix_sort_onesweep(const SortBuffers& sb, size_t n, int first_bit, int bits, int* out_buf, void* scratch,
+                               cudaStream_t st) {
     *out_buf = 0;
     if (n == 0) return 0;
     PassPlan plan;
@@ -438,7 +439,7 @@ int launch_radix_sort_onesweep(const SortBuffers& sb, size_t n, int bits, int* o
     if (plan.npasses > kMaxPasses) plan.npasses = kMaxPasses;
     for (int p = 0; p < plan.npasses; ++p) {
         const int nb = bits - 8 * p < 8 ? bits - 8 * p : 8;
-        plan.shift[p] = 8 * p;
+        plan.shift[p] = first_bit + 8 * p;
         plan.mask[p] = (1u << nb) - 1u;
     }
     const uint32_t ntiles = (uint32_t)((n + kSortTile - 1) / kSortTile);

@@ -95,10 +95,12 @@ constexpr int kScanTile = 4096;   // elements per CTA of the device-wide scan
 // LSD radix sort of (key, val) pairs by the low `bits` bits of key, 8 bits per pass, stable.
 // Input in buffers [0]; returns the index (0/1) of the buffer pair holding the result in *out_buf.
 int launch_radix_sort(const SortBuffers& sb, size_t n, int bits, int* out_buf, cudaStream_t st);
-// Same contract, one scatter kernel per digit with decoupled look-back; the first pass generates vals = slot itself
-// (the caller need not fill vals[0]).  scratch must hold onesweep_scratch_bytes(n_max, bits_max).
+// Stable sort by the key bits [first_bit, first_bit + bits), one scatter kernel per 8-bit digit with decoupled
+// look-back; the first pass generates vals = slot itself (the caller need not fill vals[0]).  scratch must hold
+// onesweep_scratch_bytes(n_max, bits_max).
 size_t onesweep_scratch_bytes(size_t n_max, int bits_max);
-int launch_radix_sort_onesweep(const SortBuffers& sb, size_t n, int bits, int* out_buf, void* scratch, cudaStream_t st);
+int launch_radix_sort_onesweep(const SortBuffers& sb, size_t n, int first_bit, int bits, int* out_buf, void* scratch,
+                               cudaStream_t st);
 
 // out[i] = sum(in[0..i-1]) (exclusive) or out[i] = max(in[0..i]) (inclusive); in == out allowed.
 int launch_scan_sum_exclusive(uint32_t* data, size_t n, uint32_t* block_sums, cudaStream_t st);
@@ -113,9 +115,12 @@ int launch_cell_keys(size_t n, const float4* posm, const float4* velid, GridDesc
 // cell_start has ncells + 1 entries; block_sums is scan scratch.
 int launch_cell_table(size_t n, const uint64_t* sorted_keys, GridDesc g, uint32_t* cell_start, uint32_t* block_sums,
                       cudaStream_t st);
-int launch_reorder(size_t n, const uint32_t* sorted_vals, const float4* posm_in, const float4* velid_in,
-                   const uint64_t* refkeys_in, float4* posm_out, float4* velid_out, uint64_t* refkeys_out, float4* pp2_out,
-                   cudaStream_t st);
+// sorted_keys need only be sorted by their cell field (key >> id_bits): the reorder kernel ranks every particle among
+// the particles of its cell by full key (= by id) and writes it to cell_start[cell] + rank, so the final layout is the
+// (cell, id) order whether or not the sort looked at the id bits.
+int launch_reorder(size_t n, const uint64_t* sorted_keys, int id_bits, const uint32_t* cell_start, const uint32_t* sorted_vals,
+                   const float4* posm_in, const float4* velid_in, const uint64_t* refkeys_in, float4* posm_out, float4* velid_out,
+                   uint64_t* refkeys_out, float4* pp2_out, cudaStream_t st);
 
 // variant 2: everything the force pass needs from a neighbour, in one 32-byte record (A = m / (2 rho), B = A * P)
 struct __align__(32) ForceRec {

@@ -1,3 +1,4 @@
-python bench.py > gpurun_out/bench_r1c.json 2> gpurun_out/bench_r1c.err; tail -1 gpurun_out/bench_r1c.json
-python bench.py --no-cpu --steps 10 --scene dam_break_10M 2>&1 | tail -1 > gpurun_out/bench_r1c_10M.json; python -c "import json; d=json.load(open('gpurun_out/bench_r1c_10M.json')); print('10M', d['value'], d['ms_per_step'], d['e2e']['value'], d['extra']['stage_ms_rank0'])"
-python bench.py --no-cpu --steps 10 --scene fluid_drop_1M 2>&1 | tail -1 > gpurun_out/bench_r1c_drop.json; python -c "import json; d=json.load(open('gpurun_out/bench_r1c_drop.json')); print('drop', d['value'], d['ms_per_step'], d['e2e']['value'], d['extra']['stage_ms_rank0'])"
+python -m pytest tests/ -x -q -m gpu 2>&1 | tail -3
+python bench.py --no-cpu --steps 10 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('dam', d['value'], d['ms_per_step'], d['extra']['stage_ms_rank0'])"
+python bench.py --no-cpu --steps 10 --math strict 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('strict', d['value'], d['ms_per_step'], d['extra']['stage_ms_rank0'])"
+python bench.py --no-cpu --steps 5 --scene dam_break_10M 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('10M', d['value'], d['ms_per_step'], d['extra']['stage_ms_rank0'])"
