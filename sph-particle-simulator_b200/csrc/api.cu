@@ -182,7 +182,7 @@ int host_cell(float p, float inv_cell) {
 
 // layout_major < 0: the reference layout (x, y, z key order, masked-key ranks).  layout_major = a: fast-mode layout
 // with physical axis a most significant and monotone ranks (see GridDesc).
-int make_grid(sphb_ctx* c, GridDesc* g, int refine, int layout_major = -1) {
+int make_grid(sphb_ctx* c, GridDesc* g, int refine, int layout_major = -1, int pad = 0) {
     const float cell = c->prm.neighbor_search_radius;
     if (!(cell > 0.0f)) return fail(c, SPHB_E_INVALID, "neighbor_search_radius must be > 0 (got %g)", (double)cell);
     g->ref_inv_cell = 1.0f / cell;  // SpatialHash::set_cell_size, reference spatial_hash.h:63-66
@@ -207,6 +207,12 @@ int make_grid(sphb_ctx* c, GridDesc* g, int refine, int layout_major = -1) {
         }
         if (lo < -kMaxCoord || hi >= kMaxCoord)
             return fail(c, SPHB_E_GRID, "cell coordinates [%d, %d] on axis %d exceed the 21-bit key range", lo, hi, a);
+        // the 0.1 % cell margin of a refined grid must dominate the fp32 rounding of p * inv_cell (relative 2^-24 of the
+        // coordinate): beyond 2^14 cells from the origin fall back to a coarser grid (the caller retries with refine - 1)
+        if (refine > 1 && (lo < -(1 << 14) || hi > (1 << 14)))
+            return fail(c, SPHB_E_GRID, "refined grid: cell coordinates [%d, %d] too far from the origin for the tie margin", lo, hi);
+        lo -= pad;   // guard cells of the fast-mode layout (always empty: positions are clamped into the box)
+        hi += pad;
         g->lo[a] = lo;
         g->hi[a] = hi;
         g->ext[a] = hi - lo + 1;
@@ -218,6 +224,7 @@ int make_grid(sphb_ctx* c, GridDesc* g, int refine, int layout_major = -1) {
                         (unsigned long long)kMaxCells);
     }
     g->monotone = layout_major >= 0 ? 1 : 0;
+    g->pad = pad;
     g->perm[0] = 0; g->perm[1] = 1; g->perm[2] = 2;
     if (layout_major == 1) { g->perm[0] = 1; g->perm[1] = 0; g->perm[2] = 2; }        // (y, x, z)
     else if (layout_major == 2) { g->perm[0] = 2; g->perm[1] = 0; g->perm[2] = 1; }   // (z, x, y)
@@ -650,7 +657,7 @@ int sphb_step(sphb_ctx* c, float dt) {
         const int Rw = c->walk_radius * refine;
         if (variant == 2 && (Rw < kMaskMinRadius || Rw > kMaskMaxRadius)) variant = 0;
         layout = (variant == 2) ? (c->slab_on ? c->slab.axis : c->layout_major) : -1;
-        rc = make_grid(c, &g, refine, layout);
+        rc = make_grid(c, &g, refine, layout, variant == 2 ? Rw : 0);
         if (rc != SPHB_E_GRID || refine == 1) break;
     }
     if (rc) return rc;

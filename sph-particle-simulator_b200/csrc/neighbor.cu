@@ -51,8 +51,8 @@ __device__ __forceinline__ uint32_t dense_cell(const GridDesc& g, const float4& 
     for (int k = 0; k < 3; ++k) {
         const int a = g.perm[k];
         int c = cell_coord(a == 0 ? p.x : (a == 1 ? p.y : p.z), g.inv_cell);
-        if (c < g.lo[k]) { c = g.lo[k]; *outside = true; }
-        if (c > g.hi[k]) { c = g.hi[k]; *outside = true; }
+        if (c < g.lo[k] + g.pad) { c = g.lo[k] + g.pad; *outside = true; }
+        if (c > g.hi[k] - g.pad) { c = g.hi[k] - g.pad; *outside = true; }
         cell = cell * (uint32_t)g.ext[k] + (uint32_t)grid_rank(g, k, c);
     }
     return cell;

@@ -32,38 +32,66 @@ constexpr int kThreads = 128;
 #endif
 
 
-struct CellPos {
-    int c0, c1, c2;
+// Static spherical stencil.  A particle in cell c can only have neighbours (distance <= nsr <= R cells) in cells whose
+// offset (d0, d1, d2) satisfies (|d0|-1)+^2 + (|d1|-1)+^2 + (|d2|-1)+^2 <= R^2 (the gap between two cells is at least
+// |d|-1 cell widths), so column (d0, d1) needs the cells |d2| <= reach(d0, d1) only — independent of the lane, hence free
+// of divergence.  R = 4: 613 of the 729 cells (4 corner columns drop out entirely), R = 3: 335 of 343, R = 2: all 125.
+// reach = -1: the column cannot contain a neighbour.  Tables in walk order (d0 outer, d1 inner).
+struct ReachTables {
+    signed char r2[25], r3[49], r4[81];
 };
+constexpr int isqrt_floor(int v) {
+    int r = 0;
+    while ((r + 1) * (r + 1) <= v) ++r;
+    return r;
+}
+constexpr int reach_of(int R, int d0, int d1) {
+    const int a0 = (d0 < 0 ? -d0 : d0) - 1, a1 = (d1 < 0 ? -d1 : d1) - 1;
+    const int rem = R * R - (a0 > 0 ? a0 * a0 : 0) - (a1 > 0 ? a1 * a1 : 0);
+    if (rem < 0) return -1;
+    const int z = isqrt_floor(rem) + 1;
+    return z < R ? z : R;
+}
+constexpr ReachTables make_reach_tables() {
+    ReachTables t{};
+    for (int d0 = -2; d0 <= 2; ++d0) for (int d1 = -2; d1 <= 2; ++d1) t.r2[(d0 + 2) * 5 + d1 + 2] = (signed char)reach_of(2, d0, d1);
+    for (int d0 = -3; d0 <= 3; ++d0) for (int d1 = -3; d1 <= 3; ++d1) t.r3[(d0 + 3) * 7 + d1 + 3] = (signed char)reach_of(3, d0, d1);
+    for (int d0 = -4; d0 <= 4; ++d0) for (int d1 = -4; d1 <= 4; ++d1) t.r4[(d0 + 4) * 9 + d1 + 4] = (signed char)reach_of(4, d0, d1);
+    return t;
+}
+__constant__ ReachTables kReach = make_reach_tables();
 
-__device__ __forceinline__ CellPos key_order_cell(const GridDesc& g, const float4& p) {
-    CellPos c;
-    c.c0 = clampi(cell_coord(pick_axis(p, g.perm[0]), g.inv_cell), g.lo[0], g.hi[0]);
-    c.c1 = clampi(cell_coord(pick_axis(p, g.perm[1]), g.inv_cell), g.lo[1], g.hi[1]);
-    c.c2 = clampi(cell_coord(pick_axis(p, g.perm[2]), g.inv_cell), g.lo[2], g.hi[2]);
-    return c;
+template <int R>
+__device__ __forceinline__ int column_reach(int col) {
+    return R == 2 ? kReach.r2[col] : (R == 3 ? kReach.r3[col] : kReach.r4[col]);
 }
 
-// Calls body(col, valid, b, e) for the (2R+1)^2 columns around cell c in walk order; [b, e) is the slot run of
-// the column's 2R+1 cells (monotone ranks: always one run).  Invalid columns (outside the cell box) get b = e = 0.
+// Linear index of the particle's cell in the (padded) cell table.  The fast-mode grid carries g.pad >= R empty cells
+// around the populated box on every axis, and the cell is clamped into the populated box exactly like the key kernel
+// does, so every cell of every column of the stencil exists in the table: no range checks in the walks.
+__device__ __forceinline__ uint32_t center_cell(const GridDesc& g, const float4& p) {
+    const int c0 = clampi(cell_coord(pick_axis(p, g.perm[0]), g.inv_cell), g.lo[0] + g.pad, g.hi[0] - g.pad) - g.lo[0];
+    const int c1 = clampi(cell_coord(pick_axis(p, g.perm[1]), g.inv_cell), g.lo[1] + g.pad, g.hi[1] - g.pad) - g.lo[1];
+    const int c2 = clampi(cell_coord(pick_axis(p, g.perm[2]), g.inv_cell), g.lo[2] + g.pad, g.hi[2] - g.pad) - g.lo[2];
+    return ((uint32_t)c0 * (uint32_t)g.ext[1] + (uint32_t)c1) * (uint32_t)g.ext[2] + (uint32_t)c2;
+}
+
+// Calls body(col, valid, b, e) for the (2R+1)^2 columns around cell `center` in walk order; [b, e) is the slot run of
+// the column's cells inside the spherical stencil (monotone ranks: always one contiguous run).
 template <int R, typename Body>
-__device__ __forceinline__ void walk_columns(const GridDesc& g, const uint32_t* __restrict__ cell_start, const CellPos& c,
+__device__ __forceinline__ void walk_columns(const GridDesc& g, const uint32_t* __restrict__ cell_start, uint32_t center,
                                              Body&& body) {
-    const int za = max(c.c2 - R, g.lo[2]) - g.lo[2];
-    const int zb = min(c.c2 + R, g.hi[2]) - g.lo[2] + 1;
+    const uint32_t e2 = (uint32_t)g.ext[2], e12 = (uint32_t)g.ext[1] * e2;
+    uint32_t row = center - (uint32_t)R * e12 - (uint32_t)R * e2;   // cell (c0 - R, c1 - R, c2)
     int col = 0;
-    for (int d0 = -R; d0 <= R; ++d0) {
-        const int x0 = c.c0 + d0;
-        const bool ok0 = x0 >= g.lo[0] && x0 <= g.hi[0];
-        const uint32_t base0 = (uint32_t)(x0 - g.lo[0]) * (uint32_t)g.ext[1];
-        for (int d1 = -R; d1 <= R; ++d1, ++col) {
-            const int x1 = c.c1 + d1;
-            if (ok0 && x1 >= g.lo[1] && x1 <= g.hi[1]) {
-                const uint32_t base = (base0 + (uint32_t)(x1 - g.lo[1])) * (uint32_t)g.ext[2];
-                body(col, true, __ldg(&cell_start[base + za]), __ldg(&cell_start[base + zb]));
-            } else {
-                body(col, false, 0u, 0u);
-            }
+#pragma unroll 1
+    for (int d0 = -R; d0 <= R; ++d0, row += e12) {
+        uint32_t idx = row;
+#pragma unroll 1
+        for (int d1 = -R; d1 <= R; ++d1, ++col, idx += e2) {
+            const int reach = column_reach<R>(col);
+            if (reach >= 0) body(col, true, __ldg(&cell_start[idx - reach]), __ldg(&cell_start[idx + reach + 1]));
+            else body(col, false, 0u, 0u);
         }
     }
 }
@@ -90,7 +118,7 @@ __global__ void __launch_bounds__(kThreads, SPHB_DMASK_MINBLOCKS) k_density_mask
     if (i < a.n) {
         const float4 pi = a.posm[i];
         if (!SLAB || wants_density(a, pi)) {
-            const CellPos c = key_order_cell(a.grid, pi);
+            const uint32_t c = center_cell(a.grid, pi);
             const float r2 = a.k.r2;
             const float inv_h = a.k.inv_h;
             float rho = 0.0f;   // the self pair (d2 = 0) stays in the loop: the polynomial gives sigma * 4/6 there
@@ -185,7 +213,7 @@ __global__ void __launch_bounds__(kThreads) k_force_mask(PairArgs a) {
     if (SLAB && is_ghost(vi)) return;   // slab mode: halo copies are never advanced here
     const float4 pi = a.posm[i];
     const float P_i = a.rho_p[i].y;
-    const CellPos c = key_order_cell(a.grid, pi);
+    const uint32_t c = center_cell(a.grid, pi);
     const GridDesc& g = a.grid;
     ForceAccum f = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
     const size_t stride = a.mask_stride;
@@ -202,20 +230,21 @@ __global__ void __launch_bounds__(kThreads) k_force_mask(PairArgs a) {
         // mirror pair is nearly the same for all lanes of a warp.  Inside a group every lane pops its own bits as
         // one flat stream (column k, then its mirror), so the warp runs max-over-lanes(sum) iterations per group:
         // at R = 2 ~300 per particle instead of ~450 with one lock-step loop per mask word (lattice, h = 2 dx).
-        const int za = max(c.c2 - R, g.lo[2]) - g.lo[2];
-        const int r0 = c.c0 - g.lo[0], r1 = c.c1 - g.lo[1];
-        int d0 = -R, d1 = -R;
+        const uint32_t e2 = (uint32_t)g.ext[2], e12 = (uint32_t)g.ext[1] * e2;
+        uint32_t off = (uint32_t)R * e12 + (uint32_t)R * e2;   // column k is at center - off, its mirror at center + off
+        int d1 = -R;
 #pragma unroll 1
         for (int k = 0; k <= kMaskCols / 2; ++k) {
             const uint2 mA = MaskStore<W>::get(a.masks, (size_t)k * stride + i);
             uint2 mB = make_uint2(0u, 0u);
             if (k < kMaskCols / 2) mB = MaskStore<W>::get(a.masks, (size_t)(kMaskCols - 1 - k) * stride + i);
-            // masks of columns outside the cell box are zero (written by the density pass), so a base is only
-            // looked up for columns that exist
-            uint32_t bA = 0, bB = 0;
-            if (mA.x | mA.y) bA = __ldg(&a.cell_start[((uint32_t)(r0 + d0) * (uint32_t)g.ext[1] + (uint32_t)(r1 + d1)) * (uint32_t)g.ext[2] + za]);
-            if (mB.x | mB.y) bB = __ldg(&a.cell_start[((uint32_t)(r0 - d0) * (uint32_t)g.ext[1] + (uint32_t)(r1 - d1)) * (uint32_t)g.ext[2] + za]);
-            if (++d1 > R) { d1 = -R; ++d0; }
+            // a column and its mirror have the same reach in the spherical stencil; masks of columns outside the
+            // stencil are zero (written by the density pass) and their bases are never used
+            const int reach = max(column_reach<R>(k), 0);
+            const uint32_t bA = __ldg(&a.cell_start[c - off - reach]);
+            const uint32_t bB = __ldg(&a.cell_start[c + off - reach]);
+            off -= e2;
+            if (++d1 > R) { d1 = -R; off -= e12 - (uint32_t)(2 * R + 1) * e2; }
             uint32_t lo = mA.x, hi = mA.y, base = bA;
             uint32_t lo2 = mB.x, hi2 = mB.y;
             if ((lo | hi) == 0u) { lo = lo2; hi = hi2; base = bB; lo2 = 0u; hi2 = 0u; }

@@ -35,6 +35,8 @@ struct GridDesc {
     int ext[3];            // hi - lo + 1
     int perm[3];           // physical axis at key position k
     int monotone;          // 1: rank = c - lo ; 0: the reference's masked-key order (non-negative cells first)
+    int pad;               // fast-mode layout: empty guard cells on every side of the populated box [lo + pad, hi - pad]
+                           // (>= the walk radius, so the stencil walks need no range checks); 0 otherwise
     uint32_t ncells;
     int id_bits;           // bits of the particle id inside the composite sort key
     int cell_bits;

@@ -1,2 +1,2 @@
-ncu --metrics gpu__time_duration.sum --clock-control none -s 0 -c 400 --csv --log-file gpurun_out/launches_r1c.csv python bench.py --no-cpu --steps 3 --warmup 3 > gpurun_out/b_r1c.log 2>&1
-tail -1 gpurun_out/b_r1c.log | cut -c1-300
+ncu --set full --clock-control none --import-source on -k regex:"k_(force|density)_mask" -s 6 -c 2 -o gpurun_out/prof_mask3 python bench.py --no-cpu --steps 2 --warmup 2 > gpurun_out/prof_mask3.log 2>&1
+tail -1 gpurun_out/prof_mask3.log | cut -c1-100
