@@ -30,6 +30,9 @@ constexpr int kThreads = 128;
 #ifndef SPHB_DENSITY_F32X2
 #define SPHB_DENSITY_F32X2 1
 #endif
+#ifndef SPHB_PIN_CONSTANTS
+#define SPHB_PIN_CONSTANTS 1
+#endif
 
 
 // Static spherical stencil.  A particle in cell c can only have neighbours (distance <= nsr <= R cells) in cells whose
@@ -99,6 +102,16 @@ __device__ __forceinline__ void walk_columns(const GridDesc& g, const uint32_t* 
 #ifndef SPHB_DMASK_MINBLOCKS
 #define SPHB_DMASK_MINBLOCKS 1
 #endif
+// Pins a loop-invariant value in a register: ptxas otherwise re-reads kernel parameters from the constant bank inside
+// the pair loops (one issue slot per use in kernels that are issue-bound).
+#if SPHB_PIN_CONSTANTS
+__device__ __forceinline__ float pin(float v) { asm volatile("" : "+f"(v)); return v; }
+template <typename T> __device__ __forceinline__ T* pin(T* p) { asm volatile("" : "+l"(p)); return p; }
+#else
+__device__ __forceinline__ float pin(float v) { return v; }
+template <typename T> __device__ __forceinline__ T* pin(T* p) { return p; }
+#endif
+
 // mask storage: W = 1 -> one uint32 per (column, particle), W = 2 -> one uint2
 template <int W> struct MaskStore;
 template <> struct MaskStore<1> {
@@ -119,16 +132,18 @@ __global__ void __launch_bounds__(kThreads, SPHB_DMASK_MINBLOCKS) k_density_mask
         const float4 pi = a.posm[i];
         if (!SLAB || wants_density(a, pi)) {
             const uint32_t c = center_cell(a.grid, pi);
-            const float r2 = a.k.r2;
-            const float inv_h = a.k.inv_h;
+            const float r2 = pin(a.k.r2);
+            const float inv_h = pin(a.k.inv_h);
+            const float4* __restrict__ posm = pin(a.posm);
             float rho = 0.0f;   // the self pair (d2 = 0) stays in the loop: the polynomial gives sigma * 4/6 there
             unsigned ovf = 0;
             const size_t stride = a.mask_stride;
             const float2 pxy = make_float2(pi.x, pi.y);
-            const float2 nz2 = make_float2(a.k.neg_zero, a.k.neg_zero);
+            const float nz = pin(a.k.neg_zero);
+            const float2 nz2 = make_float2(nz, nz);
             // test + density contribution of slot j; returns whether j is a neighbour (exact reference test)
             auto visit = [&](uint32_t j) -> bool {
-                const float4 pj = __ldg(&a.posm[j]);
+                const float4 pj = __ldg(&posm[j]);
 #if SPHB_DENSITY_F32X2
                 // (x, y) of a float4 load sit in an aligned register pair: one FADD2 + one FFMA2 (exact squares as
                 // fma(d, d, -0), see pair.cu) replace two FADDs + two FMULs; every rounding is the reference's
@@ -219,10 +234,20 @@ __global__ void __launch_bounds__(kThreads) k_force_mask(PairArgs a) {
     const size_t stride = a.mask_stride;
     const unsigned ovf = MaskStore<W>::get(a.masks, (size_t)kMaskCols * stride + i).x;
     // pair j -> i without a distance test (j was accepted by the density pass)
-    auto eval = [&](const ForceRec& q) {
+    const float inv_h = pin(a.k.inv_h), sig_h = pin(a.k.sig_h), cvis = pin(2.0f * a.k.viscosity * a.k.sig_h2);
+    const ForceRec* __restrict__ fab = pin(a.fab);
+    auto eval = [&](const ForceRec& q) {   // force_pair_fast (pair_math.cuh) with the constants held in registers
         const float rx = pi.x - q.x, ry = pi.y - q.y, rz = pi.z - q.z;
         const float d2 = rx * rx + ry * ry + rz * rz;
-        force_pair_fast(a.k, f, rx, ry, rz, d2, q.vx - vi.x, q.vy - vi.y, q.vz - vi.z, P_i, q.A, q.B);
+        const float inv_len = d2 >= 1e-12f ? fast_rsqrt(d2) : 0.0f;   // r_len >= 1e-6 (sph_engine.cpp:403)
+        const float qq = (d2 * inv_len) * inv_h;
+        const float t2 = fmaxf(2.0f - qq, 0.0f), t1 = fmaxf(1.0f - qq, 0.0f);
+        const float gq = 2.0f * (t1 * t1) - 0.5f * (t2 * t2);
+        const float lq = t2 - 4.0f * t1;
+        const float cp = (q.A * P_i + q.B) * (sig_h * gq * inv_len);
+        f.px -= cp * rx; f.py -= cp * ry; f.pz -= cp * rz;
+        const float cv = cvis * (q.A * lq);
+        f.vx += cv * (q.vx - vi.x); f.vy += cv * (q.vy - vi.y); f.vz += cv * (q.vz - vi.z);
     };
     {
         // The (2R+1)^2 columns are consumed as groups {column k, its point mirror 24 - k}: a lane close to one side of
@@ -233,11 +258,13 @@ __global__ void __launch_bounds__(kThreads) k_force_mask(PairArgs a) {
         const uint32_t e2 = (uint32_t)g.ext[2], e12 = (uint32_t)g.ext[1] * e2;
         uint32_t off = (uint32_t)R * e12 + (uint32_t)R * e2;   // column k is at center - off, its mirror at center + off
         int d1 = -R;
+        size_t ia = i, ib = (size_t)(kMaskCols - 1) * stride + i;   // mask rows of column k and of its mirror
 #pragma unroll 1
         for (int k = 0; k <= kMaskCols / 2; ++k) {
-            const uint2 mA = MaskStore<W>::get(a.masks, (size_t)k * stride + i);
+            const uint2 mA = MaskStore<W>::get(a.masks, ia);
             uint2 mB = make_uint2(0u, 0u);
-            if (k < kMaskCols / 2) mB = MaskStore<W>::get(a.masks, (size_t)(kMaskCols - 1 - k) * stride + i);
+            if (k < kMaskCols / 2) mB = MaskStore<W>::get(a.masks, ib);
+            ia += stride; ib -= stride;
             // a column and its mirror have the same reach in the spherical stencil; masks of columns outside the
             // stencil are zero (written by the density pass) and their bases are never used
             const int reach = max(column_reach<R>(k), 0);
@@ -270,15 +297,15 @@ __global__ void __launch_bounds__(kThreads) k_force_mask(PairArgs a) {
 #if SPHB_FORCE_PIPE
             bool have = (lo | hi) != 0u;
             ForceRec nxt;
-            if (have) nxt = load_rec(a.fab + pop());
+            if (have) nxt = load_rec(fab + pop());
             while (have) {
                 const ForceRec cur = nxt;
                 have = (lo | hi) != 0u;
-                if (have) nxt = load_rec(a.fab + pop());
+                if (have) nxt = load_rec(fab + pop());
                 eval(cur);
             }
 #else
-            while (lo | hi) eval(load_rec(a.fab + pop()));
+            while (lo | hi) eval(load_rec(fab + pop()));
 #endif
         }
     }
