@@ -164,11 +164,14 @@ def run_reference_arm(args):
 # our arm
 # ------------------------------------------------------------------------------------------------
 def scaled_scene(scenes, name: str, world: int, mode: str):
-    """N = 1: the named scene.  N > 1, weak scaling: the same geometry with dx shrunk by N^(1/3), i.e. about
-    N times the particles (per-GPU work fixed); strong scaling: the named scene split N ways."""
+    """N = 1: the named scene.  N > 1, weak scaling: the same geometry with dx shrunk so that the scene holds N times
+    the particles of the single-GPU scene (per-GPU work fixed); strong scaling: the named scene split N ways."""
     family, dx = scenes.SCENES[name]
     if world > 1 and mode == "weak":
-        dx = dx / world ** (1.0 / 3.0)
+        if family == "dam":
+            dx = scenes.dam_break_dx_for(world * scenes.dam_break_count(dx), dx / world ** (1.0 / 3.0))
+        else:
+            dx = dx / world ** (1.0 / 3.0)
     pos, mass, params, dt = scenes.dam_break_scene(dx) if family == "dam" else scenes.fluid_drop_scene(dx)
     return pos, mass, params, dt, dx
 

@@ -142,25 +142,30 @@ __global__ void __launch_bounds__(kThreads, SPHB_DMASK_MINBLOCKS) k_density_mask
             const float nz = pin(a.k.neg_zero);
             const float2 nz2 = make_float2(nz, nz);
             // test + density contribution of slot j; returns whether j is a neighbour (exact reference test)
-            auto visit = [&](uint32_t j) -> bool {
-                const float4 pj = __ldg(&posm[j]);
+            // exact reference radius test of slot j against this particle: returns d2, pj
+            auto dist2 = [&](const float4& pj) -> float {
 #if SPHB_DENSITY_F32X2
                 // (x, y) of a float4 load sit in an aligned register pair: one FADD2 + one FFMA2 (exact squares as
                 // fma(d, d, -0), see pair.cu) replace two FADDs + two FMULs; every rounding is the reference's
                 const float2 dxy = __fadd2_rn(pxy, make_float2(-pj.x, -pj.y));
                 const float2 sq = __ffma2_rn(dxy, dxy, nz2);
                 const float dz = __fsub_rn(pi.z, pj.z);
-                const float d2 = __fadd_rn(__fadd_rn(sq.x, sq.y), __fmul_rn(dz, dz));
+                return __fadd_rn(__fadd_rn(sq.x, sq.y), __fmul_rn(dz, dz));
 #else
-                const float dx = __fsub_rn(pi.x, pj.x), dy = __fsub_rn(pi.y, pj.y), dz = __fsub_rn(pi.z, pj.z);
-                const float d2 = dist2_exact(dx, dy, dz);
+                return dist2_exact(__fsub_rn(pi.x, pj.x), __fsub_rn(pi.y, pj.y), __fsub_rn(pi.z, pj.z));
 #endif
+            };
+            auto add = [&](float d2, float m) {
+                const float q = fast_sqrt(d2) * inv_h;
+                const float t2 = fmaxf(2.0f - q, 0.0f), t1 = fmaxf(1.0f - q, 0.0f);
+                rho += m * (t2 * t2 * t2 - 4.0f * (t1 * t1 * t1));
+            };
+            // test + density contribution of slot j; returns whether j is a neighbour
+            auto visit = [&](uint32_t j) -> bool {
+                const float4 pj = __ldg(&posm[j]);
+                const float d2 = dist2(pj);
                 const bool in = d2 <= r2;
-                if (in) {
-                    const float q = fast_sqrt(d2) * inv_h;
-                    const float t2 = fmaxf(2.0f - q, 0.0f), t1 = fmaxf(1.0f - q, 0.0f);
-                    rho += pj.w * (t2 * t2 * t2 - 4.0f * (t1 * t1 * t1));
-                }
+                if (in) add(d2, pj.w);
                 return in;
             };
             walk_columns<R>(a.grid, a.cell_start, c, [&](int col, bool valid, uint32_t b, uint32_t e) {

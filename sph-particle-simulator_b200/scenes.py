@@ -114,6 +114,23 @@ def dam_break_scene(dx: float):
     return pos, mass, params, params["timestep"]
 
 
+def dam_break_count(dx: float) -> int:
+    """Number of particles dam_break_scene(dx) yields (same fp32 int(size / spacing) arithmetic as the generators)."""
+    dxf = f32(dx)
+    n = lambda size: int(f32(size) / dxf)
+    wx, wy, wz = n(0.4), n(0.6), n(0.8)
+    return 2 * (wx * wy + wy * wz + wx * wz) + n(0.2) * n(0.4) * n(0.8)
+
+
+def dam_break_dx_for(count: int, dx_guess: float) -> float:
+    """Lattice spacing near dx_guess whose dam-break scene is closest to `count` particles (weak-scaling runs: N GPUs
+    get N times the particles of the single-GPU scene, not just dx / N^(1/3), which falls ~6 % short at N = 8 because
+    the wall layers grow with N^(2/3))."""
+    cand = np.linspace(0.9 * dx_guess, 1.1 * dx_guess, 4001)
+    err = [abs(dam_break_count(float(d)) - count) for d in cand]
+    return float(cand[int(np.argmin(err))])
+
+
 def fluid_drop_scene(dx: float):
     """S3 family: sphere of radius 0.1 centred (0, 0.5, 0) (sph_engine.cpp:56-61), h = 2.5 dx
     (the reference's 0.02 / 0.008 ratio), default [-1, 1]^3 bounds → sparse cell occupancy."""
