@@ -648,6 +648,10 @@ int sphb_step(sphb_ctx* c, float dt) {
     // strict mode keeps the reference's cell size so the device layout IS the reference order; fast mode
     // may sort on a finer grid (fewer candidates per particle) and walk refine x as many cells per axis
     int refine = (c->math_mode == 0) ? 1 : c->grid_refine;
+    // the mask kernels walk at most kMaskMaxRadius cells per axis: with a wider reference walk (SPHB_OPT_WALK_RADIUS 2 =
+    // the reference's own 125-cell query) refine only as far as they support
+    if (c->math_mode != 0 && c->pair_kernel == 2 && c->walk_radius * refine > kMaskMaxRadius && c->walk_radius <= kMaskMaxRadius)
+        refine = kMaskMaxRadius / c->walk_radius;
     // pair-kernel variant 2 (bitmask hand-off) walks R = walk_radius * refine cells per axis, R in [2, 4], and uses
     // the fast-mode layout.  A refined cell table that would be too large falls back to coarser grids.
     int variant = 0, layout = -1;
