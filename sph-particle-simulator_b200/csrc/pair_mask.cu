@@ -239,19 +239,23 @@ __global__ void __launch_bounds__(kThreads) k_force_mask(PairArgs a) {
     const size_t stride = a.mask_stride;
     const unsigned ovf = MaskStore<W>::get(a.masks, (size_t)kMaskCols * stride + i).x;
     // pair j -> i without a distance test (j was accepted by the density pass)
-    const float inv_h = pin(a.k.inv_h), sig_h = pin(a.k.sig_h), cvis = pin(2.0f * a.k.viscosity * a.k.sig_h2);
+    const float inv_h = pin(a.k.inv_h);
     const ForceRec* __restrict__ fab = pin(a.fab);
-    auto eval = [&](const ForceRec& q) {   // force_pair_fast (pair_math.cuh) with the constants held in registers
+    // force_pair_fast (pair_math.cuh) with the per-pair constant factors sigma/h and 2 mu sigma/h^2 taken out of the
+    // sums (applied once per particle below).  1/len uses max(d2, 1e-30): coincident particles (d2 = 0) get q = 0 and
+    // dW/dq(0) = 0, hence no pressure term, exactly like the reference's r_len < 1e-6 guard (sph_engine.cpp:403); a
+    // distinct pair closer than 1e-6 contributes |dW/dq| <= 2e-6 / h instead of nothing — far below the fast-mode gates.
+    auto eval = [&](const ForceRec& q) {
         const float rx = pi.x - q.x, ry = pi.y - q.y, rz = pi.z - q.z;
         const float d2 = rx * rx + ry * ry + rz * rz;
-        const float inv_len = d2 >= 1e-12f ? fast_rsqrt(d2) : 0.0f;   // r_len >= 1e-6 (sph_engine.cpp:403)
+        const float inv_len = fast_rsqrt(fmaxf(d2, 1e-30f));
         const float qq = (d2 * inv_len) * inv_h;
         const float t2 = fmaxf(2.0f - qq, 0.0f), t1 = fmaxf(1.0f - qq, 0.0f);
-        const float gq = 2.0f * (t1 * t1) - 0.5f * (t2 * t2);
-        const float lq = t2 - 4.0f * t1;
-        const float cp = (q.A * P_i + q.B) * (sig_h * gq * inv_len);
+        const float gq = 2.0f * (t1 * t1) - 0.5f * (t2 * t2);      // dW/dq / sigma
+        const float lq = t2 - 4.0f * t1;                            // d2W/dq2 / sigma
+        const float cp = (q.A * P_i + q.B) * (gq * inv_len);
         f.px -= cp * rx; f.py -= cp * ry; f.pz -= cp * rz;
-        const float cv = cvis * (q.A * lq);
+        const float cv = q.A * lq;
         f.vx += cv * (q.vx - vi.x); f.vy += cv * (q.vy - vi.y); f.vz += cv * (q.vz - vi.z);
     };
     {
@@ -313,6 +317,11 @@ __global__ void __launch_bounds__(kThreads) k_force_mask(PairArgs a) {
             while (lo | hi) eval(load_rec(fab + pop()));
 #endif
         }
+    }
+    f.px *= a.k.sig_h; f.py *= a.k.sig_h; f.pz *= a.k.sig_h;
+    {
+        const float cvis = 2.0f * a.k.viscosity * a.k.sig_h2;
+        f.vx *= cvis; f.vy *= cvis; f.vz *= cvis;
     }
     if (ovf) {
         // some column of this particle holds more candidates than its mask has bits (collapsed states, coincident
