@@ -346,3 +346,26 @@ def test_fast_mode_mask_overflow_falls_back(pkg, po, refine):
     assert ora.neighbor_counts().max() > 2000
     check_fast(ctx.download(), ora.state(), 2.0, f"overflow refine {refine}")
     ctx.close(); ora.close()
+
+
+def test_fast_mode_layout_major_axis(pkg):
+    """SPHB_OPT_LAYOUT_MAJOR only permutes the device's cell order: neighbour sets, keys and the reference-order
+    permutation are identical for every major axis, fields agree within the fast-mode gates, and the same axis twice
+    is bit-identical (what the slab == single-context parity relies on)."""
+    g = load_golden("dam_break_13k_tame")
+    prm = params_from(g["params"])
+    n = g["pos"].shape[0]
+    runs = []
+    for major in (0, 1, 2, 2):
+        ctx = make_ctx(pkg, n, prm, strict=False, OPT_LAYOUT_MAJOR=major)
+        ctx.upload(g["pos"], g["vel"], g["mass"])
+        ctx.step(float(g["dts"][0]))
+        runs.append((ctx.download(), ctx.debug_dump()))
+        ctx.close()
+    L = float(max(prm["xmax"] - prm["xmin"], prm["ymax"] - prm["ymin"], prm["zmax"] - prm["zmin"]))
+    for out, dbg in runs[1:]:
+        for f in ("keys", "perm", "nbr_count"):
+            assert_bits(dbg[f], runs[0][1][f], f"layout major: {f}")
+        check_fast(out, runs[0][0], L, "layout major")
+    for f in ("rho", "P", "acc", "pos", "vel"):
+        assert_bits(runs[2][0][f], runs[3][0][f], f"same layout twice: {f}")

@@ -45,3 +45,14 @@ def test_tame_params(scenes):
     assert p["xmin"] == -0.2 and p["zmax"] == 0.4
     pos, mass, prm, dt = scenes.make_scene("dam_break_13k")
     assert pos.shape == (13200, 3) and mass.shape == (13200,) and dt == prm["timestep"]
+
+
+def test_dam_break_count_and_weak_scaling_spacing(scenes):
+    """dam_break_count predicts the generator's yield exactly; the weak-scaling spacing gives N x the particles."""
+    for dx in (0.02, 0.013, 0.01, 0.0077):
+        assert scenes.dam_break_count(dx) == scenes.dam_break_scene(dx)[0].shape[0], dx
+    n1 = scenes.dam_break_count(0.004)
+    assert n1 == 1130000
+    for world in (2, 4, 8):
+        dx = scenes.dam_break_dx_for(world * n1, 0.004 / world ** (1.0 / 3.0))
+        assert abs(scenes.dam_break_count(dx) - world * n1) <= 0.005 * world * n1
