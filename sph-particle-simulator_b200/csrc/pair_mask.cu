@@ -26,7 +26,21 @@ namespace sphb {
 
 namespace {
 
-constexpr int kThreads = 128;
+#ifndef SPHB_MASK_THREADS
+#define SPHB_MASK_THREADS 128
+#endif
+constexpr int kThreads = SPHB_MASK_THREADS;
+#ifndef SPHB_DMASK_UNROLL
+#define SPHB_DMASK_UNROLL 4
+#endif
+#ifndef SPHB_FMASK_MINBLOCKS
+#define SPHB_FMASK_MINBLOCKS 12   // <= 40 registers: the force pass is latency-sensitive, 48 warps/SM beat 40 (0.68 -> 0.61 ms)
+#endif
+#ifndef SPHB_MASK_STREAMING
+#define SPHB_MASK_STREAMING 1
+#endif
+#define SPHB_PRAGMA(x) _Pragma(#x)
+#define SPHB_UNROLL_N(n) SPHB_PRAGMA(unroll n)
 #ifndef SPHB_DENSITY_F32X2
 #define SPHB_DENSITY_F32X2 1
 #endif
@@ -115,12 +129,24 @@ template <typename T> __device__ __forceinline__ T* pin(T* p) { return p; }
 // mask storage: W = 1 -> one uint32 per (column, particle), W = 2 -> one uint2
 template <int W> struct MaskStore;
 template <> struct MaskStore<1> {
+    // masks are written once and read once: streaming (evict-first) accesses keep them from displacing the particle
+    // records that the pair loops re-read from L1 / L2
+#if SPHB_MASK_STREAMING
+    static __device__ __forceinline__ void put(void* base, size_t idx, uint32_t lo, uint32_t) { __stcs(static_cast<uint32_t*>(base) + idx, lo); }
+    static __device__ __forceinline__ uint2 get(const void* base, size_t idx) { return make_uint2(__ldcs(static_cast<const uint32_t*>(base) + idx), 0u); }
+#else
     static __device__ __forceinline__ void put(void* base, size_t idx, uint32_t lo, uint32_t) { static_cast<uint32_t*>(base)[idx] = lo; }
     static __device__ __forceinline__ uint2 get(const void* base, size_t idx) { return make_uint2(static_cast<const uint32_t*>(base)[idx], 0u); }
+#endif
 };
 template <> struct MaskStore<2> {
+#if SPHB_MASK_STREAMING
+    static __device__ __forceinline__ void put(void* base, size_t idx, uint32_t lo, uint32_t hi) { __stcs(static_cast<uint2*>(base) + idx, make_uint2(lo, hi)); }
+    static __device__ __forceinline__ uint2 get(const void* base, size_t idx) { return __ldcs(static_cast<const uint2*>(base) + idx); }
+#else
     static __device__ __forceinline__ void put(void* base, size_t idx, uint32_t lo, uint32_t hi) { static_cast<uint2*>(base)[idx] = make_uint2(lo, hi); }
     static __device__ __forceinline__ uint2 get(const void* base, size_t idx) { return static_cast<const uint2*>(base)[idx]; }
+#endif
 };
 
 template <bool SLAB, int R, int W>
@@ -174,7 +200,7 @@ __global__ void __launch_bounds__(kThreads, SPHB_DMASK_MINBLOCKS) k_density_mask
                     uint32_t j = b;
                     const uint32_t e1 = min(e, b + 32u);
                     uint32_t bit = 1u;
-#pragma unroll 4
+SPHB_UNROLL_N(SPHB_DMASK_UNROLL)
                     for (; j < e1; ++j, bit += bit)
                         if (visit(j)) mlo |= bit;
                     if (j < e) {
@@ -225,7 +251,7 @@ __device__ __forceinline__ ForceRec load_rec(const ForceRec* __restrict__ p) {
 #endif
 
 template <bool SLAB, int R, int W>
-__global__ void __launch_bounds__(kThreads) k_force_mask(PairArgs a) {
+__global__ void __launch_bounds__(kThreads, SPHB_FMASK_MINBLOCKS) k_force_mask(PairArgs a) {
     constexpr int kMaskCols = (2 * R + 1) * (2 * R + 1);
     const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= a.n) return;
