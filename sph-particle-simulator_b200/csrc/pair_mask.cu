@@ -1,19 +1,22 @@
 // Pair kernels, variant 2 (fast math, default): the density pass hands its accepted-neighbour sets to the
 // force pass as per-column bitmasks, so the radius test runs ONCE per step instead of twice.
 //
-// Why: both pair passes are instruction-issue bound (profiles/: ~86 % / 73 % issue-active, <1 % DRAM), and
-// ~1 000 candidates are tested per particle and pass to find ~270 neighbours.  In the one-thread-per-particle
-// walk the test costs ~12 warp-instructions per candidate and the divergent "accepted" branch is entered
-// whenever ANY lane accepts.  Here
+// Why: both pair passes are instruction-issue bound (profiles/: 85 % / 74 % issue-active, < 10 % DRAM).  The
+// tested walk of variant 0 examined ~1 000 candidates per particle and pass to find ~265 neighbours, paid ~12
+// warp-instructions per test and entered the divergent "accepted" branch whenever ANY lane accepted.  Here
+//   * the grid is refined to cells of nsr / R (default R = 4: ~1 particle per cell, so all lanes of a warp — 32
+//     consecutive particles along a cell column — see the same relative neighbourhood) and only the cells of a
+//     static spherical stencil are visited (613 of 9^3 at R = 4, constant tables, no per-lane divergence);
 //   * k_density_mask walks the (2R+1)^2 cell columns (each ONE contiguous run of the sorted arrays — the
-//     fast-mode layout uses monotone cell ranks, see GridDesc), evaluates the density exactly like variant 0,
-//     and additionally records, per column, which candidates passed the reference's exact radius test
-//     (spatial_hash.h:70-73) as a 64-bit mask.  Masks are stored column-major (masks[col][slot]) so that a warp
-//     writes one fully coalesced 256-byte row per column — the per-lane scattered stores that sank the
-//     neighbour-LIST hand-off do not occur;
-//   * k_force_mask reads the 25 masks of its particle back (coalesced), and for every set bit evaluates the pair
-//     directly — no distance test, no rejected candidates; the per-column loop trip count is the popcount of
-//     the mask, so a warp runs max-over-lanes(popcount) iterations of pure pair arithmetic.
+//     fast-mode layout uses monotone cell ranks and guard cells, see GridDesc), evaluates the density, and
+//     records per column which candidates passed the reference's exact radius test (spatial_hash.h:70-73) as a
+//     32-bit (R = 4) or 64-bit (R = 2, 3) mask.  Masks are stored column-major (masks[col][slot]) so that a warp
+//     writes one fully coalesced row per column — the per-lane scattered stores that sank the neighbour-LIST
+//     hand-off do not occur;
+//   * k_force_mask reads the masks of its particle back (coalesced) and evaluates exactly the set bits — no
+//     distance test, no rejected candidates: FLO -> slot -> one 32-byte LDG.E.256 record -> 31 flops.  Columns are
+//     consumed as mirror pairs with per-lane flat bit streams, which keeps the warp's lanes balanced when the
+//     particles are disordered.
 // A column holding more candidates than its mask has bits (collapsed states, coincident wall layers) sets the
 // particle's overflow flag; the force pass then walks the candidates BEYOND the mask of each column with the tested
 // loop of variant 0, so results never depend on the mask capacity.
