@@ -195,6 +195,10 @@ def run_ours(args):
     n_total = pos.shape[0]
     stream = torch.cuda.current_stream(dev)
     strict = args.math == "strict"
+    if args.refine <= 0:
+        # scene-level tuning: internal cells of about one lattice spacing (~1 particle per cell): nsr / dx = 4 for the
+        # dam-break scenes (h = 2 dx), 5 for the fluid drop (h = 2.5 dx)
+        args.refine = int(max(1, min(6, round(float(params["neighbor_search_radius"]) / dx))))
     opts = {capi.OPT_PAIR_KERNEL: args.pair_kernel, capi.OPT_GRID_REFINE: args.refine}
 
     if world == 1:
@@ -400,7 +404,7 @@ def main():
     ap.add_argument("--cpu-scene", default=None)
     ap.add_argument("--math", default="fast", choices=["fast", "strict"])
     ap.add_argument("--pair-kernel", type=int, default=2)
-    ap.add_argument("--refine", type=int, default=4)
+    ap.add_argument("--refine", type=int, default=0, help="internal grid refine 1..6; 0 = neighbor_search_radius / dx of the scene")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     args = ap.parse_args()

@@ -94,7 +94,8 @@ enum {
     /* fast mode only: the device sorts on an internal grid of cell size neighbor_search_radius / f and walks
      * (2 f + 1)^3 cells, which cuts the candidates per particle (27 r^3 at f = 1, 15.6 r^3 at 2, 11.4 r^3 at 4) and, with
      * ~1 particle per cell, makes the work of the lanes of a warp uniform.  The reference's 63-bit keys, its
-     * permutation and the neighbour sets are unaffected (1..4, default 4; a cell table that would be too large falls
+     * permutation and the neighbour sets are unaffected (1..6, default 4 — the optimum for h = 2 dx; denser kernels, e.g.
+     * h = 2.5 dx, gain from 5: the target is ~1 particle per internal cell; a cell table that would be too large falls
      * back to coarser grids; strict mode always uses 1 so that its layout and summation order are the reference's). */
     SPHB_OPT_GRID_REFINE = 6,
     /* fast mode, pair kernel 2: physical axis (0 = x, 1 = y, 2 = z) that is most significant in the device's

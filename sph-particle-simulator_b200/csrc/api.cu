@@ -449,7 +449,7 @@ int sphb_set_option(sphb_ctx* c, int option, int64_t value) {
             c->pair_kernel = (int)value;
             return SPHB_OK;
         case SPHB_OPT_GRID_REFINE:
-            if (value < 1 || value > 4) return fail(c, SPHB_E_INVALID, "grid refine must be 1..4");
+            if (value < 1 || value > 6) return fail(c, SPHB_E_INVALID, "grid refine must be 1..6");
             c->grid_refine = (int)value;
             return SPHB_OK;
         case SPHB_OPT_LAYOUT_MAJOR:

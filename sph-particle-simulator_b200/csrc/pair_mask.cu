@@ -58,7 +58,7 @@ constexpr int kThreads = SPHB_MASK_THREADS;
 // of divergence.  R = 4: 613 of the 729 cells (4 corner columns drop out entirely), R = 3: 335 of 343, R = 2: all 125.
 // reach = -1: the column cannot contain a neighbour.  Tables in walk order (d0 outer, d1 inner).
 struct ReachTables {
-    signed char r2[25], r3[49], r4[81];
+    signed char r2[25], r3[49], r4[81], r5[121], r6[169];
 };
 constexpr int isqrt_floor(int v) {
     int r = 0;
@@ -77,13 +77,15 @@ constexpr ReachTables make_reach_tables() {
     for (int d0 = -2; d0 <= 2; ++d0) for (int d1 = -2; d1 <= 2; ++d1) t.r2[(d0 + 2) * 5 + d1 + 2] = (signed char)reach_of(2, d0, d1);
     for (int d0 = -3; d0 <= 3; ++d0) for (int d1 = -3; d1 <= 3; ++d1) t.r3[(d0 + 3) * 7 + d1 + 3] = (signed char)reach_of(3, d0, d1);
     for (int d0 = -4; d0 <= 4; ++d0) for (int d1 = -4; d1 <= 4; ++d1) t.r4[(d0 + 4) * 9 + d1 + 4] = (signed char)reach_of(4, d0, d1);
+    for (int d0 = -5; d0 <= 5; ++d0) for (int d1 = -5; d1 <= 5; ++d1) t.r5[(d0 + 5) * 11 + d1 + 5] = (signed char)reach_of(5, d0, d1);
+    for (int d0 = -6; d0 <= 6; ++d0) for (int d1 = -6; d1 <= 6; ++d1) t.r6[(d0 + 6) * 13 + d1 + 6] = (signed char)reach_of(6, d0, d1);
     return t;
 }
 __constant__ ReachTables kReach = make_reach_tables();
 
 template <int R>
 __device__ __forceinline__ int column_reach(int col) {
-    return R == 2 ? kReach.r2[col] : (R == 3 ? kReach.r3[col] : kReach.r4[col]);
+    return R == 2 ? kReach.r2[col] : (R == 3 ? kReach.r3[col] : (R == 4 ? kReach.r4[col] : (R == 5 ? kReach.r5[col] : kReach.r6[col])));
 }
 
 // Linear index of the particle's cell in the (padded) cell table.  The fast-mode grid carries g.pad >= R empty cells
@@ -387,7 +389,9 @@ int launch_density_mask(const PairArgs& a, cudaStream_t st) {
     switch (a.walk_radius) {
         case 2: SPHB_LAUNCH_D(2, 2); break;
         case 3: SPHB_LAUNCH_D(3, 2); break;
-        default: SPHB_LAUNCH_D(4, SPHB_MASK_W4); break;
+        case 4: SPHB_LAUNCH_D(4, SPHB_MASK_W4); break;
+        case 5: SPHB_LAUNCH_D(5, 1); break;
+        default: SPHB_LAUNCH_D(6, 1); break;
     }
 #undef SPHB_LAUNCH_D
     return 1;
@@ -403,7 +407,9 @@ int launch_force_mask(const PairArgs& a, cudaStream_t st) {
     switch (a.walk_radius) {
         case 2: SPHB_LAUNCH_F(2, 2); break;
         case 3: SPHB_LAUNCH_F(3, 2); break;
-        default: SPHB_LAUNCH_F(4, SPHB_MASK_W4); break;
+        case 4: SPHB_LAUNCH_F(4, SPHB_MASK_W4); break;
+        case 5: SPHB_LAUNCH_F(5, 1); break;
+        default: SPHB_LAUNCH_F(6, 1); break;
     }
 #undef SPHB_LAUNCH_F
     return 1;

@@ -165,7 +165,7 @@ struct PairArgs {
 int launch_density(const PairArgs& a, cudaStream_t st);
 int launch_force(const PairArgs& a, cudaStream_t st);
 // variant 2 walks (2R+1)^2 columns of 2R+1 cells, R = walk_radius * grid_refine in [kMaskMinRadius, kMaskMaxRadius]
-constexpr int kMaskMinRadius = 2, kMaskMaxRadius = 4;
+constexpr int kMaskMinRadius = 2, kMaskMaxRadius = 6;
 constexpr int mask_cols(int R) { return (2 * R + 1) * (2 * R + 1); }
 #ifndef SPHB_MASK_W4
 #define SPHB_MASK_W4 1

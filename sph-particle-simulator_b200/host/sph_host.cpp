@@ -275,11 +275,22 @@ void SPHEngine::initialize(const SPHParameters& params) {
     reset_performance_stats();
 }
 
+// Device-side tuning only (no effect on results beyond the fast-mode summation order): internal cells of about one
+// lattice spacing, i.e. ~1 particle per cell (include/sphb.h, SPHB_OPT_GRID_REFINE).
+void SPHEngine::tune_grid(float spacing) {
+    const float r = params_.neighbor_search_radius / spacing;
+    int refine = (int)(r + 0.5f);
+    if (refine < 1) refine = 1;
+    if (refine > 6) refine = 6;
+    sphb_set_option(ctx_, SPHB_OPT_GRID_REFINE, refine);
+}
+
 void SPHEngine::initialize_dam_break() {
     if (!initialized_) initialize(SPHParameters{});
     pull_from_device();
     particles_.clear();   // keeps time and step count (sph_engine.cpp:47)
     particles_.add_particles(utils::create_dam_break_setup(glm::vec3(0.4f, 0.6f, 0.8f), glm::vec3(0.2f, 0.4f, 0.8f), 0.01f, params_));
+    tune_grid(0.01f);
     host_changed_ = true;
 }
 
@@ -288,6 +299,7 @@ void SPHEngine::initialize_fluid_drop() {
     pull_from_device();
     particles_.clear();
     particles_.add_particles(utils::create_fluid_drop_setup(glm::vec3(0.0f, 0.5f, 0.0f), 0.1f, 0.008f, params_));
+    tune_grid(0.008f);
     host_changed_ = true;
 }
 
@@ -296,6 +308,7 @@ void SPHEngine::initialize_granular_flow() {
     pull_from_device();
     particles_.clear();
     particles_.add_particles(utils::create_granular_flow_setup(glm::vec3(0.3f, 0.4f, 0.8f), glm::vec3(1.0f, 1.0f, 1.0f), 0.012f, params_));
+    tune_grid(0.012f);
     host_changed_ = true;
 }
 

@@ -184,6 +184,7 @@ public:
 private:
     void push_to_device() const;     // host AoS → device, if the host side changed
     void pull_from_device() const;   // device → host AoS, if the device advanced
+    void tune_grid(float spacing);   // device grid refine from the generator's lattice spacing (tuning only)
     void push_params() const;
     [[noreturn]] void die(const char* what) const;
 
