@@ -178,6 +178,12 @@ int sphb_diagnostics(sphb_ctx* ctx, double* sum_density, double* kinetic, float*
  *   nbr_count[i] neighbour-list length of particle i, self included (spatial_hash.cpp:31-57)
  * Any pointer may be NULL. */
 int sphb_debug_dump(sphb_ctx* ctx, uint64_t* keys, uint32_t* perm, uint32_t* nbr_count);
+/* Test hook, no device needed: the static spherical stencil of the fast path for walk radius `radius` (2..6 = walk
+ * radius x grid refine).  reach[(d0 + radius) * (2 radius + 1) + d1 + radius] = largest |d2| visited in cell column
+ * (d0, d1), -1 = column skipped; *cell_scale = factor applied to refine / neighbor_search_radius to get the internal
+ * 1 / cell size.  Returns the number of columns, or SPHB_E_INVALID.  (Replaces nothing in the reference: its
+ * SpatialHash::query_squared, spatial_hash.cpp:31-57, visits the full cube of cells.) */
+int sphb_debug_stencil(int radius, int8_t* reach, float* cell_scale);
 
 /* ---- slab decomposition across GPUs (one context per GPU) ------------------------------------------
  * NEW, no reference counterpart: the reference is a single-process CPU program.  The domain is cut

@@ -43,7 +43,7 @@ ABI_SYMBOLS = (
     "sphb_set_stream", "sphb_synchronize", "sphb_set_params", "sphb_get_params", "sphb_upload",
     "sphb_upload_strided", "sphb_download", "sphb_download_strided", "sphb_size", "sphb_step", "sphb_run_steps",
     "sphb_get_time", "sphb_set_time", "sphb_cfl_timestep", "sphb_get_stats", "sphb_reset_stats",
-    "sphb_diagnostics", "sphb_debug_dump",
+    "sphb_diagnostics", "sphb_debug_dump", "sphb_debug_stencil",
     "sphb_set_slab", "sphb_upload_ids", "sphb_slab_append", "sphb_slab_exchange_pack", "sphb_slab_exchange_count",
     "sphb_slab_exchange_split", "sphb_get_cfl_state", "sphb_set_cfl_state",
     "sphb_slab_download",
@@ -114,6 +114,7 @@ def load_library() -> C.CDLL:
     L.sphb_reset_stats.argtypes = [vp]
     L.sphb_diagnostics.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), fp]
     L.sphb_debug_dump.argtypes = [vp, vp, vp, vp]
+    L.sphb_debug_stencil.argtypes = [C.c_int, vp, C.POINTER(C.c_float)]
     L.sphb_set_slab.argtypes = [vp, C.POINTER(SphbSlab)]
     L.sphb_upload_ids.argtypes = [vp, sz, vp, vp, vp, vp]
     L.sphb_get_cfl_state.argtypes = [vp, fp, fp, C.POINTER(C.c_int)]
@@ -133,6 +134,18 @@ def _ptr(a):
     if isinstance(a, int):
         return C.c_void_p(a)
     return C.c_void_p(a.ctypes.data)
+
+
+def debug_stencil(radius: int):
+    """(reach table int8[(2R+1), (2R+1)], cell scale) of the fast path's static spherical stencil — no GPU needed."""
+    L = load_library()
+    R = int(radius)
+    reach = np.zeros((2 * R + 1) ** 2, np.int8)
+    scale = C.c_float()
+    n = L.sphb_debug_stencil(R, _ptr(reach), C.byref(scale))
+    if n < 0:
+        raise ValueError(f"no stencil for radius {R}")
+    return reach.reshape(2 * R + 1, 2 * R + 1), float(scale.value)
 
 
 class Context:

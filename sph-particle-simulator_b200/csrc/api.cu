@@ -191,7 +191,7 @@ int make_grid(sphb_ctx* c, GridDesc* g, int refine, int layout_major = -1, int p
     // neighbor_search_radius apart (the q = 2 ties of lattice scenes) then differ by strictly less than `refine`
     // in p * inv_cell, so fp32 rounding of that product can never put them refine + 1 cells apart and outside the
     // (2 refine + 1)-cell walk.  The reference guards the same tie with a second ring of cells (spatial_hash.cpp:35).
-    if (refine > 1) g->inv_cell *= 0.9990234375f;   // 1 - 2^-10
+    if (refine > 1) g->inv_cell *= kRefinedCellScale;
     uint64_t ncells = 1;
     for (int a = 0; a < 3; ++a) {
         int lo = host_cell(c->box_min[a], g->inv_cell), hi = host_cell(c->box_max[a], g->inv_cell);
@@ -864,6 +864,13 @@ int sphb_diagnostics(sphb_ctx* c, double* sum_density, double* kinetic, float* m
         *max_speed = sqrtf(v2);
     }
     return SPHB_OK;
+}
+
+int sphb_debug_stencil(int radius, int8_t* reach, float* cell_scale) {
+    if (!reach || !cell_scale) return SPHB_E_INVALID;
+    *cell_scale = kRefinedCellScale;   // make_grid: refined cells are 1 / this times neighbor_search_radius / refine
+    const int n = stencil_reach_table(radius, reinterpret_cast<signed char*>(reach));
+    return n < 0 ? SPHB_E_INVALID : n;
 }
 
 int sphb_debug_dump(sphb_ctx* c, uint64_t* keys, uint32_t* perm, uint32_t* nbr_count) {

@@ -379,6 +379,16 @@ __global__ void __launch_bounds__(kThreads, SPHB_FMASK_MINBLOCKS) k_force_mask(P
 
 static_assert(SPHB_MASK_W4 == mask_words(4), "mask_words() and the kernels disagree");
 
+// Host copy of the stencil tables (the device reads the identical constexpr data from constant memory): lets the
+// CPU tests check the shipped stencil against a brute-force model without a GPU.
+int stencil_reach_table(int R, signed char* out) {
+    constexpr ReachTables t = make_reach_tables();
+    const signed char* src = R == 2 ? t.r2 : R == 3 ? t.r3 : R == 4 ? t.r4 : R == 5 ? t.r5 : R == 6 ? t.r6 : nullptr;
+    if (!src) return -1;
+    for (int k = 0; k < mask_cols(R); ++k) out[k] = src[k];
+    return mask_cols(R);
+}
+
 int launch_density_mask(const PairArgs& a, cudaStream_t st) {
     if (a.n == 0) return 0;
     const unsigned nb = (unsigned)((a.n + kThreads - 1) / kThreads);

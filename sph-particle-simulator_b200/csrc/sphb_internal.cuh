@@ -166,11 +166,13 @@ int launch_density(const PairArgs& a, cudaStream_t st);
 int launch_force(const PairArgs& a, cudaStream_t st);
 // variant 2 walks (2R+1)^2 columns of 2R+1 cells, R = walk_radius * grid_refine in [kMaskMinRadius, kMaskMaxRadius]
 constexpr int kMaskMinRadius = 2, kMaskMaxRadius = 6;
+constexpr float kRefinedCellScale = 0.9990234375f;   // 1 - 2^-10: refined cells are this much larger than nsr / refine (make_grid)
 constexpr int mask_cols(int R) { return (2 * R + 1) * (2 * R + 1); }
 #ifndef SPHB_MASK_W4
 #define SPHB_MASK_W4 1
 #endif
 constexpr int mask_words(int R) { return R >= 4 ? SPHB_MASK_W4 : 2; }   // 32-bit words per column mask (a column holds ~(2R+1)/R^3 of a coarse cell)
+int stencil_reach_table(int R, signed char* out);   // host: copies the (2R+1)^2 column reaches, returns their number or -1
 int launch_density_mask(const PairArgs& a, cudaStream_t st);
 int launch_force_mask(const PairArgs& a, cudaStream_t st);
 
