@@ -244,7 +244,8 @@ def step_distributed(r: SlabRank, dt: float, group=None):
         r.store.exchange_count(r.cuts, me, r.d_counts)
         dist.all_gather_into_tensor(r.d_table.view(-1), r.d_counts, group=group)
         r.h_table.copy_(r.d_table, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
+        if dev.type == "cuda":
+            torch.cuda.current_stream(dev).synchronize()
         table = r.h_table.numpy().astype(np.int64)
         r.store.exchange_split(r.cuts, me, table[me], r.send)
         table[me, 2 * me] = 0                                        # kept in place, not sent

@@ -61,6 +61,16 @@ class NumpyStore:
         self.ghost = np.zeros(len(self.rec), bool)
         return counts
 
+    # two-phase form (sphb_slab_exchange_count / _split): the routing is computed once, by the count phase
+    def exchange_count(self, cuts, me, d_counts):
+        self._staged = torch.zeros((max(3 * len(self.rec), 16), 8), dtype=torch.float32)
+        counts = self.exchange_pack(cuts, me, self._staged)
+        d_counts.copy_(torch.from_numpy(counts.astype(np.int32)))
+
+    def exchange_split(self, cuts, me, counts, buf):
+        n_out = int(np.asarray(counts, np.int64).sum() - int(counts[2 * me]))
+        buf[:n_out].copy_(self._staged[:n_out])
+
     def append(self, buf, count, ghost=None):
         if not count:
             return
