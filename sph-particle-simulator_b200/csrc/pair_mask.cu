@@ -39,6 +39,9 @@ constexpr int kThreads = SPHB_MASK_THREADS;
 #ifndef SPHB_FMASK_MINBLOCKS
 #define SPHB_FMASK_MINBLOCKS 12   // <= 40 registers: the force pass is latency-sensitive, 48 warps/SM beat 40 (0.68 -> 0.61 ms)
 #endif
+#ifndef SPHB_DMASK_LEAN
+#define SPHB_DMASK_LEAN 0
+#endif
 #ifndef SPHB_MASK_STREAMING
 #define SPHB_MASK_STREAMING 1
 #endif
@@ -169,6 +172,9 @@ __global__ void __launch_bounds__(kThreads, SPHB_DMASK_MINBLOCKS) k_density_mask
             float rho = 0.0f;   // the self pair (d2 = 0) stays in the loop: the polynomial gives sigma * 4/6 there
             unsigned ovf = 0;
             const size_t stride = a.mask_stride;
+#if SPHB_DMASK_LEAN
+            size_t mi = i;   // walk_columns calls its body for every column in order: mi == col * stride + i
+#endif
             const float2 pxy = make_float2(pi.x, pi.y);
             const float nz = pin(a.k.neg_zero);
             const float2 nz2 = make_float2(nz, nz);
@@ -224,7 +230,14 @@ SPHB_UNROLL_N(SPHB_DMASK_UNROLL)
                     }
                     count += __popc(mlo) + __popc(mhi);
                 }
+#if SPHB_DMASK_LEAN
+                // round-2 experiment (off by default, not yet measured): running mask-row index instead of the 64-bit
+                // col * stride + i arithmetic that profiles/r1d_hot_regions.md shows in the per-column bookkeeping
+                MaskStore<W>::put(a.masks, mi, mlo, mhi);
+                mi += stride;
+#else
                 MaskStore<W>::put(a.masks, (size_t)col * stride + i, mlo, mhi);
+#endif
             });
             MaskStore<W>::put(a.masks, (size_t)kMaskCols * stride + i, ovf, count);
             rho *= a.k.sigma * (1.0f / 6.0f);
