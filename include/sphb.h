@@ -88,8 +88,7 @@ enum {
     SPHB_OPT_DEBUG_CAPTURE = 4,
     /* pair kernel variant (fast mode; strict always runs 0): 2 = the density pass hands the accepted-neighbour
      * sets to the force pass as per-column bitmasks, so the radius test runs once per step (default);
-     * 0 = tested per-thread walk in both passes; 1 = packed-f32x2 walk (measured slower on B200 — kept
-     * selectable).  All variants find identical neighbour sets. */
+     * 0 = tested per-thread walk in both passes.  Both find identical neighbour sets. */
     SPHB_OPT_PAIR_KERNEL = 5,
     /* fast mode only: the device sorts on an internal grid of cell size neighbor_search_radius / f and walks
      * (2 f + 1)^3 cells, which cuts the candidates per particle (27 r^3 at f = 1, 15.6 r^3 at 2, 11.4 r^3 at 4) and, with

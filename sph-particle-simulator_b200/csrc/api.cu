@@ -12,7 +12,6 @@
 #include "sphb_internal.cuh"
 
 namespace sphb {
-int launch_cfl_probe(DeviceScalars* sc, IntegrateConsts ic, cudaStream_t st);
 int launch_unpack_strided(size_t n, const unsigned char* d_base, size_t stride, size_t off_pos, size_t off_vel, size_t off_mass,
                           float4* posm, float4* velid, DeviceScalars* sc, cudaStream_t st);
 }
@@ -38,7 +37,7 @@ struct sphb_ctx {
     int walk_radius = 1;
     int stage_timing = 0;
     int debug_capture = 0;
-    int pair_kernel = 2;     // fast mode: 2 = bitmask hand-off density -> force (default), 0 = tested walk twice, 1 = packed f32x2
+    int pair_kernel = 2;     // fast mode: 2 = bitmask hand-off density -> force (default), 0 = tested walk twice
     int layout_major = 0;    // fast-mode layout: physical axis that is most significant in the cell order (slab mode: the slab axis)
     int grid_refine = 4;     // internal cell = neighbor_search_radius / grid_refine (fast mode; strict always 1)
 
@@ -46,11 +45,8 @@ struct sphb_ctx {
     float4* velid[2] = {nullptr, nullptr};
     int cur = 0;
     float2* rho_p = nullptr;
-    float4* fa = nullptr;
+    float4* fa = nullptr;    // staging of the tested-walk kernels (strict mode, variant 0): allocated on first use
     float4* fb = nullptr;
-    float4* pp2 = nullptr;   // pair-interleaved mirrors (packed-f32x2 kernels)
-    float4* fa2 = nullptr;
-    float4* fb2 = nullptr;
     float4* acc = nullptr;
     void* masks = nullptr;       // variant 2: (mask_cols(R) + 1) rows of mask_stride accepted-neighbour masks
     size_t mask_bytes = 0;
@@ -61,9 +57,11 @@ struct sphb_ctx {
     uint64_t* dbg_keys[2] = {nullptr, nullptr};   // reference-order composite keys (debug capture with a refined grid)
     int dbg_sorted = -1;                          // which dbg_keys buffer holds the sorted keys of the last step, -1: layout order is the reference order
     int dbg_id_bits = 0;
-    SortBuffers sb{};
-    uint32_t* cell_start = nullptr;
-    size_t cell_cap = 0;
+    uint2* cell_ticket = nullptr;   // counting sort: {cell, ticket inside the cell} per particle
+    uint32_t* slot_src = nullptr;   // counting sort: particle that landed in each (cell-ordered) slot
+    uint32_t* dbg_vals[2] = {nullptr, nullptr};   // payload buffers of the debug radix sort
+    uint32_t* cell_start = nullptr; // dense cell table (ncells + 1 entries) followed by the scratch of its scan
+    size_t cell_cap = 0;            // bytes
     DeviceScalars* sc = nullptr;
     DeviceScalars* h_sc = nullptr;  // pinned mirror for read-back
     unsigned char* d_stage = nullptr;
@@ -80,8 +78,7 @@ struct sphb_ctx {
 
     bool slab_on = false;
     sphb_slab slab{};
-    void* sort_scratch = nullptr;       // one-sweep radix sort: global histograms, look-back status words, tickets
-    int sort_impl = 1;                  // 1 = one-sweep (default), 0 = multi-kernel (SPHB_SORT=legacy)
+    void* sort_scratch = nullptr;       // debug radix sort: global histograms, look-back status words, tickets
     unsigned int* d_counts = nullptr;   // 2 * kMaxRanks + 1 counters / cursors
 
     uint64_t step_count = 0;
@@ -145,6 +142,9 @@ int ensure_debug(sphb_ctx* c) {
     CU(c, cudaMalloc(&c->nbr_count, cap * sizeof(uint32_t)));
     CU(c, cudaMalloc(&c->dbg_keys[0], cap * sizeof(uint64_t)));
     CU(c, cudaMalloc(&c->dbg_keys[1], cap * sizeof(uint64_t)));
+    CU(c, cudaMalloc(&c->dbg_vals[0], cap * sizeof(uint32_t)));
+    CU(c, cudaMalloc(&c->dbg_vals[1], cap * sizeof(uint32_t)));
+    CU(c, cudaMalloc(&c->sort_scratch, onesweep_scratch_bytes(cap, 64)));
     CU(c, cudaMemset(c->refkeys[0], 0, cap * sizeof(uint64_t)));
     CU(c, cudaMemset(c->refkeys[1], 0, cap * sizeof(uint64_t)));
     CU(c, cudaMemset(c->nbr_count, 0, cap * sizeof(uint32_t)));
@@ -242,22 +242,21 @@ int make_grid(sphb_ctx* c, GridDesc* g, int refine, int layout_major = -1, int p
     return SPHB_OK;
 }
 
+// bytes of the cell table: ncells + 1 counters (rounded up to a 16-byte multiple) + the scratch of their scan
+size_t cell_table_bytes(const GridDesc& g, size_t* scratch_offset) {
+    const size_t entries = ((size_t)g.ncells + 1 + 3) & ~(size_t)3;
+    if (scratch_offset) *scratch_offset = entries * sizeof(uint32_t);
+    return entries * sizeof(uint32_t) + scan_scratch_bytes((size_t)g.ncells + 1);
+}
+
 int ensure_cell_table(sphb_ctx* c, const GridDesc& g) {
-    const size_t need = (size_t)g.ncells + 1;
-    const size_t need_bs = need / kScanTile + 2;
+    const size_t need = cell_table_bytes(g, nullptr);
     if (need > c->cell_cap) {
-        if (c->cell_start) cudaFree(c->cell_start);
+        if (c->cell_start) { CU(c, cudaStreamSynchronize(c->stream)); cudaFree(c->cell_start); }
         c->cell_start = nullptr;
         c->cell_cap = 0;
-        CU(c, cudaMalloc(&c->cell_start, need * sizeof(uint32_t)));
+        CU(c, cudaMalloc(&c->cell_start, need));
         c->cell_cap = need;
-    }
-    if (need_bs > c->sb.block_sums_cap) {
-        if (c->sb.block_sums) cudaFree(c->sb.block_sums);
-        c->sb.block_sums = nullptr;
-        c->sb.block_sums_cap = 0;
-        CU(c, cudaMalloc(&c->sb.block_sums, need_bs * sizeof(uint32_t)));
-        c->sb.block_sums_cap = need_bs;
     }
     return SPHB_OK;
 }
@@ -278,6 +277,7 @@ PairConsts make_pair_consts(const sphb_params& p) {
     k.sig_h = k.sigma / h;
     k.sig_h2 = k.sigma / k.h_sq;
     k.neg_zero = -0.0f;
+    k.r2_next = nextafterf(k.r2, INFINITY);
     return k;
 }
 
@@ -294,12 +294,12 @@ IntegrateConsts make_integrate_consts(const sphb_params& p) {
 void free_all(sphb_ctx* c) {
     cudaSetDevice(c->device);
     for (int i = 0; i < 2; ++i) {
-        cudaFree(c->posm[i]); cudaFree(c->velid[i]); cudaFree(c->refkeys[i]); cudaFree(c->dbg_keys[i]);
-        cudaFree(c->sb.keys[i]); cudaFree(c->sb.vals[i]);
+        cudaFree(c->posm[i]); cudaFree(c->velid[i]); cudaFree(c->refkeys[i]); cudaFree(c->dbg_keys[i]); cudaFree(c->dbg_vals[i]);
     }
-    cudaFree(c->pp2); cudaFree(c->fa2); cudaFree(c->fb2); cudaFree(c->masks); cudaFree(c->fab);
+    cudaFree(c->cell_ticket); cudaFree(c->slot_src);
+    cudaFree(c->masks); cudaFree(c->fab);
     cudaFree(c->rho_p); cudaFree(c->fa); cudaFree(c->fb); cudaFree(c->acc); cudaFree(c->nbr_count);
-    cudaFree(c->sb.counts); cudaFree(c->sb.block_sums); cudaFree(c->cell_start);
+    cudaFree(c->cell_start);
     cudaFree(c->sc); cudaFree(c->d_stage); cudaFree(c->d_box); cudaFree(c->d_counts); cudaFree(c->sort_scratch);
     if (c->h_sc) cudaFreeHost(c->h_sc);
     if (c->h_bounce) cudaFreeHost(c->h_bounce);
@@ -366,7 +366,6 @@ int sphb_create(sphb_ctx** out, size_t capacity, int device) {
     c->device = device;
     c->capacity = capacity;
     const size_t cap = capacity ? capacity : 1;
-    const size_t ntiles = (cap + kSortTile - 1) / kSortTile;
 #define CUC(call)                                                                                         \
     do {                                                                                                  \
         cudaError_t e2_ = (call);                                                                         \
@@ -379,38 +378,24 @@ int sphb_create(sphb_ctx** out, size_t capacity, int device) {
     } while (0)
     CUC(cudaSetDevice(device));
     for (int i = 0; i < 2; ++i) {
-        CUC(cudaMalloc(&c->posm[i], cap * sizeof(float4)));
+        // + 4 records: the pair kernels read candidates two at a time, one pair ahead, and may touch up to three
+        // records behind the last particle (k_reorder keeps slot n a massless, finite sentinel; the rest stay finite)
+        CUC(cudaMalloc(&c->posm[i], (cap + 4) * sizeof(float4)));
+        CUC(cudaMemset(c->posm[i], 0, (cap + 4) * sizeof(float4)));
         CUC(cudaMalloc(&c->velid[i], cap * sizeof(float4)));
-        CUC(cudaMalloc(&c->sb.keys[i], cap * sizeof(uint64_t)));
-        CUC(cudaMalloc(&c->sb.vals[i], cap * sizeof(uint32_t)));
     }
+    CUC(cudaMalloc(&c->cell_ticket, cap * sizeof(uint2)));
+    CUC(cudaMalloc(&c->slot_src, cap * sizeof(uint32_t)));
     CUC(cudaMalloc(&c->rho_p, cap * sizeof(float2)));
-    CUC(cudaMalloc(&c->fa, cap * sizeof(float4)));
-    CUC(cudaMalloc(&c->fb, cap * sizeof(float4)));
     CUC(cudaMalloc(&c->acc, cap * sizeof(float4)));
-    {   // pair records: ceil(cap/2) pairs of 32 B; zero-filled so the unused half of an odd tail is finite
-        const size_t pair_bytes = ((cap + 1) / 2) * 2 * sizeof(float4);
-        CUC(cudaMalloc(&c->pp2, pair_bytes));
-        CUC(cudaMalloc(&c->fa2, pair_bytes));
-        CUC(cudaMalloc(&c->fb2, pair_bytes));
-        CUC(cudaMemset(c->pp2, 0, pair_bytes));
-        CUC(cudaMemset(c->fa2, 0, pair_bytes));
-        CUC(cudaMemset(c->fb2, 0, pair_bytes));
-    }
     // densities_/pressures_/accelerations_ are value-initialised by initialize() (sph_engine.cpp:26-28)
     CUC(cudaMemset(c->rho_p, 0, cap * sizeof(float2)));
     CUC(cudaMemset(c->acc, 0, cap * sizeof(float4)));
-    c->sb.counts_cap = 256 * ntiles;
-    CUC(cudaMalloc(&c->sb.counts, c->sb.counts_cap * sizeof(uint32_t)));
-    c->sb.block_sums_cap = c->sb.counts_cap / kScanTile + 2;
-    CUC(cudaMalloc(&c->sb.block_sums, c->sb.block_sums_cap * sizeof(uint32_t)));
     CUC(cudaMalloc(&c->sc, sizeof(DeviceScalars)));
     CUC(cudaMemset(c->sc, 0, sizeof(DeviceScalars)));
     CUC(cudaMallocHost(&c->h_sc, sizeof(DeviceScalars)));
     memset(c->h_sc, 0, sizeof(DeviceScalars));
     CUC(cudaMalloc(&c->d_box, 6 * sizeof(int)));
-    CUC(cudaMalloc(&c->sort_scratch, onesweep_scratch_bytes(cap, 64)));
-    if (const char* e = std::getenv("SPHB_SORT")) c->sort_impl = (strcmp(e, "legacy") == 0) ? 0 : 1;
     CUC(cudaMalloc(&c->d_counts, (2 * kMaxRanks + 1) * sizeof(unsigned int)));
 #undef CUC
     *out = c;
@@ -445,7 +430,7 @@ int sphb_set_option(sphb_ctx* c, int option, int64_t value) {
             if (c->debug_capture) { cudaSetDevice(c->device); return ensure_debug(c); }
             return SPHB_OK;
         case SPHB_OPT_PAIR_KERNEL:
-            if (value < 0 || value > 2) return fail(c, SPHB_E_INVALID, "pair kernel variant must be 0, 1 or 2");
+            if (value != 0 && value != 2) return fail(c, SPHB_E_INVALID, "pair kernel variant must be 0 (tested walk) or 2 (bitmask hand-off)");
             c->pair_kernel = (int)value;
             return SPHB_OK;
         case SPHB_OPT_GRID_REFINE:
@@ -674,13 +659,22 @@ int sphb_step(sphb_ctx* c, float dt) {
         const size_t cap = c->capacity ? c->capacity : 1;
         const int Rw = c->walk_radius * refine;
         c->mask_stride = (cap + 31) & ~(size_t)31;
-        const size_t need = (size_t)(mask_cols(Rw) + 1) * c->mask_stride * sizeof(uint32_t) * mask_words(Rw);
+        const size_t need = mask_bytes_per_slot(Rw) * c->mask_stride;
         if (need > c->mask_bytes) {
             if (c->masks) { CU(c, cudaStreamSynchronize(c->stream)); cudaFree(c->masks); c->masks = nullptr; c->mask_bytes = 0; }
             CU(c, cudaMalloc(&c->masks, need));
             c->mask_bytes = need;
         }
-        if (!c->fab) CU(c, cudaMalloc(&c->fab, cap * sizeof(ForceRec)));
+        if (!c->fab) {
+            CU(c, cudaMalloc(&c->fab, cap * sizeof(ForceRec)));
+            CU(c, cudaMemsetAsync(c->fab, 0, cap * sizeof(ForceRec), c->stream));
+        }
+    } else if (!c->fa) {
+        const size_t cap = c->capacity ? c->capacity : 1;
+        CU(c, cudaMalloc(&c->fa, cap * sizeof(float4)));
+        CU(c, cudaMalloc(&c->fb, cap * sizeof(float4)));
+        CU(c, cudaMemsetAsync(c->fa, 0, cap * sizeof(float4), c->stream));
+        CU(c, cudaMemsetAsync(c->fb, 0, cap * sizeof(float4), c->stream));
     }
     if (c->debug_capture) { rc = ensure_debug(c); if (rc) return rc; }
 
@@ -691,29 +685,29 @@ int sphb_step(sphb_ctx* c, float dt) {
     cudaEvent_t* ev = c->stage_timing ? next_event_set(c) : nullptr;
     const bool timing = ev != nullptr;
 
-    launches += (dt <= 0.0f) ? launch_cfl_dt(c->sc, ic, st) : launch_set_dt(c->sc, dt, st);
-
     if (timing) cudaEventRecord(ev[0], st);
     const int in = c->cur, outb = c->cur ^ 1;
-    launches += launch_cell_keys(n, c->posm[in], c->velid[in], g, c->sb.keys[0], c->sb.vals[0],
-                                 c->debug_capture ? c->refkeys[in] : nullptr, dbg_ref_sort ? c->dbg_keys[0] : nullptr, gc, c->sc, st);
-    int sorted = 0;
-    // one-sweep: by the cell field only — k_reorder restores the id order inside each cell
-    launches += c->sort_impl ? launch_radix_sort_onesweep(c->sb, n, g.id_bits, g.cell_bits, &sorted, c->sort_scratch, st)
-                             : launch_radix_sort(c->sb, n, g.id_bits + g.cell_bits, &sorted, st);
-    launches += launch_cell_table(n, c->sb.keys[sorted], g, c->cell_start, c->sb.block_sums, st);
-    launches += launch_reorder(n, c->sb.keys[sorted], g.id_bits, c->cell_start, c->sb.vals[sorted], c->posm[in], c->velid[in], c->debug_capture ? c->refkeys[in] : nullptr,
-                               c->posm[outb], c->velid[outb], c->debug_capture ? c->refkeys[outb] : nullptr,
-                               variant == 1 ? c->pp2 : nullptr, st);
+    // counting sort by cell: count (+ the step's dt) -> scan -> scatter -> reorder (ids ascending inside each cell)
+    size_t scratch_off = 0;
+    const size_t table_bytes = cell_table_bytes(g, &scratch_off);
+    CU(c, cudaMemsetAsync(c->cell_start, 0, table_bytes, st));
+    launches += launch_cell_count(n, c->posm[in], c->velid[in], g, c->cell_ticket, c->cell_start,
+                                  c->debug_capture ? c->refkeys[in] : nullptr, dbg_ref_sort ? c->dbg_keys[0] : nullptr, gc, c->sc,
+                                  dt, ic, st);
+    launches += launch_scan_exclusive(c->cell_start, (size_t)g.ncells + 1, reinterpret_cast<unsigned char*>(c->cell_start) + scratch_off, st);
+    launches += launch_cell_scatter(n, c->cell_ticket, c->cell_start, c->slot_src, st);
+    launches += launch_reorder(n, c->slot_src, c->cell_ticket, c->cell_start, c->posm[in], c->velid[in],
+                               c->debug_capture ? c->refkeys[in] : nullptr, c->posm[outb], c->velid[outb],
+                               c->debug_capture ? c->refkeys[outb] : nullptr, st);
     c->cur = outb;
     if (timing) cudaEventRecord(ev[1], st);
     c->dbg_sorted = -1;
     if (dbg_ref_sort) {   // debug only: the reference-order permutation, by the same radix sort over (reference cell, id)
-        SortBuffers ds = c->sb;
-        ds.keys[0] = c->dbg_keys[0]; ds.keys[1] = c->dbg_keys[1];   // vals buffers are free again after the reorder
+        SortBuffers ds;
+        ds.keys[0] = c->dbg_keys[0]; ds.keys[1] = c->dbg_keys[1];
+        ds.vals[0] = c->dbg_vals[0]; ds.vals[1] = c->dbg_vals[1];
         int o = 0;
-        launches += c->sort_impl ? launch_radix_sort_onesweep(ds, n, 0, gc.id_bits + gc.cell_bits, &o, c->sort_scratch, st)
-                                 : launch_radix_sort(ds, n, gc.id_bits + gc.cell_bits, &o, st);
+        launches += launch_radix_sort_onesweep(ds, n, 0, gc.id_bits + gc.cell_bits, &o, c->sort_scratch, st);
         c->dbg_sorted = o;
         c->dbg_id_bits = gc.id_bits;
     }
@@ -726,9 +720,6 @@ int sphb_step(sphb_ctx* c, float dt) {
     pa.rho_p = c->rho_p;
     pa.fa = c->fa;
     pa.fb = c->fb;
-    pa.pp2 = c->pp2;
-    pa.fa2 = c->fa2;
-    pa.fb2 = c->fb2;
     pa.acc = c->acc;
     pa.masks = c->masks;
     pa.mask_stride = c->mask_stride;

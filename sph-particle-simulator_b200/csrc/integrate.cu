@@ -1,4 +1,5 @@
-// Fused leapfrog integration + AABB boundary clamp + CFL reduction, and the on-device timestep.
+// Fused leapfrog integration + AABB boundary clamp + CFL reduction (the on-device timestep rule lives in neighbor.cu:
+// k_cell_count sets the dt of a step).
 //
 // Replaces SPHEngine::integrate_leapfrog (reference src/sph_engine.cpp:290-310),
 // ParticleSystem::apply_boundary_conditions (src/particle.cpp:122-153, serial and untimed in the
@@ -88,42 +89,7 @@ __global__ void __launch_bounds__(kThreads) k_integrate(size_t n, float4* __rest
     }
 }
 
-__global__ void k_set_dt(DeviceScalars* sc, float dt) {
-    sc->dt = dt;
-    sc->max_v2_bits = 0u;  // consumed; k_integrate of this step accumulates the next value
-}
-
-// compute_cfl_timestep, sph_engine.cpp:312-333.  max|v| = sqrt(max |v|^2) because correctly rounded
-// sqrt is monotone; the force criterion reads accelerations_[0] only.
-__global__ void k_cfl_dt(DeviceScalars* sc, IntegrateConsts ic, int consume) {
-    const float max_velocity = __fsqrt_rn(__uint_as_float(sc->max_v2_bits));
-    const float dt_cfl = __fdiv_rn(__fmul_rn(ic.cfl, ic.h), __fadd_rn(max_velocity, 1e-6f));
-    const float a0 = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(sc->a0[0], sc->a0[0]), __fmul_rn(sc->a0[1], sc->a0[1])),
-                                          __fmul_rn(sc->a0[2], sc->a0[2])));
-    const float dt_force = __fmul_rn(ic.cfl, __fsqrt_rn(__fdiv_rn(ic.h, __fadd_rn(a0, 1e-6f))));
-    float m = dt_cfl;               // std::min({a, b, c}): first of the smallest
-    if (dt_force < m) m = dt_force;
-    if (ic.timestep < m) m = ic.timestep;
-    sc->dt = m;
-    if (consume) sc->max_v2_bits = 0u;
-}
-
 }  // namespace
-
-int launch_set_dt(DeviceScalars* sc, float dt, cudaStream_t st) {
-    k_set_dt<<<1, 1, 0, st>>>(sc, dt);
-    return 1;
-}
-
-int launch_cfl_dt(DeviceScalars* sc, IntegrateConsts ic, cudaStream_t st) {
-    k_cfl_dt<<<1, 1, 0, st>>>(sc, ic, 1);
-    return 1;
-}
-
-int launch_cfl_probe(DeviceScalars* sc, IntegrateConsts ic, cudaStream_t st) {
-    k_cfl_dt<<<1, 1, 0, st>>>(sc, ic, 0);
-    return 1;
-}
 
 int launch_integrate(size_t n, float4* posm, float4* velid, const float4* acc, IntegrateConsts ic, DeviceScalars* sc,
                      int* d_box_or_null, cudaStream_t st) {

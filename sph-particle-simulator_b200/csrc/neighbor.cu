@@ -25,6 +25,23 @@ __device__ __forceinline__ void block_max_v2(float v2, DeviceScalars* sc) {
     if ((threadIdx.x & 31) == 0 && bits > *(volatile unsigned int*)&sc->max_v2_bits) atomicMax(&sc->max_v2_bits, bits);
 }
 
+// compute_cfl_timestep, reference sph_engine.cpp:312-333: min(CFL h / (max|v| + 1e-6), CFL sqrt(h / (|a_0| + 1e-6)), timestep);
+// the force criterion reads accelerations_[0] only.  std::min({a, b, c}) returns the first of the smallest.
+__device__ __forceinline__ float cfl_timestep(const DeviceScalars* sc, const IntegrateConsts& ic) {
+    const float max_velocity = __fsqrt_rn(__uint_as_float(sc->max_v2_bits));
+    const float dt_cfl = __fdiv_rn(__fmul_rn(ic.cfl, ic.h), __fadd_rn(max_velocity, 1e-6f));
+    const float a0 = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(sc->a0[0], sc->a0[0]), __fmul_rn(sc->a0[1], sc->a0[1])),
+                                          __fmul_rn(sc->a0[2], sc->a0[2])));
+    const float dt_force = __fmul_rn(ic.cfl, __fsqrt_rn(__fdiv_rn(ic.h, __fadd_rn(a0, 1e-6f))));
+    float m = dt_cfl;
+    if (dt_force < m) m = dt_force;
+    if (ic.timestep < m) m = ic.timestep;
+    return m;
+}
+
+// sphb_cfl_timestep: evaluates the rule without consuming the running maximum
+__global__ void k_cfl_probe(DeviceScalars* sc, IntegrateConsts ic) { sc->dt = cfl_timestep(sc, ic); }
+
 __global__ void __launch_bounds__(kThreads) k_pack_upload(size_t n, const float* __restrict__ pos3,
                                                           const float* __restrict__ vel3, const float* __restrict__ mass,
                                                           float default_mass, float4* __restrict__ posm,
@@ -58,15 +75,32 @@ __device__ __forceinline__ uint32_t dense_cell(const GridDesc& g, const float4& 
     return cell;
 }
 
-__global__ void __launch_bounds__(kThreads) k_cell_keys(size_t n, const float4* __restrict__ posm,
-                                                        const float4* __restrict__ velid, GridDesc g,
-                                                        uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                                                        uint64_t* __restrict__ refkeys, uint64_t* __restrict__ ckeys, GridDesc gc,
-                                                        DeviceScalars* sc) {
+// ---- counting sort by cell (round 2; replaces the radix sort of (cell, id) keys on the per-step path) ----------------
+// SpatialHash::build (reference src/spatial_hash.cpp:15-25) pushes every particle index into its cell's vector.  The
+// device equivalent is a counting sort over the dense cell table:
+//   k_cell_count   cell of every particle + one atomic per particle on the cell's counter (the returned ticket is
+//                  the particle's provisional rank inside its cell), and the step's dt (fixed, or the CFL rule)
+//   scan           exclusive prefix sum of the counters, in place -> cell_start (one pass, decoupled look-back)
+//   k_cell_scatter slot_src[cell_start[cell] + ticket] = particle
+//   k_reorder      gathers the records into cell order; inside a cell the ascending-id order of the reference's
+//                  per-cell vectors (which fixes the summation order) is restored by ranking the cell's members
+// 150 B of traffic per particle and 4 kernels instead of ~250 B and 10 kernels for the radix-sort path.
+__global__ void __launch_bounds__(kThreads) k_cell_count(size_t n, const float4* __restrict__ posm,
+                                                         const float4* __restrict__ velid, GridDesc g,
+                                                         uint2* __restrict__ cell_ticket, uint32_t* __restrict__ cell_cnt,
+                                                         uint64_t* __restrict__ refkeys, uint64_t* __restrict__ ckeys, GridDesc gc,
+                                                         DeviceScalars* sc, float dt_fixed, IntegrateConsts ic) {
     size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i == 0) {
+        // dt of this step: the caller's, or compute_cfl_timestep (sph_engine.cpp:312-333) from the running max |v|^2 and
+        // accelerations_[0] of the previous step.  max |v| = sqrt(max |v|^2) because correctly rounded sqrt is monotone.
+        float dt = dt_fixed;
+        if (dt_fixed <= 0.0f) dt = cfl_timestep(sc, ic);
+        sc->dt = dt;
+        sc->max_v2_bits = 0u;   // consumed; k_integrate of this step accumulates the next value
+    }
     if (i >= n) return;
-    float4 p = posm[i];
-    unsigned id = __float_as_uint(velid[i].w) & 0x7FFFFFFFu;   // bit 31 marks halo copies in slab mode
+    const float4 p = posm[i];
     if (refkeys) {
         // SpatialHash::get_grid_coords + hash_position, reference spatial_hash.h:20-36
         const int cx = cell_coord(p.x, g.ref_inv_cell), cy = cell_coord(p.y, g.ref_inv_cell), cz = cell_coord(p.z, g.ref_inv_cell);
@@ -75,54 +109,51 @@ __global__ void __launch_bounds__(kThreads) k_cell_keys(size_t n, const float4* 
     bool outside = false;
     const uint32_t cell = dense_cell(g, p, &outside);
     if (outside) atomicOr(&sc->error_flags, 1u);
-    keys[i] = ((uint64_t)cell << g.id_bits) | (uint64_t)id;
-    vals[i] = (uint32_t)i;
-    if (ckeys) {   // (reference cell, id) composite: sorting it yields the reference-order permutation
+    cell_ticket[i] = make_uint2(cell, atomicAdd(&cell_cnt[cell], 1u));
+    if (ckeys) {   // debug: (reference cell, id) composite — sorting it yields the reference-order permutation
+        const unsigned id = __float_as_uint(velid[i].w) & 0x7FFFFFFFu;   // bit 31 marks halo copies in slab mode
         bool o2 = false;
         ckeys[i] = ((uint64_t)dense_cell(gc, p, &o2) << gc.id_bits) | (uint64_t)id;
     }
 }
 
-// cell_start[c + 1] = (last sorted slot of cell c) + 1; a max-scan then turns the table into
-// "number of particles in cells < c", valid for empty cells too.
-__global__ void __launch_bounds__(kThreads) k_cell_ends(size_t n, const uint64_t* __restrict__ sorted_keys, int id_bits,
-                                                        uint32_t* __restrict__ cell_start) {
-    size_t s = (size_t)blockIdx.x * kThreads + threadIdx.x;
-    if (s >= n) return;
-    uint32_t c = (uint32_t)(sorted_keys[s] >> id_bits);
-    uint32_t cn = (s + 1 < n) ? (uint32_t)(sorted_keys[s + 1] >> id_bits) : 0xFFFFFFFFu;
-    if (c != cn) cell_start[c + 1] = (uint32_t)(s + 1);
+__global__ void __launch_bounds__(kThreads) k_cell_scatter(size_t n, const uint2* __restrict__ cell_ticket,
+                                                           const uint32_t* __restrict__ cell_start,
+                                                           uint32_t* __restrict__ slot_src) {
+    size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    const uint2 ct = cell_ticket[i];
+    slot_src[cell_start[ct.x] + ct.y] = (uint32_t)i;
 }
 
-// The radix sort orders by CELL only (half the digit passes of a (cell, id) sort); the id order inside a cell — the
-// order of the reference's per-cell vectors (spatial_hash.cpp:19-24), which fixes the summation order — is restored
-// here: a particle's final slot is cell_start[cell] + (number of particles of its cell with a smaller key).  Cells
-// hold ~1 (refined fast grid) to ~64 (strict) particles; collapsed cells cost occupancy^2 reads, the same order as the
-// pair passes themselves.
-__global__ void __launch_bounds__(kThreads) k_reorder(size_t n, const uint64_t* __restrict__ sorted_keys, int id_bits,
+// Tickets are handed out in arrival order; the id order inside a cell — the order of the reference's per-cell vectors
+// (spatial_hash.cpp:19-24) — is restored here: a particle's final slot is cell_start[cell] + (number of members of its
+// cell with a smaller id).  Cells hold ~1 (refined fast grid) to ~64 (strict) particles; collapsed cells cost
+// occupancy^2 reads, the same order as the pair passes themselves.
+__global__ void __launch_bounds__(kThreads) k_reorder(size_t n, const uint32_t* __restrict__ slot_src,
+                                                      const uint2* __restrict__ cell_ticket,
                                                       const uint32_t* __restrict__ cell_start,
-                                                      const uint32_t* __restrict__ sorted_vals,
                                                       const float4* __restrict__ posm_in, const float4* __restrict__ velid_in,
                                                       const uint64_t* __restrict__ refkeys_in, float4* __restrict__ posm_out,
-                                                      float4* __restrict__ velid_out, uint64_t* __restrict__ refkeys_out,
-                                                      float4* __restrict__ pp2_out) {
+                                                      float4* __restrict__ velid_out, uint64_t* __restrict__ refkeys_out) {
     size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    // slot n is a massless sentinel: the pair kernels read candidates two at a time and may touch one slot past the
+    // last run (its contribution is masked, but it must be finite); the buffers hold capacity + 4 records
+    if (t == 0) posm_out[n] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     if (t >= n) return;
-    const uint32_t src = sorted_vals[t];
-    const uint64_t key = sorted_keys[t];
-    const uint32_t cell = (uint32_t)(key >> id_bits);
+    const uint32_t src = slot_src[t];
+    const uint32_t cell = cell_ticket[src].x;
     const uint32_t cs = cell_start[cell], ce = cell_start[cell + 1];
+    const float4 v = velid_in[src];
     uint32_t rank = 0;
-    if (ce - cs > 1u)
-        for (uint32_t u = cs; u < ce; ++u) rank += (__ldg(&sorted_keys[u]) < key) ? 1u : 0u;
-    const size_t s = (size_t)cs + rank;
-    const float4 p = posm_in[src];
-    posm_out[s] = p;
-    velid_out[s] = velid_in[src];
-    if (pp2_out) {   // pair-interleaved mirror {x0,x1,y0,y1 | z0,z1,m0,m1} for the packed-f32x2 pair kernels
-        float* f = reinterpret_cast<float*>(pp2_out) + 8 * (s >> 1) + (s & 1);
-        f[0] = p.x; f[2] = p.y; f[4] = p.z; f[6] = p.w;
+    if (ce - cs > 1u) {
+        const uint32_t id = __float_as_uint(v.w) & 0x7FFFFFFFu;
+        for (uint32_t u = cs; u < ce; ++u)
+            rank += ((__float_as_uint(__ldg(&velid_in[slot_src[u]].w)) & 0x7FFFFFFFu) < id) ? 1u : 0u;
     }
+    const size_t s = (size_t)cs + rank;
+    posm_out[s] = posm_in[src];
+    velid_out[s] = v;
     if (refkeys_in) refkeys_out[s] = refkeys_in[src];
 }
 
@@ -251,24 +282,29 @@ int launch_pack_upload(size_t n, const float* d_pos3, const float* d_vel3, const
     return 1;
 }
 
-int launch_cell_keys(size_t n, const float4* posm, const float4* velid, GridDesc g, uint64_t* keys, uint32_t* vals,
-                     uint64_t* refkeys_or_null, uint64_t* ckeys_or_null, GridDesc gc, DeviceScalars* sc, cudaStream_t st) {
-    k_cell_keys<<<blocks_for(n, kThreads), kThreads, 0, st>>>(n, posm, velid, g, keys, vals, refkeys_or_null, ckeys_or_null, gc, sc);
+int launch_cell_count(size_t n, const float4* posm, const float4* velid, GridDesc g, uint2* cell_ticket, uint32_t* cell_cnt,
+                      uint64_t* refkeys_or_null, uint64_t* ckeys_or_null, GridDesc gc, DeviceScalars* sc, float dt_fixed,
+                      IntegrateConsts ic, cudaStream_t st) {
+    k_cell_count<<<blocks_for(n, kThreads), kThreads, 0, st>>>(n, posm, velid, g, cell_ticket, cell_cnt, refkeys_or_null,
+                                                                ckeys_or_null, gc, sc, dt_fixed, ic);
     return 1;
 }
 
-int launch_cell_table(size_t n, const uint64_t* sorted_keys, GridDesc g, uint32_t* cell_start, uint32_t* block_sums,
-                      cudaStream_t st) {
-    cudaMemsetAsync(cell_start, 0, ((size_t)g.ncells + 1) * sizeof(uint32_t), st);
-    k_cell_ends<<<blocks_for(n, kThreads), kThreads, 0, st>>>(n, sorted_keys, g.id_bits, cell_start);
-    return 1 + launch_scan_max_inclusive(cell_start, (size_t)g.ncells + 1, block_sums, st);
+int launch_cell_scatter(size_t n, const uint2* cell_ticket, const uint32_t* cell_start, uint32_t* slot_src, cudaStream_t st) {
+    k_cell_scatter<<<blocks_for(n, kThreads), kThreads, 0, st>>>(n, cell_ticket, cell_start, slot_src);
+    return 1;
 }
 
-int launch_reorder(size_t n, const uint64_t* sorted_keys, int id_bits, const uint32_t* cell_start, const uint32_t* sorted_vals,
+int launch_reorder(size_t n, const uint32_t* slot_src, const uint2* cell_ticket, const uint32_t* cell_start,
                    const float4* posm_in, const float4* velid_in, const uint64_t* refkeys_in, float4* posm_out, float4* velid_out,
-                   uint64_t* refkeys_out, float4* pp2_out, cudaStream_t st) {
-    k_reorder<<<blocks_for(n, kThreads), kThreads, 0, st>>>(n, sorted_keys, id_bits, cell_start, sorted_vals, posm_in, velid_in,
-                                                             refkeys_in, posm_out, velid_out, refkeys_out, pp2_out);
+                   uint64_t* refkeys_out, cudaStream_t st) {
+    k_reorder<<<blocks_for(n, kThreads), kThreads, 0, st>>>(n, slot_src, cell_ticket, cell_start, posm_in, velid_in, refkeys_in,
+                                                             posm_out, velid_out, refkeys_out);
+    return 1;
+}
+
+int launch_cfl_probe(DeviceScalars* sc, IntegrateConsts ic, cudaStream_t st) {
+    k_cfl_probe<<<1, 1, 0, st>>>(sc, ic);
     return 1;
 }
 

@@ -1,13 +1,13 @@
-// Device-wide scan and hand-written LSD radix sort (key64, val32) for sm_100a.
+// Device-wide single-pass scan (cell table of the per-step counting sort, neighbor.cu) and a hand-written one-sweep LSD
+// radix sort (key64, val32) for sm_100a.
 //
-// Replaces the serial unordered_map build of SpatialHash::build (reference src/spatial_hash.cpp:15-25):
-// instead of pushing particle ids into per-cell vectors, particles are stably sorted by
-// (cell, id) so every cell's members are contiguous and in ascending id — the order in which
-// the reference's per-cell vectors hold them.
+// Both serve the spatial-hash build that replaces SpatialHash::build (reference src/spatial_hash.cpp:15-25).  The
+// per-step path is the counting sort of neighbor.cu, whose cell table is scanned here; the radix sort produces the
+// reference-order permutation (stable sort by the reference's own (cell, id) keys) that sphb_debug_dump reports when the
+// device layout differs from the reference order.
 //
-// HBM-bound integer work: every pass streams the pairs once for the digit histogram (8 B/pair) and
-// once for the scatter (12 B in, 12 B out), staged through shared memory so the global writes of
-// one digit are contiguous runs.
+// HBM-bound integer work: the scan reads and writes the table once; every sort pass streams the pairs once (12 B in,
+// 12 B out), staged through shared memory so the global writes of one digit are contiguous runs.
 #include "sphb_internal.cuh"
 
 namespace sphb {
@@ -64,180 +64,64 @@ __device__ __forceinline__ uint32_t block_exclusive(uint32_t v, uint32_t* s_warp
     return scan_op<MAX>(warp_base, excl_in_warp);
 }
 
-template <bool MAX>
-__global__ void __launch_bounds__(kScanThreads) k_scan_reduce(const uint32_t* __restrict__ in, size_t n,
-                                                              uint32_t* __restrict__ block_sums) {
-    __shared__ uint32_t s_warp[kScanThreads / 32];
-    const size_t base = (size_t)blockIdx.x * kScanTile;
-    uint32_t acc = 0;
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        size_t i = base + (size_t)k * kScanThreads + threadIdx.x;
-        if (i < n) acc = scan_op<MAX>(acc, in[i]);
-    }
-    uint32_t total;
-    block_exclusive<MAX, kScanThreads>(acc, s_warp, &total);
-    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
-}
+// ---- single-pass exclusive prefix sum with decoupled look-back ------------------------------------------------------
+// Tiles take their index from an atomic ticket, so a tile only ever waits for tiles that already started.  Status word
+// per tile: [63:62] flag (1 = tile aggregate, 2 = inclusive prefix), [61:0] value; one 64-bit store publishes both.
+constexpr unsigned long long kScanFlagLocal = 1ull << 62, kScanFlagIncl = 2ull << 62, kScanValueMask = (1ull << 62) - 1ull;
 
-// Single CTA: exclusive scan of the per-block aggregates, in place.
-template <bool MAX>
-__global__ void __launch_bounds__(1024) k_scan_block_sums(uint32_t* __restrict__ bs, size_t nb) {
-    __shared__ uint32_t s_warp[32];
-    uint32_t carry = 0;
-    for (size_t base = 0; base < nb; base += 1024) {
-        size_t i = base + threadIdx.x;
-        uint32_t v = i < nb ? bs[i] : 0u;
-        uint32_t total;
-        uint32_t ex = block_exclusive<MAX, 1024>(v, s_warp, &total);
-        if (i < nb) bs[i] = scan_op<MAX>(carry, ex);
-        carry = scan_op<MAX>(carry, total);
-        __syncthreads();
-    }
-}
-
-template <bool MAX>
-__global__ void __launch_bounds__(kScanThreads) k_scan_apply(const uint32_t* in, uint32_t* out, size_t n,
-                                                             const uint32_t* __restrict__ block_sums) {
+__global__ void __launch_bounds__(kScanThreads) k_scan_excl_lookback(uint32_t* __restrict__ data, size_t n,
+                                                                     volatile unsigned long long* status, unsigned int* ticket) {
     __shared__ uint32_t s_warp[kScanThreads / 32];
-    const size_t i0 = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+    __shared__ unsigned int s_tile;
+    __shared__ uint32_t s_prefix;
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned int tile = s_tile;
+    const size_t i0 = (size_t)tile * kScanTile + (size_t)tid * kScanItems;
     uint32_t v[kScanItems];
+    if (i0 + kScanItems <= n) {
+        const uint4 a = reinterpret_cast<const uint4*>(data + i0)[0], b = reinterpret_cast<const uint4*>(data + i0)[1];
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) v[k] = (i0 + k < n) ? in[i0 + k] : 0u;
-    uint32_t run = 0;
-    uint32_t incl[kScanItems];
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        run = scan_op<MAX>(run, v[k]);
-        incl[k] = run;
+        for (int k = 0; k < kScanItems; ++k) v[k] = (i0 + k < n) ? data[i0 + k] : 0u;
     }
+    uint32_t run = 0, excl[kScanItems];
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) { excl[k] = run; run += v[k]; }
     uint32_t total;
-    uint32_t ex = block_exclusive<MAX, kScanThreads>(run, s_warp, &total);
-    const uint32_t base = scan_op<MAX>(block_sums[blockIdx.x], ex);
+    const uint32_t ex = block_exclusive<false, kScanThreads>(run, s_warp, &total);
+    if (tid == 0) status[tile] = (tile == 0 ? kScanFlagIncl : kScanFlagLocal) | (unsigned long long)total;
+    if (tid < 32) {
+        unsigned long long prefix = 0;
+        if (tile > 0) {
+            long long t = (long long)tile - 1 - lane;   // lane 0 looks at the nearest predecessor
+            for (;;) {
+                unsigned long long w = kScanFlagIncl;   // before the first tile: an inclusive prefix of 0
+                if (t >= 0) do { w = status[t]; } while ((w >> 62) == 0ull);
+                const unsigned incl = __ballot_sync(0xffffffffu, (w >> 62) == 2ull);
+                const int first = incl ? __ffs(incl) - 1 : 32;
+                unsigned long long part = lane <= first ? (w & kScanValueMask) : 0ull;
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        if (i0 + k < n) {
-            if (MAX) out[i0 + k] = scan_op<true>(base, incl[k]);
-            else out[i0 + k] = base + (incl[k] - v[k]);
+                for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+                prefix += part;
+                if (incl) break;
+                t -= 32;
+            }
+            if (lane == 0) status[tile] = kScanFlagIncl | (prefix + (unsigned long long)total);
         }
-    }
-}
-
-template <bool MAX>
-int launch_scan(uint32_t* data, size_t n, uint32_t* block_sums, cudaStream_t st) {
-    if (n == 0) return 0;
-    const unsigned nb = (unsigned)((n + kScanTile - 1) / kScanTile);
-    k_scan_reduce<MAX><<<nb, kScanThreads, 0, st>>>(data, n, block_sums);
-    k_scan_block_sums<MAX><<<1, 1024, 0, st>>>(block_sums, nb);
-    k_scan_apply<MAX><<<nb, kScanThreads, 0, st>>>(data, data, n, block_sums);
-    return 3;
-}
-
-// ---- radix sort ---------------------------------------------------------------------------------
-
-__global__ void __launch_bounds__(kSortThreads) k_radix_hist(const uint64_t* __restrict__ keys, size_t n, int shift,
-                                                             uint32_t mask, uint32_t ntiles,
-                                                             uint32_t* __restrict__ counts) {
-    __shared__ uint32_t s_hist[256];
-    s_hist[threadIdx.x] = 0;
-    __syncthreads();
-    const size_t base = (size_t)blockIdx.x * kSortTile;
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int k = 0; k < kSortItems; ++k) {
-        size_t e = base + (size_t)k * kSortThreads + threadIdx.x;
-        bool valid = e < n;
-        uint32_t digit = valid ? (uint32_t)(keys[e] >> shift) & mask : 0xFFFFFFFFu;
-        // keys arrive nearly sorted, so most lanes of a warp share a digit: aggregate before the atomic
-        uint32_t peers = __match_any_sync(0xffffffffu, digit);
-        if (valid && lane == __ffs(peers) - 1) atomicAdd(&s_hist[digit], __popc(peers));
+        if (lane == 0) s_prefix = (uint32_t)prefix;
     }
     __syncthreads();
-    counts[(size_t)threadIdx.x * ntiles + blockIdx.x] = s_hist[threadIdx.x];
-}
-
-__global__ void __launch_bounds__(kSortThreads) k_radix_scatter(const uint64_t* __restrict__ keys_in,
-                                                                const uint32_t* __restrict__ vals_in,
-                                                                uint64_t* __restrict__ keys_out,
-                                                                uint32_t* __restrict__ vals_out,
-                                                                const uint32_t* __restrict__ scanned, size_t n, int shift,
-                                                                uint32_t mask, uint32_t ntiles) {
-    __shared__ uint64_t s_keys[kSortTile];
-    __shared__ uint32_t s_vals[kSortTile];
-    __shared__ uint32_t s_warp_cnt[kSortWarps][256];
-    __shared__ uint32_t s_tile_off[256];
-    __shared__ uint32_t s_gbase[256];
-    __shared__ uint32_t s_scan[kSortWarps];
-
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const size_t tile_base = (size_t)blockIdx.x * kSortTile;
-
-    for (int i = tid; i < kSortWarps * 256; i += kSortThreads) (&s_warp_cnt[0][0])[i] = 0;
-    __syncthreads();
-
-    uint64_t key[kSortItems];
-    uint32_t val[kSortItems];
-    uint32_t lrank[kSortItems];
-    uint32_t dig[kSortItems];
-    // warp w ranks elements [w*256, w*256+256) of the tile, 32 at a time, in element order (stable)
+    const uint32_t base = s_prefix + ex;
+    if (i0 + kScanItems <= n) {
+        reinterpret_cast<uint4*>(data + i0)[0] = make_uint4(base + excl[0], base + excl[1], base + excl[2], base + excl[3]);
+        reinterpret_cast<uint4*>(data + i0)[1] = make_uint4(base + excl[4], base + excl[5], base + excl[6], base + excl[7]);
+    } else {
 #pragma unroll
-    for (int k = 0; k < kSortItems; ++k) {
-        size_t e = tile_base + (size_t)w * (32 * kSortItems) + (size_t)k * 32 + lane;
-        bool valid = e < n;
-        key[k] = valid ? keys_in[e] : ~0ull;
-        val[k] = valid ? vals_in[e] : 0u;
-        uint32_t digit = valid ? (uint32_t)(key[k] >> shift) & mask : 255u;  // padding ranks last in its bin
-        dig[k] = digit;
-        uint32_t peers = __match_any_sync(0xffffffffu, digit);
-        uint32_t below = __popc(peers & ((1u << lane) - 1u));
-        int leader = __ffs(peers) - 1;
-        uint32_t old = 0;
-        if (lane == leader) {
-            old = s_warp_cnt[w][digit];
-            s_warp_cnt[w][digit] = old + __popc(peers);
-        }
-        old = __shfl_sync(0xffffffffu, old, leader);
-        lrank[k] = old + below;
-        __syncwarp();
-    }
-    __syncthreads();
-
-    {   // thread d owns digit d: prefix over warps, then exclusive scan over digits
-        const int d = tid;
-        uint32_t run = 0;
-#pragma unroll
-        for (int ww = 0; ww < kSortWarps; ++ww) {
-            uint32_t t = s_warp_cnt[ww][d];
-            s_warp_cnt[ww][d] = run;
-            run += t;
-        }
-        uint32_t total;
-        uint32_t ex = block_exclusive<false, kSortThreads>(run, s_scan, &total);
-        s_tile_off[d] = ex;
-        s_gbase[d] = scanned[(size_t)d * ntiles + blockIdx.x] - ex;
-    }
-    __syncthreads();
-
-#pragma unroll
-    for (int k = 0; k < kSortItems; ++k) {
-        uint32_t pos = s_tile_off[dig[k]] + s_warp_cnt[w][dig[k]] + lrank[k];
-        s_keys[pos] = key[k];
-        s_vals[pos] = val[k];
-    }
-    __syncthreads();
-
-    const size_t remaining = n - tile_base;
-    const uint32_t nvalid = remaining < (size_t)kSortTile ? (uint32_t)remaining : (uint32_t)kSortTile;
-#pragma unroll
-    for (int k = 0; k < kSortItems; ++k) {
-        uint32_t pos = (uint32_t)k * kSortThreads + tid;
-        if (pos < nvalid) {
-            uint64_t kk = s_keys[pos];
-            uint32_t d = (uint32_t)(kk >> shift) & mask;
-            uint32_t g = s_gbase[d] + pos;
-            keys_out[g] = kk;
-            vals_out[g] = s_vals[pos];
-        }
+        for (int k = 0; k < kScanItems; ++k)
+            if (i0 + k < n) data[i0 + k] = base + excl[k];
     }
 }
 
@@ -397,30 +281,16 @@ __global__ void __launch_bounds__(kSortThreads) k_onesweep_pass(const uint64_t* 
 
 }  // namespace
 
-int launch_scan_sum_exclusive(uint32_t* data, size_t n, uint32_t* block_sums, cudaStream_t st) {
-    return launch_scan<false>(data, n, block_sums, st);
-}
-int launch_scan_max_inclusive(uint32_t* data, size_t n, uint32_t* block_sums, cudaStream_t st) {
-    return launch_scan<true>(data, n, block_sums, st);
-}
-
-int launch_radix_sort(const SortBuffers& sb, size_t n, int bits, int* out_buf, cudaStream_t st) {
-    int cur = 0, launches = 0;
-    if (n == 0) { *out_buf = 0; return 0; }
-    const uint32_t ntiles = (uint32_t)((n + kSortTile - 1) / kSortTile);
-    for (int shift = 0; shift < bits; shift += 8) {
-        const int nb = bits - shift < 8 ? bits - shift : 8;
-        const uint32_t mask = (1u << nb) - 1u;
-        k_radix_hist<<<ntiles, kSortThreads, 0, st>>>(sb.keys[cur], n, shift, mask, ntiles, sb.counts);
-        launches += 1;
-        launches += launch_scan<false>(sb.counts, (size_t)256 * ntiles, sb.block_sums, st);
-        k_radix_scatter<<<ntiles, kSortThreads, 0, st>>>(sb.keys[cur], sb.vals[cur], sb.keys[cur ^ 1], sb.vals[cur ^ 1],
-                                                        sb.counts, n, shift, mask, ntiles);
-        launches += 1;
-        cur ^= 1;
-    }
-    *out_buf = cur;
-    return launches;
+// In-place exclusive prefix sum of data[0..n).  scratch holds scan_scratch_bytes(n) bytes and must be ZERO on entry
+// (status words + the tile ticket); the caller clears it together with the counters it scans.
+size_t scan_scratch_bytes(size_t n) { return ((n + kScanTile - 1) / kScanTile + 2) * sizeof(unsigned long long); }
+int launch_scan_exclusive(uint32_t* data, size_t n, void* scratch, cudaStream_t st) {
+    if (n == 0) return 0;
+    const unsigned nb = (unsigned)((n + kScanTile - 1) / kScanTile);
+    unsigned long long* status = static_cast<unsigned long long*>(scratch);
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(status + nb);
+    k_scan_excl_lookback<<<nb, kScanThreads, 0, st>>>(data, n, status, ticket);
+    return 1;
 }
 
 // One-sweep variant.  scratch: (npasses * 256 + npasses * ntiles * 256) u64 + npasses u32 tickets, zeroed here.

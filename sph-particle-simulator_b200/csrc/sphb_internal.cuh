@@ -59,7 +59,8 @@ struct PairConsts {
     float inv_h;        // 1/h
     float sig_h;        // sigma / h
     float sig_h2;       // sigma / h_sq
-    float neg_zero;     // -0.0f, deliberately a RUN-TIME value: see f2_sq_exact in pair.cu
+    float neg_zero;     // -0.0f, deliberately a RUN-TIME value: exact packed squares are formed as fma(d, d, -0) (pair_mask.cu)
+    float r2_next;      // nextafterf(r2, +inf): d2 <= r2 <=> d2 - r2_next < 0 (sign-bit radius test of pair_mask.cu)
 };
 
 struct IntegrateConsts {
@@ -82,47 +83,39 @@ struct DeviceScalars {
 };
 
 // ---- launch wrappers (each returns the number of kernels it enqueued) ---------------------------
-struct SortBuffers {
+struct SortBuffers {      // radix sort of the debug path (reference-order permutation)
     uint64_t* keys[2];
     uint32_t* vals[2];
-    uint32_t* counts;     // 256 * ntiles digit counts, scanned in place
-    uint32_t* block_sums; // scratch of the device-wide scan
-    size_t counts_cap;    // elements available in counts
-    size_t block_sums_cap;
 };
 
 constexpr int kSortTile = 2048;   // keys per CTA tile of the radix sort
 constexpr int kScanTile = 4096;   // elements per CTA of the device-wide scan
 
-// LSD radix sort of (key, val) pairs by the low `bits` bits of key, 8 bits per pass, stable.
-// Input in buffers [0]; returns the index (0/1) of the buffer pair holding the result in *out_buf.
-int launch_radix_sort(const SortBuffers& sb, size_t n, int bits, int* out_buf, cudaStream_t st);
 // Stable sort by the key bits [first_bit, first_bit + bits), one scatter kernel per 8-bit digit with decoupled
 // look-back; the first pass generates vals = slot itself (the caller need not fill vals[0]).  scratch must hold
-// onesweep_scratch_bytes(n_max, bits_max).
+// onesweep_scratch_bytes(n_max, bits_max).  Input in buffers [0]; *out_buf = index of the buffer pair holding the result.
 size_t onesweep_scratch_bytes(size_t n_max, int bits_max);
 int launch_radix_sort_onesweep(const SortBuffers& sb, size_t n, int first_bit, int bits, int* out_buf, void* scratch,
                                cudaStream_t st);
 
-// out[i] = sum(in[0..i-1]) (exclusive) or out[i] = max(in[0..i]) (inclusive); in == out allowed.
-int launch_scan_sum_exclusive(uint32_t* data, size_t n, uint32_t* block_sums, cudaStream_t st);
-int launch_scan_max_inclusive(uint32_t* data, size_t n, uint32_t* block_sums, cudaStream_t st);
+// In-place exclusive prefix sum of data[0..n) in one pass (decoupled look-back).  scratch: scan_scratch_bytes(n) bytes,
+// ZERO on entry.
+size_t scan_scratch_bytes(size_t n);
+int launch_scan_exclusive(uint32_t* data, size_t n, void* scratch, cudaStream_t st);
 
 int launch_pack_upload(size_t n, const float* d_pos3, const float* d_vel3, const float* d_mass, float default_mass,
                        float4* posm, float4* velid, DeviceScalars* sc, cudaStream_t st);
-// refkeys (63-bit reference keys) and ckeys (composite keys on the coarse reference grid gc) are optional
-// debug outputs.
-int launch_cell_keys(size_t n, const float4* posm, const float4* velid, GridDesc g, uint64_t* keys, uint32_t* vals,
-                     uint64_t* refkeys_or_null, uint64_t* ckeys_or_null, GridDesc gc, DeviceScalars* sc, cudaStream_t st);
-// cell_start has ncells + 1 entries; block_sums is scan scratch.
-int launch_cell_table(size_t n, const uint64_t* sorted_keys, GridDesc g, uint32_t* cell_start, uint32_t* block_sums,
-                      cudaStream_t st);
-// sorted_keys need only be sorted by their cell field (key >> id_bits): the reorder kernel ranks every particle among
-// the particles of its cell by full key (= by id) and writes it to cell_start[cell] + rank, so the final layout is the
-// (cell, id) order whether or not the sort looked at the id bits.
-int launch_reorder(size_t n, const uint64_t* sorted_keys, int id_bits, const uint32_t* cell_start, const uint32_t* sorted_vals,
+// Counting sort by cell (neighbor.cu).  launch_cell_count also sets the dt of the step (dt_fixed > 0: that value, else
+// the CFL rule of compute_cfl_timestep); cell_cnt must be zero on entry.  refkeys (63-bit reference keys) and ckeys
+// (composite keys on the coarse reference grid gc) are optional debug outputs.
+int launch_cell_count(size_t n, const float4* posm, const float4* velid, GridDesc g, uint2* cell_ticket, uint32_t* cell_cnt,
+                      uint64_t* refkeys_or_null, uint64_t* ckeys_or_null, GridDesc gc, DeviceScalars* sc, float dt_fixed,
+                      IntegrateConsts ic, cudaStream_t st);
+int launch_cell_scatter(size_t n, const uint2* cell_ticket, const uint32_t* cell_start, uint32_t* slot_src, cudaStream_t st);
+// gathers the records into (cell, id) order: slot = cell_start[cell] + rank of the id among the cell's members
+int launch_reorder(size_t n, const uint32_t* slot_src, const uint2* cell_ticket, const uint32_t* cell_start,
                    const float4* posm_in, const float4* velid_in, const uint64_t* refkeys_in, float4* posm_out, float4* velid_out,
-                   uint64_t* refkeys_out, float4* pp2_out, cudaStream_t st);
+                   uint64_t* refkeys_out, cudaStream_t st);
 
 // variant 2: everything the force pass needs from a neighbour, in one 32-byte record (A = m / (2 rho), B = A * P)
 struct __align__(32) ForceRec {
@@ -138,16 +131,12 @@ struct PairArgs {
     float2* rho_p;             // density, pressure
     float4* fa;                // force-pass staging A (fast: x,y,z,m/(2 rho) ; strict: x,y,z,m)
     float4* fb;                // force-pass staging B (fast: v, A*P ; strict: v, rho)
-    // pair-interleaved mirrors for the packed-f32x2 kernels: record k = particles 2k, 2k+1 as
-    // {x0,x1,y0,y1 | z0,z1,w0,w1} (two float4)
-    const float4* pp2;         // position + mass pairs (written by the reorder kernel)
-    float4* fa2;               // x, y, z, A' = (sigma/h) m / (2 rho)
-    float4* fb2;               // vx, vy, vz, B' = A' P
     float4* acc;               // ax, ay, az, (unused)
-    // variant 2: accepted-neighbour bitmasks handed from the density pass to the force pass, column-major:
-    // masks[col * mask_stride + slot], col = 0 .. mask_cols(R)-1 are the (2R+1)^2 cell columns in walk order (bit k =
-    // k-th candidate of the column run), col = mask_cols(R) is {overflow flag, neighbour count}
-    void* masks;               // uint2 per (column, particle) for R <= 3, uint32 for R = 4 (mask_words())
+    // variant 2: accepted-neighbour bitmasks handed from the density pass to the force pass, row-major by column
+    // group: masks[row * mask_stride + slot].  R >= 4 (pair_mask.cu): one uint32 per mirror pair of cell columns
+    // (16 bits each) in walk order, empty corner groups skipped, last row = centre column + overflow flag.
+    // R <= 3 (pair_mask_wide.cu): one uint2 per column, last row = {overflow flag, neighbour count}.
+    void* masks;
     size_t mask_stride;
     ForceRec* fab;             // variant 2: force-pass records, written by the density pass
     uint32_t* nbr_count;       // optional, per sorted slot
@@ -168,16 +157,14 @@ int launch_force(const PairArgs& a, cudaStream_t st);
 constexpr int kMaskMinRadius = 2, kMaskMaxRadius = 6;
 constexpr float kRefinedCellScale = 0.9990234375f;   // 1 - 2^-10: refined cells are this much larger than nsr / refine (make_grid)
 constexpr int mask_cols(int R) { return (2 * R + 1) * (2 * R + 1); }
-#ifndef SPHB_MASK_W4
-#define SPHB_MASK_W4 1
-#endif
-constexpr int mask_words(int R) { return R >= 4 ? SPHB_MASK_W4 : 2; }   // 32-bit words per column mask (a column holds ~(2R+1)/R^3 of a coarse cell)
+size_t mask_bytes_per_slot(int R);                  // bytes of mask storage per unit of mask_stride
 int stencil_reach_table(int R, signed char* out);   // host: copies the (2R+1)^2 column reaches, returns their number or -1
 int launch_density_mask(const PairArgs& a, cudaStream_t st);
 int launch_force_mask(const PairArgs& a, cudaStream_t st);
+int launch_density_mask_wide(const PairArgs& a, cudaStream_t st);   // R = 2, 3
+int launch_force_mask_wide(const PairArgs& a, cudaStream_t st);
 
-int launch_set_dt(DeviceScalars* sc, float dt, cudaStream_t st);
-int launch_cfl_dt(DeviceScalars* sc, IntegrateConsts ic, cudaStream_t st);
+int launch_cfl_probe(DeviceScalars* sc, IntegrateConsts ic, cudaStream_t st);   // sphb_cfl_timestep: sc->dt = the CFL rule, nothing consumed
 int launch_integrate(size_t n, float4* posm, float4* velid, const float4* acc, IntegrateConsts ic, DeviceScalars* sc,
                      int* d_box_or_null, cudaStream_t st);
 int launch_max_speed(size_t n, const float4* velid, DeviceScalars* sc, cudaStream_t st);
