@@ -101,7 +101,13 @@ enum {
      * cell order (default 0).  In slab mode the slab axis is used, so that ghost layers are contiguous in the
      * sorted arrays.  Only the fp32 summation ORDER depends on it (results agree within the fast-mode
      * tolerances; identical layouts give bit-identical results). */
-    SPHB_OPT_LAYOUT_MAJOR = 7
+    SPHB_OPT_LAYOUT_MAJOR = 7,
+    /* fast mode, pair kernel 2, internal walk radius >= 4 (grid refine >= 4): where the pair kernels read their
+     * candidates from.  0 = every lane loads its candidates from global memory (pair_mask.cu; default);
+     * 1 = staged (pair_stage.cu): the neighbour-cell particles of a tile of consecutive cell-sorted particles are
+     * brought into shared memory by asynchronous copies and the lanes traverse them from there.  Identical results,
+     * bit for bit.  Environment override of the default: SPHB_PAIR_MODE. */
+    SPHB_OPT_PAIR_MODE = 8
 };
 
 /* ---- lifetime ---------------------------------------------------------------------------------

@@ -34,6 +34,7 @@ OPT_DEBUG_CAPTURE = 4
 OPT_PAIR_KERNEL = 5
 OPT_GRID_REFINE = 6
 OPT_LAYOUT_MAJOR = 7
+OPT_PAIR_MODE = 8
 MATH_STRICT = 0
 MATH_FAST = 1
 

@@ -38,6 +38,7 @@ struct sphb_ctx {
     int stage_timing = 0;
     int debug_capture = 0;
     int pair_kernel = 2;     // fast mode: 2 = bitmask hand-off density -> force (default), 0 = tested walk twice
+    int pair_mode = 0;       // R >= 4 mask kernels: 0 = per-lane global loads (pair_mask.cu), 1 = shared-memory staged (pair_stage.cu)
     int layout_major = 0;    // fast-mode layout: physical axis that is most significant in the cell order (slab mode: the slab axis)
     int grid_refine = 4;     // internal cell = neighbor_search_radius / grid_refine (fast mode; strict always 1)
 
@@ -365,6 +366,7 @@ int sphb_create(sphb_ctx** out, size_t capacity, int device) {
     if (!c) return fail(nullptr, SPHB_E_NOMEM, "out of host memory");
     c->device = device;
     c->capacity = capacity;
+    if (const char* e = getenv("SPHB_PAIR_MODE")) { if (e[0] >= '0' && e[0] <= '1') c->pair_mode = e[0] - '0'; }   // A/B runs without touching the caller
     const size_t cap = capacity ? capacity : 1;
 #define CUC(call)                                                                                         \
     do {                                                                                                  \
@@ -437,6 +439,10 @@ int sphb_set_option(sphb_ctx* c, int option, int64_t value) {
             if (value < 1 || value > 6) return fail(c, SPHB_E_INVALID, "grid refine must be 1..6");
             c->grid_refine = (int)value;
             return SPHB_OK;
+        case SPHB_OPT_PAIR_MODE:
+            if (value < 0 || value > 1) return fail(c, SPHB_E_INVALID, "pair mode must be 0 (per-lane global loads) or 1 (staged)");
+            c->pair_mode = (int)value;
+            return SPHB_OK;
         case SPHB_OPT_LAYOUT_MAJOR:
             if (value < 0 || value > 2) return fail(c, SPHB_E_INVALID, "layout major axis must be 0..2");
             c->layout_major = (int)value;
@@ -456,6 +462,7 @@ int sphb_get_option(const sphb_ctx* c, int option, int64_t* value) {
         case SPHB_OPT_PAIR_KERNEL: *value = c->pair_kernel; return SPHB_OK;
         case SPHB_OPT_GRID_REFINE: *value = c->grid_refine; return SPHB_OK;
         case SPHB_OPT_LAYOUT_MAJOR: *value = c->layout_major; return SPHB_OK;
+        case SPHB_OPT_PAIR_MODE: *value = c->pair_mode; return SPHB_OK;
         default: return SPHB_E_INVALID;
     }
 }
@@ -665,11 +672,19 @@ int sphb_step(sphb_ctx* c, float dt) {
             CU(c, cudaMalloc(&c->masks, need));
             c->mask_bytes = need;
         }
-        if (!c->fab) {
-            CU(c, cudaMalloc(&c->fab, cap * sizeof(ForceRec)));
-            CU(c, cudaMemsetAsync(c->fab, 0, cap * sizeof(ForceRec), c->stream));
-        }
-    } else if (!c->fa) {
+    }
+    // force-pass records: ONE 32-byte record per particle for the kernels whose lanes gather them from global memory
+    // (one LDG.E.256), two arrays of 16-byte halves for the staged kernels (conflict-free LDS.128 gathers) and for the
+    // tested-walk kernels (strict mode, variant 0)
+    const PairConsts pk = make_pair_consts(c->prm);
+    const int mode = (variant == 2 && c->walk_radius * refine >= 4) ? c->pair_mode : 0;
+    const bool staged = mode == 1;
+    if (variant == 2 && !staged && !c->fab) {
+        const size_t cap = c->capacity ? c->capacity : 1;
+        CU(c, cudaMalloc(&c->fab, cap * sizeof(ForceRec)));
+        CU(c, cudaMemsetAsync(c->fab, 0, cap * sizeof(ForceRec), c->stream));
+    }
+    if ((variant != 2 || staged) && !c->fa) {
         const size_t cap = c->capacity ? c->capacity : 1;
         CU(c, cudaMalloc(&c->fa, cap * sizeof(float4)));
         CU(c, cudaMalloc(&c->fb, cap * sizeof(float4)));
@@ -727,16 +742,23 @@ int sphb_step(sphb_ctx* c, float dt) {
     pa.nbr_count = c->debug_capture ? c->nbr_count : nullptr;
     pa.sc = c->sc;
     pa.grid = g;
-    pa.k = make_pair_consts(c->prm);
+    pa.k = pk;
     pa.walk_radius = c->walk_radius * refine;
     pa.strict = c->math_mode == 0;
     pa.variant = variant;
+    pa.mode = mode;
     pa.slab_axis = c->slab_on ? c->slab.axis : -1;
     pa.rho_lo = c->slab_on ? c->slab.own_lo - 1 : 0;
     pa.rho_hi = c->slab_on ? c->slab.own_hi + 1 : 0;
-    launches += launch_density(pa, st);
-    if (timing) cudaEventRecord(ev[2], st);
-    launches += launch_force(pa, st);
+    {
+        const int ld = launch_density(pa, st);
+        if (timing) cudaEventRecord(ev[2], st);
+        const int lf = ld < 0 ? ld : launch_force(pa, st);
+        if (ld < 0 || lf < 0)
+            return fail(c, SPHB_E_CUDA, "the staged pair kernels cannot be configured on this device (%s); set SPHB_OPT_PAIR_MODE 0",
+                        cudaGetErrorString(cudaGetLastError()));
+        launches += (uint64_t)(ld + lf);
+    }
     if (timing) cudaEventRecord(ev[3], st);
     // after the clamp every position lies inside the AABB (particle.cpp:122-153), so the next step can size its
     // cell table from the bounds without looking at the device.  When that table would be far larger than the

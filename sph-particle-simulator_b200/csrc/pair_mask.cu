@@ -54,41 +54,6 @@ constexpr int kThreads = SPHB_MASK_THREADS;
 #define SPHB_PRAGMA(x) _Pragma(#x)
 #define SPHB_UNROLL_N(n) SPHB_PRAGMA(unroll n)
 
-constexpr int kMaskBits = 16;   // candidates per column mask
-
-// Mask rows: one per mirror-pair group whose columns lie inside the stencil, in walk order, plus the centre column.
-// Bit 31 of the centre word is the particle's overflow flag (the centre column only uses the low half).
-template <int R>
-struct Groups {
-    static constexpr int kCols = (2 * R + 1) * (2 * R + 1);
-    static constexpr int kGroups = kCols / 2;   // groups 0 .. kGroups-1 are {column g, column kCols-1-g}, group kGroups is the centre
-};
-
-// The non-empty mirror-pair groups of the stencil in walk order, then the centre column (d0 = d1 = 0) as entry n.
-template <int R>
-struct GroupTable {
-    int n;
-    int d0[Groups<R>::kGroups + 1], d1[Groups<R>::kGroups + 1], reach[Groups<R>::kGroups + 1];
-};
-template <int R>
-constexpr GroupTable<R> make_group_table() {
-    GroupTable<R> t{};
-    const int w = 2 * R + 1;
-    for (int g = 0; g < Groups<R>::kGroups; ++g) {
-        const int r = reach_of(R, g / w - R, g % w - R);
-        if (r >= 0) { t.d0[t.n] = g / w - R; t.d1[t.n] = g % w - R; t.reach[t.n] = r; ++t.n; }
-    }
-    t.d0[t.n] = 0; t.d1[t.n] = 0; t.reach[t.n] = reach_of(R, 0, 0);
-    return t;
-}
-__constant__ GroupTable<4> kGroups4 = make_group_table<4>();
-__constant__ GroupTable<5> kGroups5 = make_group_table<5>();
-__constant__ GroupTable<6> kGroups6 = make_group_table<6>();
-template <int R> __device__ __forceinline__ const GroupTable<R>& group_table();
-template <> __device__ __forceinline__ const GroupTable<4>& group_table<4>() { return kGroups4; }
-template <> __device__ __forceinline__ const GroupTable<5>& group_table<5>() { return kGroups5; }
-template <> __device__ __forceinline__ const GroupTable<6>& group_table<6>() { return kGroups6; }
-
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 
 // Pins a loop-invariant value in a register: ptxas otherwise re-reads kernel parameters from the constant bank inside
@@ -455,6 +420,7 @@ size_t mask_bytes_per_slot(int R) {
 int launch_density_mask(const PairArgs& a, cudaStream_t st) {
     if (a.n == 0) return 0;
     if (a.walk_radius < 4) return launch_density_mask_wide(a, st);
+    if (a.mode == 1) return launch_density_stage(a, st);
     const unsigned nb = (unsigned)((a.n + kThreads - 1) / kThreads);
     const bool slab = a.slab_axis >= 0;
     // neighbor_search_radius < 2 h: the kernel support is truncated by the search radius (see k_density_mask16)
@@ -476,6 +442,7 @@ int launch_density_mask(const PairArgs& a, cudaStream_t st) {
 int launch_force_mask(const PairArgs& a, cudaStream_t st) {
     if (a.n == 0) return 0;
     if (a.walk_radius < 4) return launch_force_mask_wide(a, st);
+    if (a.mode == 1) return launch_force_stage(a, st);
     const unsigned nb = (unsigned)((a.n + kThreads - 1) / kThreads);
     const bool slab = a.slab_axis >= 0;
 #define SPHB_LAUNCH_F(RR)                                                 \

@@ -57,6 +57,42 @@ __device__ __forceinline__ uint32_t center_cell(const GridDesc& g, const float4&
     return ((uint32_t)c0 * (uint32_t)g.ext[1] + (uint32_t)c1) * (uint32_t)g.ext[2] + (uint32_t)c2;
 }
 
+// ---- 16-bit column masks (pair_mask.cu, pair_stage.cu; R >= 4) ----
+constexpr int kMaskBits = 16;   // candidates per column mask
+
+// Mask rows: one per mirror-pair group whose columns lie inside the stencil, in walk order, plus the centre column.
+// Bit 31 of the centre word is the particle's overflow flag (the centre column only uses the low half).
+template <int R>
+struct Groups {
+    static constexpr int kCols = (2 * R + 1) * (2 * R + 1);
+    static constexpr int kGroups = kCols / 2;   // groups 0 .. kGroups-1 are {column g, column kCols-1-g}, group kGroups is the centre
+};
+
+// The non-empty mirror-pair groups of the stencil in walk order, then the centre column (d0 = d1 = 0) as entry n.
+template <int R>
+struct GroupTable {
+    int n;
+    int d0[Groups<R>::kGroups + 1], d1[Groups<R>::kGroups + 1], reach[Groups<R>::kGroups + 1];
+};
+template <int R>
+constexpr GroupTable<R> make_group_table() {
+    GroupTable<R> t{};
+    const int w = 2 * R + 1;
+    for (int g = 0; g < Groups<R>::kGroups; ++g) {
+        const int r = reach_of(R, g / w - R, g % w - R);
+        if (r >= 0) { t.d0[t.n] = g / w - R; t.d1[t.n] = g % w - R; t.reach[t.n] = r; ++t.n; }
+    }
+    t.d0[t.n] = 0; t.d1[t.n] = 0; t.reach[t.n] = reach_of(R, 0, 0);
+    return t;
+}
+__constant__ GroupTable<4> kGroups4 = make_group_table<4>();
+__constant__ GroupTable<5> kGroups5 = make_group_table<5>();
+__constant__ GroupTable<6> kGroups6 = make_group_table<6>();
+template <int R> __device__ __forceinline__ const GroupTable<R>& group_table();
+template <> __device__ __forceinline__ const GroupTable<4>& group_table<4>() { return kGroups4; }
+template <> __device__ __forceinline__ const GroupTable<5>& group_table<5>() { return kGroups5; }
+template <> __device__ __forceinline__ const GroupTable<6>& group_table<6>() { return kGroups6; }
+
 // 32-byte force-pass record of one particle, fetched with ONE 256-bit load (LDG.E.256, sm_100)
 __device__ __forceinline__ ForceRec load_rec(const ForceRec* __restrict__ p) {
     ForceRec r;
