@@ -103,10 +103,11 @@ enum {
      * tolerances; identical layouts give bit-identical results). */
     SPHB_OPT_LAYOUT_MAJOR = 7,
     /* fast mode, pair kernel 2, internal walk radius >= 4 (grid refine >= 4): where the pair kernels read their
-     * candidates from.  0 = every lane loads its candidates from global memory (pair_mask.cu; default);
-     * 1 = staged (pair_stage.cu): the neighbour-cell particles of a tile of consecutive cell-sorted particles are
-     * brought into shared memory by asynchronous copies and the lanes traverse them from there.  Identical results,
-     * bit for bit.  Environment override of the default: SPHB_PAIR_MODE. */
+     * candidates from.  0 = every lane loads its candidates from global memory (pair_mask.cu); 1 = staged
+     * (pair_stage.cu): every warp brings the neighbour-cell particles of its 32 consecutive cell-sorted particles into
+     * shared memory with asynchronous copies, one cell-column group ahead, and the lanes traverse them from there;
+     * 2 (default) = the density pass staged, the force pass per lane (the faster combination as measured).
+     * Identical results in all three, bit for bit.  Environment override of the default: SPHB_PAIR_MODE. */
     SPHB_OPT_PAIR_MODE = 8
 };
 

@@ -38,7 +38,7 @@ struct sphb_ctx {
     int stage_timing = 0;
     int debug_capture = 0;
     int pair_kernel = 2;     // fast mode: 2 = bitmask hand-off density -> force (default), 0 = tested walk twice
-    int pair_mode = 0;       // R >= 4 mask kernels: 0 = per-lane global loads (pair_mask.cu), 1 = shared-memory staged (pair_stage.cu)
+    int pair_mode = 2;       // R >= 4 mask kernels: 0 = per-lane global loads (pair_mask.cu), 1 = shared-memory staged (pair_stage.cu), 2 = staged density pass + per-lane force pass
     int layout_major = 0;    // fast-mode layout: physical axis that is most significant in the cell order (slab mode: the slab axis)
     int grid_refine = 4;     // internal cell = neighbor_search_radius / grid_refine (fast mode; strict always 1)
 
@@ -366,7 +366,7 @@ int sphb_create(sphb_ctx** out, size_t capacity, int device) {
     if (!c) return fail(nullptr, SPHB_E_NOMEM, "out of host memory");
     c->device = device;
     c->capacity = capacity;
-    if (const char* e = getenv("SPHB_PAIR_MODE")) { if (e[0] >= '0' && e[0] <= '1') c->pair_mode = e[0] - '0'; }   // A/B runs without touching the caller
+    if (const char* e = getenv("SPHB_PAIR_MODE")) { if (e[0] >= '0' && e[0] <= '2') c->pair_mode = e[0] - '0'; }   // A/B runs without touching the caller
     const size_t cap = capacity ? capacity : 1;
 #define CUC(call)                                                                                         \
     do {                                                                                                  \
@@ -440,7 +440,7 @@ int sphb_set_option(sphb_ctx* c, int option, int64_t value) {
             c->grid_refine = (int)value;
             return SPHB_OK;
         case SPHB_OPT_PAIR_MODE:
-            if (value < 0 || value > 1) return fail(c, SPHB_E_INVALID, "pair mode must be 0 (per-lane global loads) or 1 (staged)");
+            if (value < 0 || value > 2) return fail(c, SPHB_E_INVALID, "pair mode must be 0 (per-lane global loads), 1 (staged) or 2 (staged density, per-lane force)");
             c->pair_mode = (int)value;
             return SPHB_OK;
         case SPHB_OPT_LAYOUT_MAJOR:
@@ -673,18 +673,18 @@ int sphb_step(sphb_ctx* c, float dt) {
             c->mask_bytes = need;
         }
     }
-    // force-pass records: ONE 32-byte record per particle for the kernels whose lanes gather them from global memory
-    // (one LDG.E.256), two arrays of 16-byte halves for the staged kernels (conflict-free LDS.128 gathers) and for the
-    // tested-walk kernels (strict mode, variant 0)
+    // force-pass records: two arrays of 16-byte halves for the 16-bit mask kernels (conflict-free LDS.128 gathers when
+    // staged) and the tested-walk kernels (strict mode, variant 0); ONE 32-byte record per particle (one LDG.E.256) for
+    // the 64-bit mask kernels of pair_mask_wide.cu
     const PairConsts pk = make_pair_consts(c->prm);
     const int mode = (variant == 2 && c->walk_radius * refine >= 4) ? c->pair_mode : 0;
-    const bool staged = mode == 1;
-    if (variant == 2 && !staged && !c->fab) {
+    const bool split = variant == 2 && c->walk_radius * refine >= 4;   // 16-bit mask kernels (pair_mask.cu, pair_stage.cu)
+    if (variant == 2 && !split && !c->fab) {
         const size_t cap = c->capacity ? c->capacity : 1;
         CU(c, cudaMalloc(&c->fab, cap * sizeof(ForceRec)));
         CU(c, cudaMemsetAsync(c->fab, 0, cap * sizeof(ForceRec), c->stream));
     }
-    if ((variant != 2 || staged) && !c->fa) {
+    if ((variant != 2 || split) && !c->fa) {
         const size_t cap = c->capacity ? c->capacity : 1;
         CU(c, cudaMalloc(&c->fa, cap * sizeof(float4)));
         CU(c, cudaMalloc(&c->fb, cap * sizeof(float4)));

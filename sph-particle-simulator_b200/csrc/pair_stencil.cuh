@@ -93,6 +93,112 @@ template <> __device__ __forceinline__ const GroupTable<4>& group_table<4>() { r
 template <> __device__ __forceinline__ const GroupTable<5>& group_table<5>() { return kGroups5; }
 template <> __device__ __forceinline__ const GroupTable<6>& group_table<6>() { return kGroups6; }
 
+__device__ __forceinline__ float2 mk2(float a, float b) { return make_float2(a, b); }
+// clamp(fma(a, b, c), 0, 1) in one FFMA.SAT
+__device__ __forceinline__ float fma_sat(float a, float b, float c) {
+    float r;
+    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+// Keeps a kernel parameter in a register for good: ptxas otherwise re-reads it from the constant bank inside the pair
+// loops (one issue slot per use).  `zero` is a run-time 0 the compiler cannot see through.
+__device__ __forceinline__ float hold(float v, uint32_t zero) { return __uint_as_float(__float_as_uint(v) ^ zero); }
+
+// The density pass of ONE particle over runs of candidates, shared by the per-lane (pair_mask.cu) and the staged
+// (pair_stage.cu) kernels so that both produce the same bits.
+//   * Candidates are taken two at a time, packed across them on the f32x2 pipe; an odd one at the end of a run takes the
+//     same operations in scalar form.
+//   * Squared distances carry the reference's roundings (spatial_hash.h:70-73): fl(fl(fl(dx dx) + fl(dy dy)) +
+//     fl(dz dz)); the squares are formed as fma(d, d, -0) with a RUN-TIME -0 (an exact product; ptxas would contract a
+//     packed multiply with the following packed add into one FFMA2, see pair.cu).
+//   * accepted <=> d2 <= r2 <=> d2 - nextafter(r2) < 0: the sign bit, shifted into the column mask with one funnel
+//     shift — no compare, no predicate; NaN gives 0 like the reference's compare.
+//   * The weight is evaluated unconditionally in compact-support form: W * 6 / (4 sigma) = 2 u^3 - t^3 with
+//     u = (2 - q)+ / 2 and t = (1 - q)+, both clamped by the saturating FFMA they are formed with (they lie in [0, 1]):
+//     exactly 0 for q >= 2, so there is no "accepted" branch.  TRUNC: the search radius cuts the kernel support short
+//     (neighbor_search_radius < 2 h, e.g. the reference's dam-break example: h = 0.025, radius 0.04): the weight is
+//     additionally gated by the accept bit.
+template <bool TRUNC>
+struct DensityWalker {
+    float2 npxy, nz2, nr2;
+    float npz, nzf, nr2f, ninvh, nhinvh;
+    float rho0, rho1;        // sum of m_j W_j * 6 / (4 sigma), even / odd candidates of the runs (the self pair included)
+    uint32_t m;              // mask of the column being walked
+    unsigned ovf, extra;     // a column held more than 16 candidates; neighbours found beyond the masks
+
+    __device__ __forceinline__ void init(const float4& pi, const PairConsts& k, uint32_t zero) {
+        npxy = mk2(-pi.x, -pi.y); npz = -pi.z;
+        nzf = hold(k.neg_zero, zero); nz2 = mk2(nzf, nzf);
+        nr2f = hold(-k.r2_next, zero); nr2 = mk2(nr2f, nr2f);
+        ninvh = hold(-k.inv_h, zero); nhinvh = hold(-0.5f * k.inv_h, zero);
+        rho0 = rho1 = 0.0f; m = 0; ovf = 0; extra = 0;
+    }
+    __device__ __forceinline__ void visit2(const float4& pa, const float4& pb) {
+        const float2 da = __fadd2_rn(mk2(pa.x, pa.y), npxy), db = __fadd2_rn(mk2(pb.x, pb.y), npxy);
+        const float2 dz = mk2(__fadd_rn(pa.z, npz), __fadd_rn(pb.z, npz));
+        const float2 sa = __ffma2_rn(da, da, nz2), sb = __ffma2_rn(db, db, nz2), sz = __ffma2_rn(dz, dz, nz2);
+        const float2 d2 = __fadd2_rn(mk2(__fadd_rn(sa.x, sa.y), __fadd_rn(sb.x, sb.y)), sz);
+        const float2 t = __fadd2_rn(d2, nr2);
+        m = __funnelshift_l(__float_as_uint(t.x), m, 1);
+        m = __funnelshift_l(__float_as_uint(t.y), m, 1);
+        const float s0 = fast_sqrt(d2.x), s1 = fast_sqrt(d2.y);
+        const float2 u = mk2(fma_sat(s0, nhinvh, 1.0f), fma_sat(s1, nhinvh, 1.0f));
+        const float2 t1 = mk2(fma_sat(s0, ninvh, 1.0f), fma_sat(s1, ninvh, 1.0f));
+        const float2 u3 = __fmul2_rn(__fmul2_rn(u, u), u);
+        const float2 nt2 = __fmul2_rn(t1, mk2(-t1.x, -t1.y));
+        float2 w = __ffma2_rn(u3, mk2(2.0f, 2.0f), __fmul2_rn(nt2, t1));
+        if (TRUNC) {
+            w.x = t.x < 0.0f ? w.x : 0.0f;
+            w.y = t.y < 0.0f ? w.y : 0.0f;
+        }
+        rho0 = fmaf(pa.w, w.x, rho0);
+        rho1 = fmaf(pb.w, w.y, rho1);
+    }
+    __device__ __forceinline__ void visit1(const float4& pa) {
+        const float2 da = __fadd2_rn(mk2(pa.x, pa.y), npxy);
+        const float dz = __fadd_rn(pa.z, npz);
+        const float2 sa = __ffma2_rn(da, da, nz2);
+        const float d2 = __fadd_rn(__fadd_rn(sa.x, sa.y), __fmaf_rn(dz, dz, nzf));
+        const float t = __fadd_rn(d2, nr2f);
+        m = __funnelshift_l(__float_as_uint(t), m, 1);
+        const float s0 = fast_sqrt(d2);
+        const float u = fma_sat(s0, nhinvh, 1.0f), t1 = fma_sat(s0, ninvh, 1.0f);
+        float w = __fmaf_rn(__fmul_rn(__fmul_rn(u, u), u), 2.0f, __fmul_rn(__fmul_rn(t1, -t1), t1));
+        if (TRUNC) w = t < 0.0f ? w : 0.0f;
+        rho0 = fmaf(pa.w, w, rho0);
+    }
+    // One cell column: candidates [b, e) of `src` (posm itself or a staged copy of a slot range); `to_slot` turns an index
+    // of src into a slot of posm.  Returns the 16-bit mask, candidate q at bit 15 - q.  Candidates beyond the mask
+    // (collapsed states, coincident wall layers) are walked with the scalar tested loop and set `ovf`; the force pass
+    // does the same, so results never depend on the mask capacity.
+    __device__ __forceinline__ uint32_t column(const float4* __restrict__ src, uint32_t b, uint32_t e, uint32_t to_slot,
+                                               const float4* __restrict__ posm, const float4& pi, const PairConsts& k) {
+        const uint32_t end = min(e, b + (uint32_t)kMaskBits);
+        m = 0;
+        uint32_t j = b;
+#pragma unroll 1
+        for (; j + 1u < end; j += 2) visit2(src[j], src[j + 1]);
+        if (j < end) visit1(src[j]);
+        m <<= (b + (uint32_t)kMaskBits) - end;   // end - b candidates were shifted in
+        if (e > end) {
+            ovf = 1u;
+            const float r2 = k.r2, inv_h = k.inv_h;
+            for (uint32_t u = end + to_slot; u < e + to_slot; ++u) {
+                const float4 pj = __ldg(posm + u);
+                const float d2 = dist2_exact(__fsub_rn(pi.x, pj.x), __fsub_rn(pi.y, pj.y), __fsub_rn(pi.z, pj.z));
+                if (d2 <= r2) {
+                    ++extra;
+                    const float q = fast_sqrt(d2) * inv_h;
+                    const float uu = fmaxf(1.0f - 0.5f * q, 0.0f), tt = fmaxf(1.0f - q, 0.0f);
+                    rho0 += pj.w * (2.0f * (uu * uu * uu) - tt * tt * tt);
+                }
+            }
+        }
+        return m;
+    }
+    __device__ __forceinline__ float density(const PairConsts& k) const { return (rho0 + rho1) * (k.sigma * (4.0f / 6.0f)); }
+};
+
 // 32-byte force-pass record of one particle, fetched with ONE 256-bit load (LDG.E.256, sm_100)
 __device__ __forceinline__ ForceRec load_rec(const ForceRec* __restrict__ p) {
     ForceRec r;

@@ -146,7 +146,7 @@ struct PairArgs {
     int walk_radius;
     int strict;
     int variant;
-    int mode;                  // variant 2, R >= 4: 0 = pair_mask.cu, 1 = pair_stage.cu (SPHB_OPT_PAIR_MODE)
+    int mode;                  // variant 2, R >= 4: 0 = pair_mask.cu, 1 = pair_stage.cu, 2 = staged density + per-lane force (SPHB_OPT_PAIR_MODE)
     // slab mode (slab_axis >= 0): density is evaluated for particles whose reference cell on the axis lies in
     // [rho_lo, rho_hi) (owned + one halo layer); force only for owned particles (id word bit 31 clear)
     int slab_axis;

@@ -399,17 +399,18 @@ def _staged_vs_global(pkg, pos, vel, mass, prm, dts, refine, what):
     """Runs the same steps with the staged pair kernels (pair_stage.cu, default) and with the per-lane global-memory
     kernels (pair_mask.cu): every output must be the same bits."""
     outs = []
-    for staged in (1, 0):
+    for staged in (1, 0, 2):
         ctx = make_ctx(pkg, len(pos), prm, strict=False, OPT_PAIR_KERNEL=2, OPT_GRID_REFINE=refine, OPT_PAIR_MODE=staged)
         ctx.upload(pos, vel, mass)
         for dt in dts:
             ctx.step(float(dt))
         outs.append((ctx.download(), ctx.debug_dump(), ctx.stats()["max_neighbors"]))
         ctx.close()
-    for f in ("rho", "P", "acc", "pos", "vel"):
-        assert_bits(outs[0][0][f], outs[1][0][f], f"{what}: staged vs global {f}")
-    assert_bits(outs[0][1]["nbr_count"], outs[1][1]["nbr_count"], f"{what}: staged vs global counts")
-    assert outs[0][2] == outs[1][2]
+    for other in outs[1:]:
+        for f in ("rho", "P", "acc", "pos", "vel"):
+            assert_bits(outs[0][0][f], other[0][f], f"{what}: staged vs global {f}")
+        assert_bits(outs[0][1]["nbr_count"], other[1]["nbr_count"], f"{what}: staged vs global counts")
+        assert outs[0][2] == other[2]
     return outs[0]
 
 

@@ -1,0 +1,6 @@
+# round 2, job o: staged kernels with the trimmed density loop: tolerance tests under SPHB_PAIR_MODE=1, bench
+set -x
+SPHB_PAIR_MODE=1 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "fast or refine or overflow or sixty or ten_steps or full_size" 2>&1 | tail -6
+one() { timeout 300 python bench.py --no-cpu "$@" 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['extra']['stage_ms_rank0'], d['extra']['max_neighbors'])"; }
+SPHB_PAIR_MODE=1 one --warmup 60 --steps 60
+SPHB_PAIR_MODE=1 one --warmup 20 --steps 20 --scene dam_break_10M
