@@ -4,15 +4,23 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--scene NAME] [--impl ours|reference]
 
 A "step" is one call of the hot path (SPHEngine::step: neighbour build, density + EOS, force,
-integrate + clamp) over every particle of the scene.  Default workload: BASELINE.json configs[1],
-the 1M-particle dam break (N = 1 130 000 from the reference's own lattice generator at dx = 0.004)
-with the bounded "P-tame" parameter set (the reference's defaults explode in one step).
+integrate + clamp) over every particle of the scene.  Default workload: the 10M-particle dam break the
+north star is quoted on (BASELINE.json metric "at 1M and 10M"; N = 10 684 224 from the reference's own
+lattice generator at dx = 0.00185) with the bounded "P-tame" parameter set (the
+reference's defaults explode in one step); the 1M dam break (configs[1]) is measured in the same run and
+reported under `extra.also`.  With N GPUs the scene is weak-scaled (N x the particles, same geometry).
+
+The lattice is advanced until 60 steps have passed before the timed region starts (the ordered initial
+lattice is the flattering state: all lanes of a warp see identical neighbourhoods).
 
 One JSON line on stdout (rank 0).  `value` = particles x steps / device time with the state resident in
 HBM; `e2e` = the same metric through the C ABI with HOST buffers (pinned H2D upload + step + D2H
-download every step); `roofline` = the dominant kernel against the measured HBM peak; `cpu_baseline`
-= the reference's own CPU/OpenMP code (oracle/_ref, compiled from the unmodified reference sources
-with its own flags) timed on this box's host cores on a bounded sample.
+download every step); `roofline` = the dominant kernel against the measured HBM peak (the mandated
+bound) and `roofline_issue` = the same kernel against the instruction-issue peak of the SMs (the bound
+that governs it); `cpu_baseline` = the reference's own CPU/OpenMP code (oracle/_ref, compiled from the
+unmodified reference sources with its own flags) timed on this box's host cores on a bounded sample;
+`validation` = the product checked after the timed region (N = 1: against that CPU reference run on
+the sample scene; N > 1: the slab run against a single-GPU run of the same scene).
 """
 from __future__ import annotations
 
@@ -36,6 +44,8 @@ METRIC = "particle_updates_per_sec"
 UNIT = "M particle-updates/s"
 B_ALG_STEP = 276.0     # algorithmic HBM bytes per particle-step
 B_ALG = {"density": 24.0, "force": 48.0, "integrate": 60.0, "neighbor": 144.0}
+PREROLL_TO = 60        # steps advanced before the timed region (warm-up included)
+SM_COUNT, SMSP_PER_SM = 148, 4
 
 
 def read_peaks():
@@ -176,6 +186,256 @@ def scaled_scene(scenes, name: str, world: int, mode: str):
     return pos, mass, params, dt, dx
 
 
+class Run:
+    """One workload on this rank's GPU (a single context, or this rank's slab of a distributed scene)."""
+
+    def __init__(self, args, pkg, torch, dist, scene_name, rank, world, local):
+        from sph_b200 import scenes, slab
+        self.args, self.pkg, self.torch, self.dist, self.slab = args, pkg, torch, dist, slab
+        self.rank, self.world, self.local = rank, world, local
+        capi = pkg.capi
+        self.dev = torch.device("cuda", local)
+        self.stream = torch.cuda.current_stream(self.dev)
+        pos, mass, params, dt, dx = scaled_scene(scenes, scene_name, world, args.scaling)
+        self.scene_name, self.pos, self.mass, self.params, self.dt, self.dx = scene_name, pos, mass, params, dt, dx
+        self.n_total = pos.shape[0]
+        strict = args.math == "strict"
+        refine = args.refine
+        if refine <= 0:
+            # scene-level tuning: internal cells of about one lattice spacing (~1 particle per cell): nsr / dx = 4 for the
+            # dam-break scenes (h = 2 dx), 5 for the fluid drop (h = 2.5 dx)
+            refine = int(max(1, min(6, round(float(params["neighbor_search_radius"]) / dx))))
+        self.refine = refine
+        self.opts = {capi.OPT_PAIR_KERNEL: args.pair_kernel, capi.OPT_GRID_REFINE: refine}
+        if world == 1:
+            self.n_local = self.n_total
+            ctx = pkg.Context(self.n_total, local)
+            ctx.set_stream(self.stream.cuda_stream)
+            ctx.set_option(capi.OPT_MATH_MODE, capi.MATH_STRICT if strict else capi.MATH_FAST)
+            for k, v in self.opts.items():
+                ctx.set_option(k, v)
+            ctx.set_params(params)
+            self.ctx, self.sr, self.mine, self.cuts = ctx, None, None, None
+            self.parallelism = "single"
+        else:
+            nsr = float(params["neighbor_search_radius"])
+            self.axis = axis = 2
+            cells = slab.axis_cells(pos, axis, nsr)
+            cuts = slab.plan_cuts(cells, world, 2)
+            owner = slab.rank_of_cells(cuts, cells)
+            self.n_local = int((owner == rank).sum())
+            lay = int(((cells >= cuts[rank + 1]) & (cells < cuts[rank + 1] + 2)).sum() + ((cells < cuts[rank]) & (cells >= cuts[rank] - 2)).sum())
+            cap = int(1.25 * self.n_local + 2 * lay + 65536)
+            store = slab.GpuStore(pkg, cap, local, params, strict=strict, stream=self.stream.cuda_stream, options=self.opts)
+            box_min = np.minimum(pos.min(0), [params["xmin"], params["ymin"], params["zmin"]])
+            box_max = np.maximum(pos.max(0), [params["xmax"], params["ymax"], params["zmax"]])
+            self.sr = slab.SlabRank(store, rank, cuts, axis, 2, self.n_total, box_min, box_max, max(4 * lay + 65536, self.n_local // 2))
+            self.ctx, self.store, self.cuts = store.ctx, store, cuts
+            self.mine = np.flatnonzero(owner == rank)
+            self.parallelism = (f"slab{world}(z), 2 ghost layers; per step one exchange round: device counts -> all_gather -> one host read "
+                                f"-> all_to_all_single of 32-byte records (migration + halo together)")
+        # pinned host buffers (the user's arrays at the API boundary)
+        sel = slice(None) if self.mine is None else self.mine
+        self.h_pos = torch.from_numpy(np.ascontiguousarray(pos[sel])).pin_memory()
+        self.h_mass = torch.from_numpy(np.ascontiguousarray(mass[sel])).pin_memory()
+        self.h_vel = torch.zeros((self.n_local, 3), dtype=torch.float32).pin_memory()
+        self.h_ids = None if self.mine is None else torch.from_numpy(self.mine.astype(np.int32)).pin_memory()
+        self.o_cap = self.n_local if world == 1 else self.store.capacity
+        self.o_pos = torch.empty((self.o_cap, 3), dtype=torch.float32).pin_memory()
+        self.o_vel = torch.empty((self.o_cap, 3), dtype=torch.float32).pin_memory()
+        self.o_rho = torch.empty((self.o_cap,), dtype=torch.float32).pin_memory()
+        self.o_ids = torch.empty((self.o_cap,), dtype=torch.int32).pin_memory()
+
+    def upload(self):
+        import ctypes
+        ctx = self.ctx
+        if self.world == 1:
+            ctx.upload_raw(self.n_local, self.h_pos.data_ptr(), self.h_vel.data_ptr(), self.h_mass.data_ptr())
+        else:
+            ctx._ck(ctx.L.sphb_upload_ids(ctx.h, self.n_local, ctypes.c_void_p(self.h_pos.data_ptr()), ctypes.c_void_p(self.h_vel.data_ptr()),
+                                          ctypes.c_void_p(self.h_mass.data_ptr()), ctypes.c_void_p(self.h_ids.data_ptr())))
+
+    def step(self):
+        if self.world == 1:
+            self.ctx.step(self.dt)
+        else:
+            self.slab.step_distributed(self.sr, self.dt)
+
+    def download(self):
+        import ctypes
+        ctx = self.ctx
+        if self.world == 1:
+            ctx.download_raw(self.o_pos.data_ptr(), self.o_vel.data_ptr(), self.o_rho.data_ptr(), None, None)
+            return self.n_local
+        cnt = ctypes.c_size_t()
+        ctx._ck(ctx.L.sphb_slab_download(ctx.h, self.o_cap, ctypes.c_void_p(self.o_ids.data_ptr()), ctypes.c_void_p(self.o_pos.data_ptr()),
+                                         ctypes.c_void_p(self.o_vel.data_ptr()), ctypes.c_void_p(self.o_rho.data_ptr()), None, None,
+                                         ctypes.byref(cnt)))
+        return cnt.value
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def allmax(self, x: float) -> float:
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, steps, warmup, flush, sample_clocks):
+        """Device-resident throughput: `warmup` untimed steps (after the pre-roll), then exactly `steps` timed ones."""
+        capi, torch = self.pkg.capi, self.torch
+        self.upload()
+        self.preroll = max(0, PREROLL_TO - warmup)
+        for _ in range(self.preroll + warmup):
+            self.step()
+        self.ctx.set_option(capi.OPT_STAGE_TIMING, 1)
+        self.ctx.reset_stats()
+        self.barrier()
+        sampler = ClockSampler(self.local) if (sample_clocks and self.rank == 0) else None
+        if sampler:
+            sampler.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        wall0 = time.perf_counter()
+        for k in range(steps):
+            flush.zero_()                      # evict L2 between timed steps (outside the event bracket)
+            ev[k][0].record(self.stream)
+            self.step()
+            ev[k][1].record(self.stream)
+        self.barrier()
+        wall = time.perf_counter() - wall0
+        clocks = sampler.stop() if sampler else None
+        step_ms = [a.elapsed_time(b) for a, b in ev]
+        st = self.ctx.stats()
+        self.ctx.set_option(capi.OPT_STAGE_TIMING, 0)
+        total_ms_max = self.allmax(sum(step_ms))
+        stages = {"neighbor": st["neighbor_search_time"], "density": st["density_computation_time"],
+                  "force": st["force_computation_time"], "integrate": st["integration_time"]}
+        return dict(value=self.n_total * steps / (total_ms_max * 1e-3) / 1e6, ms_per_step=total_ms_max / steps, step_ms=step_ms,
+                    wall_ms_per_step=1e3 * wall / steps, clocks=clocks, launches=int(st["kernel_launches"]),
+                    stage_ms={k: 1e3 * v / max(1, st["steps"]) for k, v in stages.items()}, max_neighbors=int(st["max_neighbors"]))
+
+    def e2e(self, steps):
+        """The same metric through the host-buffer API: pinned H2D upload + step + D2H download every step."""
+        for _ in range(2):
+            self.upload(); self.step(); self.download()
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            self.upload()
+            self.step()
+            self.download()                    # synchronises
+        self.torch.cuda.synchronize(self.dev)
+        secs = self.allmax(time.perf_counter() - t0)
+        per = self.n_local * (12 + 12 + 4 + (4 if self.world > 1 else 0))
+        return dict(value=self.n_total * steps / secs / 1e6, h2d=per, d2h=per, steps=steps)
+
+    def neighbour_stats(self):
+        """Mean accepted neighbours per particle (self included) of one more step, from the per-particle counts."""
+        capi = self.pkg.capi
+        if self.world > 1:
+            return None
+        self.ctx.set_option(capi.OPT_DEBUG_CAPTURE, 1)
+        self.step()
+        cnt = self.ctx.debug_dump(keys=False, perm=False)["nbr_count"]
+        self.ctx.set_option(capi.OPT_DEBUG_CAPTURE, 0)
+        return float(cnt.mean())
+
+    def close(self):
+        self.ctx.close()
+
+
+def pair_stencil_cells(R: int) -> int:
+    """Cells of the static spherical stencil of the mask kernels (csrc/pair_stencil.cuh: reach_of)."""
+    total = 0
+    for d0 in range(-R, R + 1):
+        for d1 in range(-R, R + 1):
+            a0, a1 = max(abs(d0) - 1, 0), max(abs(d1) - 1, 0)
+            rem = R * R - a0 * a0 - a1 * a1
+            if rem >= 0:
+                total += 2 * min(int(rem ** 0.5) + 1, R) + 1
+    return total
+
+
+def validate_single(pkg, po, capi, local, stream, sample_scene, pair_kernel):
+    """N = 1: the product against the reference's CPU code (IEEE-strict build: the parity target; its -ffast-math build
+    breaks exact q = 2 ties of the lattice differently) on the sample scene the CPU baseline ran."""
+    from sph_b200 import scenes
+    pos, mass, params, dt = scenes.make_scene(sample_scene)
+    n = pos.shape[0]
+    kind = "strict" if po.available("strict") else "port"
+    eng = po.Engine(kind, n); eng.initialize(params); eng.add_particles(pos, None, mass)
+    ctx = pkg.Context(n, local)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_option(capi.OPT_PAIR_KERNEL, pair_kernel)
+    ctx.set_option(capi.OPT_DEBUG_CAPTURE, 1)
+    ctx.set_params(params)
+    ctx.upload(pos, None, mass)
+    steps = 2
+    for _ in range(steps):
+        eng.step(dt); ctx.step(dt)
+    want, got = eng.state(), ctx.download()
+    cnt_ok = bool(np.array_equal(ctx.debug_dump(keys=False, perm=False)["nbr_count"], eng.neighbor_counts()))
+    rho_rel = float(np.abs(got["rho"].astype(np.float64) - want["rho"]).max() / np.abs(want["rho"]).max())
+    L = float(max(params["xmax"] - params["xmin"], params["ymax"] - params["ymin"], params["zmax"] - params["zmin"]))
+    pos_abs = float(np.abs(got["pos"].astype(np.float64) - want["pos"]).max())
+    sum_rho, ke, vmax = ctx.diagnostics()
+    h = float(np.float32(params["smoothing_length"]))
+    mass_rel = abs(sum_rho * h ** 3 - eng.total_mass()) / abs(eng.total_mass())
+    ke_rel = abs(ke - eng.total_energy()) / max(abs(eng.total_energy()), 1e-30)
+    ok = cnt_ok and rho_rel <= 2 * 2e-5 and pos_abs <= 2 * 1e-6 * L and mass_rel <= 1e-4 and ke_rel <= 1e-3
+    eng.close(); ctx.close()
+    return {"ok": bool(ok), "against": f"reference CPU code ({kind}) on {sample_scene} (N={n}), {steps} steps", "neighbour_counts_equal": cnt_ok,
+            "rho_max_rel": rho_rel, "pos_max_abs_over_L": pos_abs / L, "mass_diag_rel": mass_rel, "kinetic_rel": ke_rel,
+            "gates": "counts bit-exact; rho rel <= 4e-5, pos <= 2e-6 L (2 steps: 2 x the single-step gates), sum(rho) h^3 rel <= 1e-4, KE rel <= 1e-3"}
+
+
+def validate_slabs(run, steps=3):
+    """N > 1: the distributed run against a single-GPU run of the same scene on rank 0 (same cell order => same bits):
+    every particle owned exactly once, sum(rho), kinetic energy, max|v| and max neighbours."""
+    torch, dist, pkg, capi = run.torch, run.dist, run.pkg, run.pkg.capi
+    run.upload()
+    for _ in range(steps):
+        run.step()
+    cnt = run.download()
+    ids = run.o_ids[:cnt].numpy().astype(np.int64)
+    sum_rho, ke, vmax = run.ctx.diagnostics()
+    loc = torch.tensor([float(cnt), float(ids.sum() % (1 << 52)), float((ids * ids % 1000003).sum()), sum_rho, ke], dtype=torch.float64, device=run.dev)
+    dist.all_reduce(loc, op=dist.ReduceOp.SUM)
+    mx = torch.tensor([vmax, float(run.ctx.stats()["max_neighbors"])], dtype=torch.float64, device=run.dev)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    out = None
+    if run.rank == 0:
+        n = run.n_total
+        all_ids = np.arange(n, dtype=np.int64)
+        owners_ok = int(loc[0].item()) == n and abs(loc[1].item() - float(all_ids.sum() % (1 << 52))) < 0.5 \
+            and abs(loc[2].item() - float((all_ids * all_ids % 1000003).sum())) < 0.5
+        ref = pkg.Context(n, run.local)
+        ref.set_stream(run.stream.cuda_stream)
+        for k, v in run.opts.items():
+            ref.set_option(k, v)
+        ref.set_option(capi.OPT_LAYOUT_MAJOR, run.axis)
+        ref.set_params(run.params)
+        ref.upload(run.pos, None, run.mass)
+        for _ in range(steps):
+            ref.step(run.dt)
+        r_rho, r_ke, r_vmax = ref.diagnostics()
+        r_maxn = int(ref.stats()["max_neighbors"])
+        ref.close()
+        rho_rel = abs(loc[3].item() - r_rho) / abs(r_rho)
+        ke_rel = abs(loc[4].item() - r_ke) / max(abs(r_ke), 1e-30)
+        v_rel = abs(mx[0].item() - r_vmax) / max(abs(r_vmax), 1e-30)
+        ok = owners_ok and rho_rel <= 1e-9 and ke_rel <= 1e-9 and v_rel <= 1e-6 and int(mx[1].item()) == r_maxn
+        out = {"ok": bool(ok), "against": f"single-GPU run of the same scene on rank 0 (N={n}, cell order z-major like the slabs), {steps} steps",
+               "every_particle_owned_once": bool(owners_ok), "sum_rho_rel": rho_rel, "kinetic_rel": ke_rel, "max_speed_rel": v_rel,
+               "max_neighbors": [int(mx[1].item()), r_maxn],
+               "gates": "owners == 1 (count + two id checksums); sum(rho), KE rel <= 1e-9 (fp64 sums of identical fp32 fields), max|v| rel <= 1e-6, max neighbours equal"}
+    run.barrier()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -186,213 +446,138 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-
     pkg = graft.load_package()
-    from sph_b200 import scenes, slab
     capi = pkg.capi
-
-    pos, mass, params, dt, dx = scaled_scene(scenes, args.scene, world, args.scaling)
-    n_total = pos.shape[0]
-    stream = torch.cuda.current_stream(dev)
-    strict = args.math == "strict"
-    if args.refine <= 0:
-        # scene-level tuning: internal cells of about one lattice spacing (~1 particle per cell): nsr / dx = 4 for the
-        # dam-break scenes (h = 2 dx), 5 for the fluid drop (h = 2.5 dx)
-        args.refine = int(max(1, min(6, round(float(params["neighbor_search_radius"]) / dx))))
-    opts = {capi.OPT_PAIR_KERNEL: args.pair_kernel, capi.OPT_GRID_REFINE: args.refine}
-
-    if world == 1:
-        n_local = n_total
-        ctx = pkg.Context(n_total, local)
-        ctx.set_stream(stream.cuda_stream)
-        ctx.set_option(capi.OPT_MATH_MODE, capi.MATH_STRICT if strict else capi.MATH_FAST)
-        for k, v in opts.items():
-            ctx.set_option(k, v)
-        ctx.set_params(params)
-        mine = None
-        parallelism = "single"
-    else:
-        nsr = float(params["neighbor_search_radius"])
-        axis = 2
-        cells = slab.axis_cells(pos, axis, nsr)
-        cuts = slab.plan_cuts(cells, world, 2)
-        owner = slab.rank_of_cells(cuts, cells)
-        n_local = int((owner == rank).sum())
-        lay = int(((cells >= cuts[rank + 1]) & (cells < cuts[rank + 1] + 2)).sum() + ((cells < cuts[rank]) & (cells >= cuts[rank] - 2)).sum())
-        cap = int(1.25 * n_local + 2 * lay + 65536)
-        store = slab.GpuStore(pkg, cap, local, params, strict=strict, stream=stream.cuda_stream, options=opts)
-        box_min = np.minimum(pos.min(0), [params["xmin"], params["ymin"], params["zmin"]])
-        box_max = np.maximum(pos.max(0), [params["xmax"], params["ymax"], params["zmax"]])
-        sr = slab.SlabRank(store, rank, cuts, axis, 2, n_total, box_min, box_max, max(4 * lay + 65536, n_local // 2))
-        ctx = store.ctx
-        mine = np.flatnonzero(owner == rank)
-        parallelism = f"slab{world}(z), 2-layer halo, NCCL all_to_all migration + isend/irecv halo"
-
-    # pinned host buffers (the user's arrays at the API boundary)
-    sel = slice(None) if mine is None else mine
-    h_pos = torch.from_numpy(np.ascontiguousarray(pos[sel])).pin_memory()
-    h_mass = torch.from_numpy(np.ascontiguousarray(mass[sel])).pin_memory()
-    h_vel = torch.zeros((n_local, 3), dtype=torch.float32).pin_memory()
-    h_ids = None if mine is None else torch.from_numpy(mine.astype(np.int32)).pin_memory()
-    o_cap = n_local if world == 1 else store.capacity
-    o_pos = torch.empty((o_cap, 3), dtype=torch.float32).pin_memory()
-    o_vel = torch.empty((o_cap, 3), dtype=torch.float32).pin_memory()
-    o_rho = torch.empty((o_cap,), dtype=torch.float32).pin_memory()
-    o_ids = torch.empty((o_cap,), dtype=torch.int32).pin_memory()
-
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    import ctypes
-
-    def upload():
-        if world == 1:
-            ctx.upload_raw(n_local, h_pos.data_ptr(), h_vel.data_ptr(), h_mass.data_ptr())
-        else:
-            ctx._ck(ctx.L.sphb_upload_ids(ctx.h, n_local, ctypes.c_void_p(h_pos.data_ptr()), ctypes.c_void_p(h_vel.data_ptr()),
-                                          ctypes.c_void_p(h_mass.data_ptr()), ctypes.c_void_p(h_ids.data_ptr())))
-
-    def step():
-        if world == 1:
-            ctx.step(dt)
-        else:
-            slab.step_distributed(sr, dt)
-
-    def download():
-        if world == 1:
-            ctx.download_raw(o_pos.data_ptr(), o_vel.data_ptr(), o_rho.data_ptr(), None, None)
-            return n_local
-        cnt = ctypes.c_size_t()
-        ctx._ck(ctx.L.sphb_slab_download(ctx.h, o_cap, ctypes.c_void_p(o_ids.data_ptr()), ctypes.c_void_p(o_pos.data_ptr()),
-                                         ctypes.c_void_p(o_vel.data_ptr()), ctypes.c_void_p(o_rho.data_ptr()), None, None,
-                                         ctypes.byref(cnt)))
-        return cnt.value
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    # ---- device-resident throughput -------------------------------------------------------------
-    upload()
-    for _ in range(args.warmup):
-        step()
-    ctx.set_option(capi.OPT_STAGE_TIMING, 1)
-    ctx.reset_stats()
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    wall0 = time.perf_counter()
-    for k in range(args.steps):
-        flush.zero_()                      # evict L2 between timed steps (outside the event bracket)
-        ev[k][0].record(stream)
-        step()
-        ev[k][1].record(stream)
-    barrier()
-    wall = time.perf_counter() - wall0
-    clocks = sampler.stop() if rank == 0 else None
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = sum(step_ms)
-    st = ctx.stats()
-    ctx.set_option(capi.OPT_STAGE_TIMING, 0)
-    launches = int(st["kernel_launches"])
-
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    run = Run(args, pkg, torch, dist, args.scene, rank, world, local)
+    m = run.timed(args.steps, args.warmup, flush, sample_clocks=True)
+    e2e = run.e2e(max(3, min(args.steps, 10)))
+    mean_nbrs = run.neighbour_stats()
+    validation = validate_slabs(run) if world > 1 else None
+    n_total, n_local = run.n_total, run.n_local
+    slab_stats = None
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
-    value = n_total * args.steps / (total_ms_max * 1e-3) / 1e6
-
-    # ---- end-to-end through the host-buffer API --------------------------------------------------
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        upload(); step(); download()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        upload()
-        step()
-        download()                         # synchronises
-    torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = n_total * e2e_steps / float(t.item()) / 1e6
-    h2d = n_local * (12 + 12 + 4 + (4 if world > 1 else 0))
-    d2h = n_local * (12 + 12 + 4 + (4 if world > 1 else 0))
-
+        slab_stats = {"cuts": [int(c) for c in run.cuts[1:-1]], "owned_rank0": n_local, **run.sr.stats}
     if rank != 0:
-        ctx.close()
+        run.close()
         if world > 1:
             dist.destroy_process_group()
         return
+    stream = run.stream
+    run.close()
 
-    # ---- roofline of the dominant kernel (stage times from CUDA events inside the timed region) ---
+    # ---- rooflines of the dominant kernel (stage times from CUDA events inside the timed region) ---
     peak, peak_src = read_peaks()
-    stages = {"neighbor": st["neighbor_search_time"], "density": st["density_computation_time"],
-              "force": st["force_computation_time"], "integrate": st["integration_time"]}
+    stages = m["stage_ms"]
     dom = max(("density", "force"), key=lambda k: stages[k])
-    dom_s = stages[dom] / max(1, st["steps"])
-    n_kernel = n_local     # particles the profiled kernel (rank 0's) processes per launch
-    achieved = B_ALG[dom] * n_kernel / dom_s / 1e9 if dom_s > 0 else 0.0
-    traffic = None
+    dom_s = stages[dom] * 1e-3
+    achieved = B_ALG[dom] * n_local / dom_s / 1e9 if dom_s > 0 else 0.0
+    prof = {}
     tp = ROOT / "profiles" / "traffic.json"
     if tp.exists():
         try:
-            rec = json.loads(tp.read_text()).get(args.scene, {}).get(f"k_{dom}")
-            if rec and world == 1:
-                traffic = rec["dram_bytes_per_launch"]
+            prof = json.loads(tp.read_text()).get(args.scene, {}) if world == 1 else {}
         except Exception:
-            traffic = None
+            prof = {}
+    rec = prof.get(f"k_{dom}", {})
     roofline = {"bound": "hbm", "kernel": f"k_{dom}", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,
+                "frac": round(achieved / peak, 5), "traffic": rec.get("dram_bytes_per_launch"), "peak_source": peak_src,
                 "algorithmic_bytes_per_particle": B_ALG[dom], "kernel_ms": round(1e3 * dom_s, 4),
-                "note": "pair kernels are instruction-issue bound at h = 2 dx (hundreds of candidate pairs per particle; ncu: 85 % / 74 % "
-                        "issue-active, 6-9 % DRAM utilisation, profiles/r1d_pair_kernels_mask_full.md); traffic exceeds the algorithmic "
-                        "bytes on purpose (neighbour bitmasks handed from the density to the force pass); HBM fraction reported as mandated"}
-    step_s = total_ms_max * 1e-3 / args.steps
+                "note": "the pair kernels are bound by instruction issue and the FMA / ALU pipes, not by HBM (hundreds of candidate pairs per "
+                        "particle at h = 2 dx; see roofline_issue and profiles/r2_pair_kernels.md); traffic exceeds the algorithmic bytes on "
+                        "purpose (neighbour bitmasks handed from the density to the force pass); HBM fraction reported as mandated"}
+    clk = (m["clocks"] or {}).get("sm_mhz") or 1965.0
+    issue_peak = SM_COUNT * SMSP_PER_SM * clk * 1e6 / 1e9     # G warp-instructions / s: one per SM sub-partition per clock
+    winstr = rec.get("warp_instructions_per_launch")
+    roofline_issue = {"bound": "issue", "kernel": f"k_{dom}", "peak": round(issue_peak, 1), "unit": "G warp-instr/s",
+                      "peak_source": f"148 SMs x 4 sub-partitions x {clk:.0f} MHz (median SM clock of the timed region)",
+                      "achieved": round(winstr / dom_s / 1e9, 1) if winstr else None,
+                      "frac": round(winstr / dom_s / 1e9 / issue_peak, 4) if winstr else None,
+                      "warp_instructions_per_launch": winstr,
+                      "source": "smsp__inst_executed.sum of the same kernel on this workload (ncu, profiles/traffic.json)" if winstr else
+                                "no ncu instruction count committed for this workload"}
+    pairs = None
+    if mean_nbrs is not None and args.pair_kernel == 2 and run.refine >= 4:
+        cand = pair_stencil_cells(run.refine) * (n_local / max(1, _occupied_cells(run)))   # candidates per particle ~ stencil cells x particles per cell
+        pairs = {"accepted_per_particle": round(mean_nbrs, 2),
+                 "accepted_pair_interactions_per_s_density": round(mean_nbrs * n_local / (stages["density"] * 1e-3) / 1e9, 2),
+                 "accepted_pair_interactions_per_s_force": round(mean_nbrs * n_local / (stages["force"] * 1e-3) / 1e9, 2),
+                 "unit": "G pair interactions / s",
+                 "stencil_cells": pair_stencil_cells(run.refine)}
+    step_s = m["ms_per_step"] * 1e-3
     extra = {
         "step_hbm_frac": round(B_ALG_STEP * n_total / world / step_s / 1e9 / peak, 5),
-        "stage_ms_rank0": {k: round(1e3 * v / max(1, st["steps"]), 4) for k, v in stages.items()},
-        "max_neighbors": int(st["max_neighbors"]),
-        "ms_per_step_min": round(min(step_ms), 4), "ms_per_step_max": round(max(step_ms), 4),
-        "wall_ms_per_step_incl_l2_flush": round(1e3 * wall / args.steps, 3),
+        "step_dram_bytes": prof.get("step", {}).get("dram_bytes"),
+        "stage_ms_rank0": {k: round(v, 4) for k, v in stages.items()},
+        "max_neighbors": m["max_neighbors"],
+        "ms_per_step_min": round(min(m["step_ms"]), 4), "ms_per_step_max": round(max(m["step_ms"]), 4),
+        "wall_ms_per_step_incl_l2_flush": round(m["wall_ms_per_step"], 3),
+        "pair_interactions": pairs,
     }
-    if world > 1:
-        extra["slab"] = {"cuts": [int(c) for c in cuts[1:-1]], "owned_rank0": n_local, **sr.stats}
+    if slab_stats:
+        extra["slab"] = slab_stats
 
-    # ---- CPU baseline: the reference's own code on this box's host cores, bounded sample ---------
+    # ---- CPU baseline: the reference's own code on this box's host cores, bounded sample; validation against it ----
     cpu = None
     if not args.no_cpu and world == 1:      # contract: CPU baseline on rank 0 at N = 1 only
+        sample = args.cpu_scene or "dam_break_347k"
         try:
-            r = cpu_reference_run(args.cpu_scene or "dam_break_347k", 3, 1)
+            r = cpu_reference_run(sample, 3, 1)
             cpu = {"value": round(r["value"], 6), "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
         except Exception as e:  # the baseline must never take the GPU number down with it
             cpu = {"value": None, "unit": UNIT, "cores": None, "kind": "unavailable", "sample": f"failed: {e}"}
+        try:
+            validation = validate_single(pkg, graft.load_oracle(), capi, local, stream, sample, args.pair_kernel)
+        except Exception as e:
+            validation = {"ok": False, "error": str(e)}
+
+    # ---- second workload of the metric ("at 1M and 10M"): the other dam break, device-resident rate only ----
+    if world == 1 and args.also:
+        try:
+            r2 = Run(args, pkg, torch, dist, args.also, rank, world, local)
+            m2 = r2.timed(args.steps, args.warmup, flush, sample_clocks=False)
+            extra["also"] = {args.also: {"value": round(m2["value"], 3), "unit": UNIT, "ms_per_step": round(m2["ms_per_step"], 4),
+                                         "particles_total": r2.n_total, "stage_ms": {k: round(v, 4) for k, v in m2["stage_ms"].items()},
+                                         "step_hbm_frac": round(B_ALG_STEP * r2.n_total / (m2["ms_per_step"] * 1e-3) / 1e9 / peak, 5),
+                                         "preroll_steps": r2.preroll, "max_neighbors": m2["max_neighbors"]}}
+            r2.close()
+        except Exception as e:
+            extra["also"] = {args.also: {"error": str(e)}}
 
     line = {
-        "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(total_ms_max / args.steps, 4), "higher_is_better": True,
-        "scaling": args.scaling if world > 1 else "weak",
+        "metric": METRIC, "value": round(m["value"], 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(m["ms_per_step"], 4), "higher_is_better": True,
+        "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.scene, "dx": dx, "particles_total": n_total, "particles_rank0": n_local, "h_over_dx": 2.0,
-                   "params": "P-tame", "dt": dt, "math": args.math, "pair_kernel": args.pair_kernel, "grid_refine": args.refine,
-                   "parallelism": parallelism, "l2": "flushed between timed steps (512 MiB write outside the event bracket)"},
-        "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "what": "sphb_upload(host pos,vel,mass) + sphb_step + sphb_download(host pos,vel,rho) per step"
-                                            + (" per rank, slab exchange included" if world > 1 else "")},
-        "gpu_launches": launches,
-        "clocks": clocks,
+        "config": {"workload": args.scene, "dx": run.dx, "particles_total": n_total, "particles_rank0": n_local, "h_over_dx": 2.0,
+                   "params": "P-tame", "dt": run.dt, "math": args.math, "pair_kernel": args.pair_kernel, "grid_refine": run.refine,
+                   "parallelism": run.parallelism, "preroll_steps": run.preroll,
+                   "l2": "flushed between timed steps (512 MiB write outside the event bracket)"},
+        "e2e": {"value": round(e2e["value"], 3), "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                "steps": e2e["steps"], "what": "sphb_upload(host pos,vel,mass) + sphb_step + sphb_download(host pos,vel,rho) per step"
+                                                + (" per rank, slab exchange included" if world > 1 else "")},
+        "gpu_launches": m["launches"],
+        "clocks": m["clocks"],
         "roofline": roofline,
+        "roofline_issue": roofline_issue,
         "cpu_baseline": cpu,
+        "validation": validation,
         "extra": extra,
     }
     print(json.dumps(line), flush=True)
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def _occupied_cells(run):
+    """Occupied internal cells of the scene's initial lattice (cell = neighbor_search_radius / refine)."""
+    cell = float(run.params["neighbor_search_radius"]) / run.refine
+    c = np.floor(run.pos / np.float32(cell)).astype(np.int64)
+    c -= c.min(0)
+    ext = c.max(0) + 1
+    lin = (c[:, 0] * ext[1] + c[:, 1]) * ext[2] + c[:, 2]
+    return int(np.unique(lin).size)
 
 
 def main():
@@ -401,7 +586,8 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scene", default="dam_break_1M")
+    ap.add_argument("--scene", default="dam_break_10M")
+    ap.add_argument("--also", default=None, help="second workload measured at N = 1 (default: the other of dam_break_1M / dam_break_10M)")
     ap.add_argument("--cpu-scene", default=None)
     ap.add_argument("--math", default="fast", choices=["fast", "strict"])
     ap.add_argument("--pair-kernel", type=int, default=2)
@@ -410,6 +596,8 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.also is None:
+        args.also = {"dam_break_10M": "dam_break_1M", "dam_break_1M": "dam_break_10M"}.get(args.scene, "")
     if args.impl == "reference":
         run_reference_arm(args)
     else:

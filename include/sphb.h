@@ -70,7 +70,11 @@ typedef struct sphb_stats {
     uint64_t total_neighbor_queries;
     uint64_t steps;
     uint64_t kernel_launches;      /* kernels of this library launched since the last reset */
+    uint64_t error_flags;          /* sticky since the last reset.  SPHB_ERR_OUTSIDE_CELL_BOX (bit 0): a position fell outside
+                                    * the internal cell table (NaN/inf, or outside the slab's ghost range) and was binned
+                                    * into an edge cell — neighbour sets stay exact (the radius test is), the step is slower */
 } sphb_stats;
+#define SPHB_ERR_OUTSIDE_CELL_BOX 1u
 
 enum {
     /* 0 = strict: every fp32 operation of density/force/integration is issued in the reference's

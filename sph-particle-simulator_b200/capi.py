@@ -61,6 +61,7 @@ class SphbStats(C.Structure):
         ("density_computation_time", C.c_double), ("force_computation_time", C.c_double),
         ("integration_time", C.c_double), ("max_neighbors", C.c_uint64),
         ("total_neighbor_queries", C.c_uint64), ("steps", C.c_uint64), ("kernel_launches", C.c_uint64),
+        ("error_flags", C.c_uint64),
     ]
 
 
@@ -277,13 +278,13 @@ class Context:
         self._ck(self.L.sphb_diagnostics(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
-    def debug_dump(self) -> dict:
+    def debug_dump(self, keys=True, perm=True, counts=True) -> dict:
         n = self.size
-        keys = np.zeros(n, np.uint64)
-        perm = np.zeros(n, np.uint32)
-        cnt = np.zeros(n, np.uint32)
-        self._ck(self.L.sphb_debug_dump(self.h, _ptr(keys), _ptr(perm), _ptr(cnt)))
-        return {"keys": keys, "perm": perm, "nbr_count": cnt}
+        k = np.zeros(n, np.uint64) if keys else None
+        p = np.zeros(n, np.uint32) if perm else None
+        c = np.zeros(n, np.uint32) if counts else None
+        self._ck(self.L.sphb_debug_dump(self.h, _ptr(k), _ptr(p), _ptr(c)))
+        return {"keys": k, "perm": p, "nbr_count": c}
 
     # ---- slab decomposition (multi-GPU) -----------------------------------------------------------
     def set_slab(self, axis: int, own_lo: int, own_hi: int, halo_layers: int, id_space: int, box_min, box_max):

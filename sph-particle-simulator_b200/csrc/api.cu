@@ -198,10 +198,11 @@ int make_grid(sphb_ctx* c, GridDesc* g, int refine, int layout_major = -1, int p
         int lo = host_cell(c->box_min[a], g->inv_cell), hi = host_cell(c->box_max[a], g->inv_cell);
         if (hi < lo) { int t = lo; lo = hi; hi = t; }
         if (c->slab_on && a == c->slab.axis) {
-            // only the owned cells and their ghost layers can be populated (+1 internal cell of slack for
-            // the rounding difference between floor(p * inv) * refine and floor(p * (inv * refine)))
-            const int slo = refine * (c->slab.own_lo - c->slab.halo_layers) - 1;
-            const int shi = refine * (c->slab.own_hi + c->slab.halo_layers);
+            // only the owned reference cells and their ghost layers can be populated: the internal cells of the positions
+            // at their two faces, by the same formula as the keys (internal cells are 0.1 % larger than
+            // neighbor_search_radius / refine), +-1 cell of slack for the roundings of the two products
+            const int slo = host_cell((float)(c->slab.own_lo - c->slab.halo_layers) * cell, g->inv_cell) - 1;
+            const int shi = host_cell((float)(c->slab.own_hi + c->slab.halo_layers) * cell, g->inv_cell) + 1;
             if (lo < slo) lo = slo;
             if (hi > shi) hi = shi;
             if (hi < lo) hi = lo;
@@ -849,6 +850,7 @@ int sphb_get_stats(sphb_ctx* c, sphb_stats* out) {
     if (rc) return rc;
     drain_events(c);
     c->stats.max_neighbors = c->h_sc->max_neighbors;
+    c->stats.error_flags = c->h_sc->error_flags;
     *out = c->stats;
     return SPHB_OK;
 }
@@ -856,7 +858,7 @@ int sphb_get_stats(sphb_ctx* c, sphb_stats* out) {
 int sphb_reset_stats(sphb_ctx* c) {
     if (!c) return SPHB_E_INVALID;
     CU(c, cudaSetDevice(c->device));
-    CU(c, cudaMemsetAsync(&c->sc->max_neighbors, 0, sizeof(unsigned), c->stream));
+    CU(c, cudaMemsetAsync(&c->sc->max_neighbors, 0, 2 * sizeof(unsigned), c->stream));   // max_neighbors, error_flags
     drain_events(c);
     c->stats = sphb_stats{};
     return SPHB_OK;

@@ -31,6 +31,14 @@ def test_params_struct_layout(pkg):
     assert pkg.DEFAULT_PARAMS["neighbor_search_radius"] == 0.04 and pkg.DEFAULT_PARAMS["damping"] == 0.99
 
 
+def test_stats_struct_layout(pkg):
+    # sphb_stats of include/sphb.h: five doubles, then five 64-bit counters, in this order
+    assert ctypes.sizeof(pkg.capi.SphbStats) == 80
+    text = (ROOT / "include" / "sphb.h").read_text()
+    body = re.sub(r"/\*.*?\*/", "", text[text.index("typedef struct sphb_stats"):text.index("} sphb_stats;")], flags=re.S)
+    assert re.findall(r"(?:double|uint64_t)\s+(\w+);", body) == [f for f, _ in pkg.capi.SphbStats._fields_]
+
+
 def test_fails_loudly_without_gpu(pkg, has_gpu):
     if has_gpu:
         pytest.skip("a GPU is present")
