@@ -172,6 +172,58 @@ def main():
         "adaptive_total_mass": float(np.float32(e.total_mass())), "adaptive_total_energy": float(np.float32(e.total_energy())),
     }
     e.close()
+
+    # ---- 5. adaptive timestep where the CFL rule bites (compute_cfl_timestep, sph_engine.cpp:312-333) ----
+    # The tame scene above never leaves dt = params.timestep.  Three runs whose dt comes from the other two branches:
+    #   perf_test      the reference's own benchmark set-up (benchmarks/performance_test.cpp:85-125: capacity 2 x 5000,
+    #                  h = (m / rho0)^(1/3) = 0.01 with the default 0.04 search radius, initialize_dam_break truncated to
+    #                  10 000 wall particles, step() with dt = 0): the default parameters explode, so after the first step
+    #                  both CFL terms are far below params.timestep
+    #   fast_cloud     tame dam break with initial speeds up to 40: dt_cfl = CFL h / max|v| wins from the first step
+    #   light_zero*    tame dam break with a light particle 0: dt_force = CFL sqrt(h / |a_0|) wins (every step / some steps)
+    def cfl_terms(e, prm):
+        st = e.state()
+        vmax = float(np.sqrt((st["vel"].astype(np.float64) ** 2).sum(1)).max())
+        a0 = float(np.sqrt((st["acc"][0].astype(np.float64) ** 2).sum()))
+        h, cfl = float(prm["smoothing_length"]), float(prm["CFL_factor"])
+        return cfl * h / (vmax + 1e-6), cfl * np.sqrt(h / (a0 + 1e-6))
+
+    def adaptive_run(e, prm, steps):
+        dts, times, branch = [], [], []
+        for _ in range(steps):
+            d_cfl, d_force = cfl_terms(e, prm)
+            dt = e.cfl_timestep()
+            branch.append("timestep" if np.float32(dt) == np.float32(prm["timestep"]) else ("cfl" if d_cfl < d_force else "force"))
+            dts.append(dt); e.step(0.0); times.append(e.time)
+        st = e.state()
+        return {"dts": [float(np.float32(x)) for x in dts], "times": [float(np.float32(x)) for x in times], "branch": branch,
+                "final_pos_sha256": sha(st["pos"]), "final_vel_sha256": sha(st["vel"]), "final_rho_sha256": sha(st["rho"])}
+
+    cfl_cases = {}
+    pt = dict(defaults)
+    pt.update(rest_density=1000.0, gas_constant=2000.0, viscosity=0.001, particle_mass=0.001, timestep=0.001, gravity=-9.81)
+    pt["smoothing_length"] = float(np.float32(np.float32(np.float32(1.0) / np.float32(1000.0) * np.float32(0.001)) ** np.float32(1.0 / 3.0)))
+    e = po.Engine(KIND, 10000); e.initialize(pt); e.initialize_dam_break()
+    cfl_cases["perf_test"] = {"capacity": 10000, "n": int(e.size), "params": {k: float(np.float32(v)) for k, v in e.get_parameters().items()},
+                              **adaptive_run(e, e.get_parameters(), 5)}
+    e.close()
+    pos, mass, prm, dt = scenes.dam_break_scene(0.02)
+    rng = np.random.default_rng(77)
+    vel = (rng.normal(size=pos.shape) * 12.0).astype(np.float32)
+    e = po.Engine(KIND, pos.shape[0]); e.initialize(prm); e.add_particles(pos, vel, mass)
+    cfl_cases["fast_cloud"] = {"vel_seed": 77, "vel_sigma": 12.0, **adaptive_run(e, prm, 5)}
+    e.close()
+    # particle 0 made light: a = F / m_i (quirk Q6) gives it the largest acceleration while every speed stays moderate,
+    # so dt_force = CFL sqrt(h / |a_0|) (particle 0 only, previous step's a: quirk Q10) undercuts dt_cfl
+    for name, fac in (("light_zero", 1.0e-2), ("light_zero_mixed", 3.0e-3)):
+        mass2 = mass.copy()
+        mass2[0] *= np.float32(fac)
+        e = po.Engine(KIND, pos.shape[0]); e.initialize(prm); e.add_particles(pos, None, mass2)
+        cfl_cases[name] = {"mass0_factor": fac, **adaptive_run(e, prm, 5)}
+        e.close()
+    for name, c in cfl_cases.items():
+        print(name, c["branch"], c["dts"])
+    meta["cfl_cases"] = cfl_cases
     # generator hashes (scene parity without storing the arrays)
     gens = {}
     for name in ("dam_break_13k", "dam_break_85k", "dam_break_347k", "dam_break_1M", "fluid_drop_65k", "fluid_drop_1M"):

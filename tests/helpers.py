@@ -63,3 +63,22 @@ def rel_err(a, b):
     a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
     scale = np.abs(b).max()
     return float(np.abs(a - b).max() / scale) if scale > 0 else float(np.abs(a - b).max())
+
+
+def cfl_case_inputs(po, scenes, name: str, case: dict):
+    """Initial state (params, pos, vel, mass, capacity) of a CFL-limited adaptive-dt case of tests/golden/scalars.json
+    (tests/golden/make_golden.py, section 5)."""
+    if name == "perf_test":          # the reference benchmark's set-up: initialize(params) + initialize_dam_break(), truncated
+        prm = {k: np.float32(v) for k, v in case["params"].items()}
+        e = po.Engine("port", case["capacity"]); e.initialize(prm); e.initialize_dam_break()
+        s0 = e.state(); e.close()
+        assert s0["pos"].shape[0] == case["n"]
+        return prm, s0["pos"], None, s0["mass"], case["capacity"]
+    pos, mass, prm, _ = scenes.dam_break_scene(0.02)
+    vel = None
+    if name == "fast_cloud":
+        vel = (np.random.default_rng(case["vel_seed"]).normal(size=pos.shape) * case["vel_sigma"]).astype(np.float32)
+    else:
+        mass = mass.copy()
+        mass[0] *= np.float32(case["mass0_factor"])
+    return prm, pos, vel, mass, pos.shape[0]

@@ -137,6 +137,37 @@ def test_adaptive_timestep(pkg):
     ctx.close()
 
 
+@pytest.mark.parametrize("name", ["perf_test", "fast_cloud", "light_zero", "light_zero_mixed"])
+def test_cfl_limited_adaptive_timestep(pkg, po, name):
+    """k_cfl_dt on the branches the tame scenes never take: dt_cfl = CFL h / max|v| and dt_force = CFL sqrt(h / |a_0|)
+    (particle 0 only, previous step's a), incl. the set-up of the reference's own benchmarks/performance_test.cpp
+    (exploding default parameters, step() with dt = 0).  Strict mode: every dt, every time and the final state are the
+    reference's bits (golden vectors from the unmodified reference, tests/golden/make_golden.py section 5)."""
+    import hashlib
+    from helpers import cfl_case_inputs
+    from sph_b200 import scenes
+    case = json.loads((GOLDEN / "scalars.json").read_text())["cfl_cases"][name]
+    prm, pos, vel, mass, cap = cfl_case_inputs(po, scenes, name, case)
+    ctx = make_ctx(pkg, cap, prm, strict=True)
+    ctx.upload(pos, vel, mass)
+    for k, (want_dt, want_t) in enumerate(zip(case["dts"], case["times"])):
+        assert np.float32(ctx.cfl_timestep()) == np.float32(want_dt), f"{name} step {k} ({case['branch'][k]} branch)"
+        ctx.step(0.0)
+        assert np.float32(ctx.get_time()[0]) == np.float32(want_t)
+    s = ctx.download()
+    for f in ("pos", "vel", "rho"):
+        assert hashlib.sha256(np.ascontiguousarray(s[f]).tobytes()).hexdigest() == case[f"final_{f}_sha256"], f"{name} final {f}"
+    # fast mode walks the same branches: same dt up to the fast-mode tolerances of the velocities behind it
+    if name != "perf_test":        # (exploding parameters: fast and strict diverge in the last bits of 1e8-sized velocities)
+        cf = make_ctx(pkg, cap, prm, strict=False)
+        cf.upload(pos, vel, mass)
+        for want_dt in case["dts"]:
+            assert abs(cf.cfl_timestep() - want_dt) <= 1e-3 * want_dt
+            cf.step(0.0)
+        cf.close()
+    ctx.close()
+
+
 def test_walk_radius_two_equals_one(pkg):
     """27-cell walk vs the reference's 125-cell walk (spatial_hash.cpp:35): identical sets and sums."""
     g = load_golden("cloud600")
@@ -269,6 +300,39 @@ def test_full_size_properties_1M(pkg):
     a, b = res["f1"][1], res["s1"][1]
     assert rel_err(a["rho"], b["rho"]) <= 2 * TOL_RHO
     assert np.abs(a["pos"].astype(np.float64) - b["pos"]).max() <= 2 * TOL_POS * 0.8
+
+
+@pytest.mark.parametrize("scene", ["dam_break_1M", "fluid_drop_1M"])
+def test_full_size_step_vs_oracle(pkg, po, scene):
+    """BASELINE.json configs[1] and configs[2] at FULL size against the oracle itself (the C restatement, OpenMP, ~1 s per
+    step on the box's host cores): keys, sorted permutation and neighbour counts bit-exact in both math modes, strict
+    fields bit-exact, the default fast path (fluid drop: the R = 5 kernels at size) inside the single-step gates."""
+    from sph_b200 import scenes
+    pos, mass, prm, dt = scenes.make_scene(scene)
+    n = pos.shape[0]
+    ora = po.Engine("port", n); ora.initialize(prm); ora.add_particles(pos, None, mass)
+    keys = ora.keys()
+    ora.step(dt)
+    want, counts = ora.state(), ora.neighbor_counts()
+    ora.close()
+    refine = int(max(1, min(6, round(float(prm["neighbor_search_radius"]) / scenes.SCENES[scene][1]))))
+    L = float(max(prm["xmax"] - prm["xmin"], prm["ymax"] - prm["ymin"], prm["zmax"] - prm["zmin"]))
+    for strict in (True, False):
+        ctx = make_ctx(pkg, n, prm, strict=strict, OPT_GRID_REFINE=refine)
+        ctx.upload(pos, None, mass)
+        ctx.step(dt)
+        d, got = ctx.debug_dump(), ctx.download()
+        what = f"{scene} {'strict' if strict else 'fast'}"
+        assert_bits(d["keys"], keys, f"{what} keys")
+        assert_bits(d["perm"], stable_perm(keys), f"{what} sorted permutation")
+        assert_bits(d["nbr_count"], counts, f"{what} neighbour counts")
+        assert ctx.stats()["max_neighbors"] == int(counts.max())
+        if strict:
+            for f in ("rho", "P", "acc", "pos", "vel"):
+                assert_bits(got[f], want[f], f"{what} {f}")
+        else:
+            check_fast(got, want, L, what)
+        ctx.close()
 
 
 def test_sparse_fluid_drop_multi_step(pkg, po):

@@ -92,6 +92,29 @@ def test_adaptive_timestep_and_scalars(po, graft):
     e.close()
 
 
+@pytest.mark.parametrize("name", ["perf_test", "fast_cloud", "light_zero", "light_zero_mixed"])
+def test_cfl_limited_adaptive_timestep(po, graft, name):
+    """compute_cfl_timestep where it bites (sph_engine.cpp:312-333): dt_cfl = CFL h / max|v| and dt_force =
+    CFL sqrt(h / |a_0|) (particle 0 only, previous step's acceleration), incl. the reference benchmark's own set-up
+    (benchmarks/performance_test.cpp:85-125).  The C restatement reproduces the reference's dt sequence bit for bit."""
+    from helpers import cfl_case_inputs
+    import hashlib
+    graft.load_package()
+    from sph_b200 import scenes
+    case = json.loads((GOLDEN / "scalars.json").read_text())["cfl_cases"][name]
+    assert set(case["branch"]) - {"timestep"}, "the case must leave dt = params.timestep"
+    prm, pos, vel, mass, cap = cfl_case_inputs(po, scenes, name, case)
+    e = po.Engine("port", cap); e.initialize(prm); e.add_particles(pos, vel, mass)
+    for want_dt, want_t in zip(case["dts"], case["times"]):
+        assert np.float32(e.cfl_timestep()) == np.float32(want_dt)
+        e.step(0.0)
+        assert np.float32(e.time) == np.float32(want_t)
+    st = e.state()
+    for f in ("pos", "vel", "rho"):
+        assert hashlib.sha256(np.ascontiguousarray(st[f]).tobytes()).hexdigest() == case[f"final_{f}_sha256"], f
+    e.close()
+
+
 def test_engine_quirks(po):
     """Behavioural quirks of SPHEngine the drop-in must keep."""
     meta = json.loads((GOLDEN / "scalars.json").read_text())

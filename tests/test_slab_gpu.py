@@ -210,3 +210,30 @@ def test_sparse_drop_slabs_track_bbox(pkg):
         assert (got["owners"] == 1).all()
         for f in ("pos", "vel", "rho", "acc"):
             assert_bits(got[f], want[f], f"drop G={G} {f}")
+
+
+@pytest.mark.parametrize("name", ["fast_cloud", "light_zero_mixed"])
+def test_cfl_limited_adaptive_timestep_across_slabs(pkg, po, name):
+    """The CFL-limited cases of tests/golden/scalars.json on 2 slabs: max |v|^2 is reduced across the slabs and the
+    acceleration of particle 0 is handed over by the rank that advanced it, so both branches of the rule (dt_cfl,
+    dt_force) give the reference's dt, times and final state bit for bit."""
+    import hashlib, json
+    from helpers import GOLDEN, cfl_case_inputs
+    from sph_b200 import scenes, slab
+    case = json.loads((GOLDEN / "scalars.json").read_text())["cfl_cases"][name]
+    prm, pos, vel, mass, n = cfl_case_inputs(po, scenes, name, case)
+    nsr = float(prm["neighbor_search_radius"])
+    cuts = slab.plan_cuts(slab.axis_cells(pos, 2, nsr), 2, 2)
+    ranks = []
+    for d in range(2):
+        store = slab.GpuStore(pkg, n, 0, prm, strict=True)
+        ranks.append(slab.SlabRank(store, d, cuts, 2, 2, n, [-0.2, 0.0, -0.4], [0.2, 0.6, 0.4], 3 * n))
+        ranks[-1].load_initial(pos, vel, mass, nsr)
+    for k, want_dt in enumerate(case["dts"]):
+        assert np.float32(slab.step_local(ranks, 0.0)) == np.float32(want_dt), f"{name} step {k} ({case['branch'][k]} branch)"
+    merged = slab.gather_by_id([r.store.download() for r in ranks], n)
+    for f in ("pos", "vel", "rho"):
+        assert hashlib.sha256(np.ascontiguousarray(merged[f]).tobytes()).hexdigest() == case[f"final_{f}_sha256"], f"{name} final {f}"
+    for r in ranks:
+        assert np.float32(r.store.ctx.get_time()[0]) == np.float32(case["times"][-1])
+        r.store.close()
