@@ -148,7 +148,9 @@ int sphb_upload_strided(sphb_ctx* ctx, size_t n, const void* base, size_t stride
                         size_t off_pos, size_t off_vel, size_t off_mass);
 /* replaces the getters SPHEngine::get_positions/get_velocities/get_densities/get_pressures
  * (sph_engine.h:133-136) and the engine's accelerations_ buffer (sph_engine.h:64).  Each output is
- * in insertion order, n entries (n*3 for vectors); any pointer may be NULL. */
+ * in insertion order, n entries (n*3 for vectors); any pointer may be NULL.  Density, pressure and
+ * acceleration belong to the last step: between an upload and the next step they read as zeros (the
+ * reference would show its previous per-id buffers there). */
 int sphb_download(sphb_ctx* ctx, float* pos3, float* vel3, float* rho, float* pressure, float* acc3);
 /* Write position/velocity/density/pressure back into an array-of-structs (byte offsets; pass
  * (size_t)-1 for a field to skip). */

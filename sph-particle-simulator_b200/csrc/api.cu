@@ -586,6 +586,15 @@ int sphb_download(sphb_ctx* c, float* pos3, float* vel3, float* rho, float* pres
     float* d_acc = d_vel + 3 * n;
     float* d_rho = d_acc + 3 * n;
     float* d_P = d_rho + n;
+    // density, pressure and acceleration belong to the particles of the last STEP: after an upload they still sit in the
+    // previous set's slot order, so until the next step they read as zeros instead of landing on the wrong particles
+    if (!c->stepped_since_upload) {
+        if (rho) memset(rho, 0, n * sizeof(float));
+        if (pressure) memset(pressure, 0, n * sizeof(float));
+        if (acc3) memset(acc3, 0, n * 3 * sizeof(float));
+        rho = nullptr; pressure = nullptr; acc3 = nullptr;
+        if (!pos3 && !vel3) return SPHB_OK;
+    }
     c->stats.kernel_launches += launch_unpermute(n, c->posm[c->cur], c->velid[c->cur], c->rho_p, c->acc, nullptr, nullptr,
                                                  pos3 ? d_pos : nullptr, vel3 ? d_vel : nullptr, rho ? d_rho : nullptr,
                                                  pressure ? d_P : nullptr, acc3 ? d_acc : nullptr, nullptr, nullptr, nullptr,
@@ -871,7 +880,7 @@ int sphb_diagnostics(sphb_ctx* c, double* sum_density, double* kinetic, float* m
     c->stats.kernel_launches += launch_diagnostics(c->n, c->posm[c->cur], c->velid[c->cur], c->rho_p, c->sc, c->stream);
     int rc = read_scalars(c);
     if (rc) return rc;
-    if (sum_density) *sum_density = c->h_sc->sum_rho;
+    if (sum_density) *sum_density = c->stepped_since_upload ? c->h_sc->sum_rho : 0.0;   // no densities of this particle set yet
     if (kinetic) *kinetic = c->h_sc->kinetic;
     if (max_speed) {
         float v2;

@@ -38,17 +38,19 @@ constexpr int kThreads = SPHB_PAIR_THREADS;
 
 // Calls body(begin, end) for every contiguous slot run of the neighbourhood of cell (cx, cy, cz),
 // in the reference's visiting order.
+// `edge`: bit 2a / 2a + 1 = the particle sits within a few ulps of the lower / upper face of its cell on axis a: the
+// walk then reaches one cell further on that side (see face_bits).
 template <typename Body>
 __device__ __forceinline__ void walk_runs(const GridDesc& g, const uint32_t* __restrict__ cell_start, int R, int cx, int cy,
-                                          int cz, Body&& body) {
-    const int za = max(cz - R, g.lo[2]), zb = min(cz + R, g.hi[2]);
+                                          int cz, unsigned edge, Body&& body) {
+    const int za = max(cz - R - (int)(edge >> 4 & 1u), g.lo[2]), zb = min(cz + R + (int)(edge >> 5 & 1u), g.hi[2]);
     if (za > zb) return;
     const bool split = (za < 0) && (zb >= 0);
-    for (int dx = -R; dx <= R; ++dx) {
+    for (int dx = -R - (int)(edge & 1u); dx <= R + (int)(edge >> 1 & 1u); ++dx) {
         const int x = cx + dx;
         if (x < g.lo[0] || x > g.hi[0]) continue;
         const uint32_t bx = (uint32_t)grid_rank(g, 0, x) * (uint32_t)g.ext[1];
-        for (int dy = -R; dy <= R; ++dy) {
+        for (int dy = -R - (int)(edge >> 2 & 1u); dy <= R + (int)(edge >> 3 & 1u); ++dy) {
             const int y = cy + dy;
             if (y < g.lo[1] || y > g.hi[1]) continue;
             const uint32_t base = (bx + (uint32_t)grid_rank(g, 1, y)) * (uint32_t)g.ext[2];
@@ -60,6 +62,23 @@ __device__ __forceinline__ void walk_runs(const GridDesc& g, const uint32_t* __r
             }
         }
     }
+}
+
+// With cells of exactly neighbor_search_radius, two particles that distance apart can sit TWO cells apart when both lie
+// within rounding of a cell face (fp32: nsr = 0.03, a = 0.029999996 in cell 0, b = 0.059999995 in cell 2, d2 <= r2);
+// the reference finds such a pair because it queries two rings (spatial_hash.cpp:35).  Instead of always walking 125
+// cells, a particle within 2^-20 (relative, >= 8 ulps of the product) of a face reaches one cell further on that side
+// — the only place such a partner can be.  (Refined grids guard the same tie with 0.1 % larger cells, make_grid.)
+__device__ __forceinline__ unsigned face_bits(const float4& p, float inv_cell) {
+    unsigned bits = 0;
+    const float c[3] = {p.x, p.y, p.z};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float t = __fmul_rn(c[a], inv_cell), f = t - floorf(t), eps = fmaxf(fabsf(t), 1.0f) * 9.5367431640625e-07f;
+        if (f <= eps) bits |= 1u << (2 * a);
+        if (f >= 1.0f - eps) bits |= 2u << (2 * a);
+    }
+    return bits;
 }
 
 // ---- one thread per particle, private tested walk (strict mode; fast-mode variant 0) -------------------------------------------------
@@ -79,7 +98,7 @@ __global__ void __launch_bounds__(kThreads, SPHB_DENSITY_MINBLOCKS) k_density_si
         float rho = STRICT ? __fmul_rn(pi.w, a.k.w0) : 0.0f;
         const float r2 = a.k.r2;
         const float inv_h = a.k.inv_h, sig6 = a.k.sigma * (1.0f / 6.0f);
-        walk_runs(a.grid, a.cell_start, a.walk_radius, cx, cy, cz, [&](uint32_t b, uint32_t e) {
+        walk_runs(a.grid, a.cell_start, a.walk_radius, cx, cy, cz, face_bits(pi, a.grid.inv_cell), [&](uint32_t b, uint32_t e) {
             SPHB_UNROLL(SPHB_DENSITY_UNROLL)
             for (uint32_t j = b; j < e; ++j) {
                 const float4 pj = __ldg(&a.posm[j]);
@@ -130,7 +149,7 @@ __global__ void __launch_bounds__(kThreads, SPHB_FORCE_MINBLOCKS) k_force_simple
     ForceAccum f = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
     const float r2 = a.k.r2;
     const float4* __restrict__ ja = STRICT ? a.posm : a.fa;
-    walk_runs(a.grid, a.cell_start, a.walk_radius, cx, cy, cz, [&](uint32_t b, uint32_t e) {
+    walk_runs(a.grid, a.cell_start, a.walk_radius, cx, cy, cz, face_bits(pi, a.grid.inv_cell), [&](uint32_t b, uint32_t e) {
         SPHB_UNROLL(SPHB_FORCE_UNROLL)
         for (uint32_t j = b; j < e; ++j) {
             const float4 pj = __ldg(&ja[j]);

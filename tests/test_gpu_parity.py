@@ -512,3 +512,60 @@ def test_staged_equals_global_1M(pkg):
     from sph_b200 import scenes
     pos, mass, prm, dt = scenes.make_scene("dam_break_1M")
     _staged_vs_global(pkg, pos, None, mass, prm, [dt] * 3, 4, "dam_break_1M")
+
+
+def test_download_between_upload_and_step(pkg):
+    """Density, pressure and acceleration belong to the last step: after a new upload (another particle set, another
+    order) they must not be un-permuted with the new ids.  Until the next step they read as zeros."""
+    g = load_golden("cloud600")
+    prm = params_from(g["params"])
+    ctx = make_ctx(pkg, 600, prm, strict=True)
+    ctx.upload(g["pos"], g["vel"], g["mass"])
+    ctx.step(float(g["dts"][0]))
+    assert np.abs(ctx.download()["rho"]).min() > 0
+    ctx.upload(g["pos"][::-1].copy(), None, g["mass"][::-1].copy())    # same particles, reversed ids, no step yet
+    s = ctx.download()
+    assert_bits(s["pos"], g["pos"][::-1].copy(), "positions of the new upload")
+    assert not s["rho"].any() and not s["P"].any() and not s["acc"].any()
+    assert ctx.diagnostics()[0] == 0.0
+    ctx.step(float(g["dts"][0]))
+    assert rel_err(ctx.download()["rho"], g["s0_rho"][::-1]) <= 1e-6    # (summation order follows the ids: last bits may differ)
+    ctx.close()
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+@pytest.mark.parametrize("strict", [True, False])
+def test_two_cells_apart_tie_at_cell_faces(pkg, po, axis, strict):
+    """fp32 edge of the 27-cell walk with cell = neighbor_search_radius: a = 0.029999996 lies in cell 0, b = 0.059999995
+    in cell 2, yet (b - a)^2 <= fl(nsr nsr) — the reference's two-ring query (spatial_hash.cpp:35) finds the pair.  The
+    same on the negative side, with bystanders around so that the cells are not trivially empty."""
+    prm = dict(pkg.DEFAULT_PARAMS)
+    prm.update(smoothing_length=0.015, neighbor_search_radius=0.03, gas_constant=1e-3, viscosity=1e-6, particle_mass=1e-4,
+               xmin=-1.0, xmax=1.0, ymin=-1.0, ymax=1.0, zmin=-1.0, zmax=1.0)
+    a, b = np.float32(0.029999996), np.float32(0.059999995)
+    base = np.zeros((6, 3), np.float32)
+    base[:, (axis + 1) % 3] = 0.0151; base[:, (axis + 2) % 3] = 0.0449
+    base[0, axis], base[1, axis] = a, b
+    base[2, axis], base[3, axis] = -a, -b
+    base[4, axis], base[5, axis] = 0.0451, 0.0149
+    rng = np.random.default_rng(5)
+    pos = np.concatenate([base, rng.uniform(-0.12, 0.12, size=(400, 3)).astype(np.float32)])
+    mass = np.full(len(pos), prm["particle_mass"], np.float32)
+    ora = po.Engine("port", len(pos)); ora.initialize(prm); ora.add_particles(pos, None, mass)
+    ora.step(1e-4)
+    cnt = ora.neighbor_counts()
+    d = pos[1, axis] - pos[0, axis]
+    assert np.float32(d) * np.float32(d) <= np.float32(0.03) * np.float32(0.03), "the constructed pair must be a neighbour pair"
+    inv = np.float32(1.0) / np.float32(0.03)
+    assert np.floor(a * inv) == 0.0 and np.floor(b * inv) == 2.0, "... whose cells are two apart"
+    for refine in ((1,) if strict else (1, 2, 4)):
+        ctx = make_ctx(pkg, len(pos), prm, strict=strict, OPT_GRID_REFINE=refine)
+        ctx.upload(pos, None, mass)
+        ctx.step(1e-4)
+        assert_bits(ctx.debug_dump()["nbr_count"], cnt, f"axis {axis} refine {refine}: neighbour counts with the face tie")
+        if strict:
+            got, want = ctx.download(), ora.state()
+            for f in ("rho", "acc", "pos"):
+                assert_bits(got[f], want[f], f"face tie {f}")
+        ctx.close()
+    ora.close()
