@@ -2,12 +2,14 @@
 """Headless counterpart of the reference's examples/dam_break.cpp (lines 40-61 parameters, 114-175 main loop,
 153-166 CSV row) on the B200 engine, through the drop-in Python module `sph`.
 
-    python examples/dam_break_headless.py [num_particles=10000] [duration_s=0.05] [csv_path]
+    python examples/dam_break_headless.py [num_particles=10000] [duration_s=0.05] [csv_path] [--strict]
 
 Like the reference program, `num_particles` only sets the capacity (2 x num_particles); the scene itself is the
 hard-wired dam break of SPHEngine::initialize_dam_break, truncated at capacity (SURVEY.md §0.5).  The CSV has the
 reference's columns: time,particles,mass_error,energy,total_energy,avg_density,max_velocity — avg_density is the
-mean over the capacity-length density buffer, as in dam_break.cpp:146-151 (quirk Q13).
+mean over the capacity-length density buffer, as in dam_break.cpp:146-151 (quirk Q13).  The report values come from
+ONE device reduction per report (Simulator.get_report_diagnostics); the reference program pulls the full velocity and
+density arrays for them.  --strict selects the bit-exact reference arithmetic (default: the fast path).
 """
 import sys
 import time
@@ -20,11 +22,14 @@ import sph  # noqa: E402
 
 
 def main():
-    num_particles = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
-    duration = float(sys.argv[2]) if len(sys.argv) > 2 else 0.05
-    csv_path = sys.argv[3] if len(sys.argv) > 3 else "dam_break_data.csv"
+    argv = [a for a in sys.argv[1:] if not a.startswith("--")]
+    num_particles = int(argv[0]) if len(argv) > 0 else 10000
+    duration = float(argv[1]) if len(argv) > 1 else 0.05
+    csv_path = argv[2] if len(argv) > 2 else "dam_break_data.csv"
 
     engine = sph.Simulator(max_particles=num_particles * 2)
+    if "--strict" in sys.argv:
+        engine.set_math_mode(0)
     params = sph.SPHParameters()
     params.rest_density = 1000.0
     params.gas_constant = 2000.0
@@ -47,12 +52,9 @@ def main():
     for step in range(max_steps):
         engine.step(dt)
         if step % 10 == 9 or step == max_steps - 1:
-            mass_error, energy_error = engine.compute_conservation_errors()
-            ke = engine.get_total_energy()
-            vel = engine.get_velocities()
-            rho = engine.get_densities()
-            vmax = float(np.sqrt((vel.astype(np.float64) ** 2).sum(1)).max()) if len(vel) else 0.0
-            rows.append(f"{engine.get_current_time():.6f},{n},{mass_error:.6g},{energy_error:.6g},{ke:.6g},{float(rho.mean()):.6g},{vmax:.6g}")
+            d = engine.get_report_diagnostics()    # one device reduction; energy_error is a constant 0 in the reference too
+            rows.append(f"{engine.get_current_time():.6f},{n},{d['mass_error']:.6g},0,{d['kinetic_energy']:.6g},"
+                        f"{d['average_density']:.6g},{d['max_velocity']:.6g}")
     wall = time.perf_counter() - t0
     Path(csv_path).write_text("\n".join(rows) + "\n")
     st = engine.get_performance_stats()

@@ -434,6 +434,23 @@ float SPHEngine::get_total_energy() const {
     return static_cast<float>(ke);
 }
 
+SPHEngine::ReportDiagnostics SPHEngine::get_report_diagnostics() const {
+    ReportDiagnostics d{0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    if (!initialized_ || particles_.size() == 0) return d;
+    if (host_changed_) push_to_device();
+    double sum_rho = 0.0, ke = 0.0;
+    float vmax = 0.0f;
+    SPHB_CHECK(sphb_diagnostics(ctx_, &sum_rho, &ke, &vmax));
+    const float h = params_.smoothing_length;
+    d.total_mass = static_cast<float>(sum_rho) * (h * h * h);
+    const float initial = particles_.size() * params_.particle_mass;
+    d.mass_error = std::abs(d.total_mass - initial) / initial;
+    d.kinetic_energy = static_cast<float>(ke);
+    d.average_density = particles_.capacity() ? static_cast<float>(sum_rho / static_cast<double>(particles_.capacity())) : 0.0f;
+    d.max_velocity = vmax;
+    return d;
+}
+
 // reference sph_engine.cpp:178-185 (energy error is a constant 0 there too)
 void SPHEngine::compute_conservation_errors(float& mass_error, float& energy_error) const {
     const float total = get_total_mass();

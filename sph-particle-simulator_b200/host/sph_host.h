@@ -179,6 +179,17 @@ public:
     float compute_cfl_timestep() const;
     // false (default): step() returns when the GPU finished it, like the reference; true: enqueue and return
     void set_async(bool on);
+    // What the reference's drivers derive from full-array getters every report (examples/dam_break.cpp:132-166:
+    // compute_conservation_errors, get_total_energy, the mean of get_densities() over the CAPACITY-long buffer (quirk
+    // Q13), the maximum of |get_velocities()|), from ONE device reduction — no array leaves the GPU.
+    struct ReportDiagnostics {
+        float mass_error;        // |sum(rho) h^3 - N m| / (N m)      (sph_engine.cpp:178-190)
+        float kinetic_energy;    // sum 1/2 m |v|^2                   (sph_engine.cpp:192-200)
+        float average_density;   // sum(rho) / capacity               (dam_break.cpp:146-151)
+        float max_velocity;      // max |v|                           (dam_break.cpp:139-144)
+        float total_mass;        // sum(rho) h^3
+    };
+    ReportDiagnostics get_report_diagnostics() const;
     sphb_ctx* native_handle() const { return ctx_; }
 
 private:

@@ -145,7 +145,19 @@ PYBIND11_MODULE(sph, m) {
         .def("set_math_mode", &SPHEngine::set_math_mode, py::arg("mode"))
         .def("set_async", &SPHEngine::set_async, py::arg("on"))
         .def("get_accelerations", [](const SPHEngine& e) { return vec3_array(e.get_accelerations()); })
-        .def("compute_cfl_timestep", &SPHEngine::compute_cfl_timestep);
+        .def("compute_cfl_timestep", &SPHEngine::compute_cfl_timestep)
+        .def("get_report_diagnostics",
+             [](const SPHEngine& e) {
+                 const SPHEngine::ReportDiagnostics d = e.get_report_diagnostics();
+                 py::dict out;
+                 out["mass_error"] = d.mass_error;
+                 out["kinetic_energy"] = d.kinetic_energy;
+                 out["average_density"] = d.average_density;
+                 out["max_velocity"] = d.max_velocity;
+                 out["total_mass"] = d.total_mass;
+                 return out;
+             },
+             "mass error, kinetic energy, mean density over the capacity-long buffer and max |v| from one device reduction");
 
     m.def("create_fluid_block",
           [](const py::array_t<float>& center, const py::array_t<float>& size, float spacing, float mass) {

@@ -200,3 +200,70 @@ def test_headless_dam_break_example(tmp_path):
     rows = (tmp_path / "d.csv").read_text().splitlines()
     assert rows[0] == "time,particles,mass_error,energy,total_energy,avg_density,max_velocity" and len(rows) >= 2
     assert rows[1].split(",")[1] == "20000"
+
+
+@pytest.mark.gpu
+def test_headless_example_rows_match_the_reference(tmp_path, po):
+    """The first five CSV rows of the example (one device reduction per report) against what the reference program
+    computes from full arrays (examples/dam_break.cpp:132-166): compute_conservation_errors, get_total_energy, the mean
+    of the CAPACITY-long density buffer (quirk Q13) and max |v| — on the reference engine itself (strict build or the C
+    port), same parameters, same 50 steps.  The scene explodes (reference defaults): rows agree while finite and turn
+    non-finite together."""
+    import subprocess
+    out = subprocess.run([sys.executable, str(ROOT / "examples" / "dam_break_headless.py"), "10000", "0.05", str(tmp_path / "d.csv"), "--strict"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+    rows = [r.split(",") for r in (tmp_path / "d.csv").read_text().splitlines()[1:]]
+    assert len(rows) == 5
+    prm = dict(po.DEFAULT_PARAMS) if hasattr(po, "DEFAULT_PARAMS") else None
+    e = po.Engine("strict" if po.available("strict") else "port", 20000)
+    p = e.get_parameters() if prm is None else prm
+    p.update(rest_density=1000.0, gas_constant=2000.0, viscosity=0.001, smoothing_length=0.025, particle_mass=0.001, timestep=0.001,
+             gravity=-9.81, damping=0.995)
+    e.initialize(p)
+    e.set_boundaries(-1.0, 1.0, -0.5, 1.5, -1.0, 1.0)
+    e.initialize_dam_break()
+    n = e.size
+    k = 0
+    max_steps = int(0.05 / float(np.float32(0.001)))   # 49: duration / (float)timestep truncated, as in the example and dam_break.cpp
+    for step in range(max_steps):
+        e.step(0.001)
+        if step % 10 == 9 or step == max_steps - 1:
+            st = e.state()
+            want = [e.time, float(n), e.conservation_errors()[0], 0.0, e.total_energy(), float(e.densities_raw().astype(np.float64).mean()),
+                    float(np.sqrt((st["vel"] * st["vel"]).sum(1, dtype=np.float32)).max())]   # glm::length in fp32, like dam_break.cpp:141
+            got = [float(x) for x in rows[k]]
+            for name, g_, w_ in zip("time particles mass_error energy total_energy avg_density max_velocity".split(), got, want):
+                if np.isfinite(w_) and abs(w_) < 1e30:
+                    assert abs(g_ - w_) <= 2e-3 * abs(w_) + 1e-12, f"row {k} {name}: {g_} vs reference {w_}"
+                else:       # the exploded phase: fp32 sums overflow in the reference; huge or non-finite on both sides
+                    assert not np.isfinite(g_) or abs(g_) >= 1e30, f"row {k} {name}: {g_} vs reference {w_}"
+            k += 1
+    e.close()
+
+
+@pytest.mark.gpu
+def test_reference_benchmark_dt_sequence_through_the_drop_in(sph):
+    """benchmarks/performance_test.cpp:85-125 driven through the drop-in class exactly as the reference program does
+    (SPHEngine(2 x 5000), its parameter block incl. h = (m / rho0)^(1/3), initialize, initialize_dam_break, step() with
+    dt = 0): the adaptive dt sequence — params.timestep, then the CFL branch of the exploding defaults — equals the
+    unmodified reference's (tests/golden/scalars.json cfl_cases.perf_test), time by time, bit for bit."""
+    import hashlib, json
+    case = json.loads((ROOT / "tests" / "golden" / "scalars.json").read_text())["cfl_cases"]["perf_test"]
+    sim = sph.Simulator(max_particles=case["capacity"])
+    sim.set_math_mode(0)
+    p = sph.SPHParameters()
+    p.rest_density = 1000.0; p.gas_constant = 2000.0; p.viscosity = 0.001; p.particle_mass = 0.001; p.timestep = 0.001; p.gravity = -9.81
+    p.smoothing_length = float(np.float32(np.float32(np.float32(1.0) / np.float32(1000.0) * np.float32(0.001)) ** np.float32(1.0 / 3.0)))
+    sim.initialize(p)
+    sim.initialize_dam_break()
+    assert sim.get_particles().size() == case["n"]
+    for want_dt, want_t in zip(case["dts"], case["times"]):
+        assert np.float32(sim.compute_cfl_timestep()) == np.float32(want_dt)
+        sim.step()
+        assert np.float32(sim.get_current_time()) == np.float32(want_t)
+    assert hashlib.sha256(np.ascontiguousarray(sim.get_positions()).tobytes()).hexdigest() == case["final_pos_sha256"]
+    d = sim.get_report_diagnostics()
+    vel = sim.get_velocities().astype(np.float64)
+    assert abs(d["max_velocity"] - np.sqrt((vel ** 2).sum(1)).max()) <= 1e-6 * d["max_velocity"]
+    assert abs(d["average_density"] - sim.get_densities().astype(np.float64).mean()) <= 1e-5 * abs(d["average_density"])
