@@ -183,6 +183,15 @@ int sphb_reset_stats(sphb_ctx* ctx);
  * kinetic = Σ 0.5 m_i |v_i|^2, max_speed = max |v_i|.  Any pointer may be NULL. */
 int sphb_diagnostics(sphb_ctx* ctx, double* sum_density, double* kinetic, float* max_speed);
 
+/* replaces the per-frame array-of-structs walk of Renderer::update_particle_data (reference src/renderer.cpp:279-312):
+ * writes the renderer's instance records — position (3), velocity (3), colour (3) floats per particle, insertion
+ * order, n * 9 floats — with one kernel.  dst_on_device != 0: dst is a DEVICE pointer (e.g. a CUDA-mapped vertex
+ * buffer) and nothing crosses the bus; otherwise dst is host memory.  Colours: sphb_set_colors uploads per-particle RGB
+ * once (sph::Particle::color is never changed by the physics); without it every record carries default_rgb (NULL:
+ * the reference's Particle default 0, 0.5, 1). */
+int sphb_set_colors(sphb_ctx* ctx, size_t n, const float* rgb3);
+int sphb_export_instances(sphb_ctx* ctx, float* dst, int dst_on_device, const float* default_rgb);
+
 /* Parity hooks (need SPHB_OPT_DEBUG_CAPTURE = 1 before the step), all for the LAST step, i.e. for
  * the positions that step's neighbour build saw:
  *   keys[i]      63-bit cell key of particle i — SpatialHash::hash_position (spatial_hash.h:20-36)

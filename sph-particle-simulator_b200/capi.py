@@ -44,7 +44,7 @@ ABI_SYMBOLS = (
     "sphb_set_stream", "sphb_synchronize", "sphb_set_params", "sphb_get_params", "sphb_upload",
     "sphb_upload_strided", "sphb_download", "sphb_download_strided", "sphb_size", "sphb_step", "sphb_run_steps",
     "sphb_get_time", "sphb_set_time", "sphb_cfl_timestep", "sphb_get_stats", "sphb_reset_stats",
-    "sphb_diagnostics", "sphb_debug_dump", "sphb_debug_stencil",
+    "sphb_diagnostics", "sphb_set_colors", "sphb_export_instances", "sphb_debug_dump", "sphb_debug_stencil",
     "sphb_set_slab", "sphb_upload_ids", "sphb_slab_append", "sphb_slab_exchange_pack", "sphb_slab_exchange_count",
     "sphb_slab_exchange_split", "sphb_get_cfl_state", "sphb_set_cfl_state",
     "sphb_slab_download",
@@ -115,6 +115,8 @@ def load_library() -> C.CDLL:
     L.sphb_get_stats.argtypes = [vp, C.POINTER(SphbStats)]
     L.sphb_reset_stats.argtypes = [vp]
     L.sphb_diagnostics.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), fp]
+    L.sphb_set_colors.argtypes = [vp, sz, vp]
+    L.sphb_export_instances.argtypes = [vp, vp, C.c_int, vp]
     L.sphb_debug_dump.argtypes = [vp, vp, vp, vp]
     L.sphb_debug_stencil.argtypes = [C.c_int, vp, C.POINTER(C.c_float)]
     L.sphb_set_slab.argtypes = [vp, C.POINTER(SphbSlab)]
@@ -277,6 +279,20 @@ class Context:
         a, b, c = C.c_double(), C.c_double(), C.c_float()
         self._ck(self.L.sphb_diagnostics(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
+
+    def set_colors(self, rgb):
+        rgb = np.ascontiguousarray(rgb, np.float32).reshape(-1, 3)
+        self._ck(self.L.sphb_set_colors(self.h, rgb.shape[0], _ptr(rgb)))
+
+    def export_instances(self, default_rgb=None, device_ptr: int | None = None):
+        """The renderer's instance records (n, 9): position, velocity, colour.  device_ptr: write into device memory instead."""
+        d = None if default_rgb is None else np.ascontiguousarray(default_rgb, np.float32)
+        if device_ptr is not None:
+            self._ck(self.L.sphb_export_instances(self.h, C.c_void_p(device_ptr), 1, _ptr(d)))
+            return None
+        out = np.zeros((self.size, 9), np.float32)
+        self._ck(self.L.sphb_export_instances(self.h, _ptr(out), 0, _ptr(d)))
+        return out
 
     def debug_dump(self, keys=True, perm=True, counts=True) -> dict:
         n = self.size

@@ -53,6 +53,8 @@ struct sphb_ctx {
     size_t mask_bytes = 0;
     size_t mask_stride = 0;
     ForceRec* fab = nullptr;     // variant 2: 32-byte force-pass records
+    float* colors = nullptr;     // optional per-id RGB of the renderer's instance records (sphb_set_colors)
+    size_t n_colors = 0;
     uint32_t* nbr_count = nullptr;
     uint64_t* refkeys[2] = {nullptr, nullptr};
     uint64_t* dbg_keys[2] = {nullptr, nullptr};   // reference-order composite keys (debug capture with a refined grid)
@@ -299,7 +301,7 @@ void free_all(sphb_ctx* c) {
         cudaFree(c->posm[i]); cudaFree(c->velid[i]); cudaFree(c->refkeys[i]); cudaFree(c->dbg_keys[i]); cudaFree(c->dbg_vals[i]);
     }
     cudaFree(c->cell_ticket); cudaFree(c->slot_src);
-    cudaFree(c->masks); cudaFree(c->fab);
+    cudaFree(c->masks); cudaFree(c->fab); cudaFree(c->colors);
     cudaFree(c->rho_p); cudaFree(c->fa); cudaFree(c->fb); cudaFree(c->acc); cudaFree(c->nbr_count);
     cudaFree(c->cell_start);
     cudaFree(c->sc); cudaFree(c->d_stage); cudaFree(c->d_box); cudaFree(c->d_counts); cudaFree(c->sort_scratch);
@@ -870,6 +872,43 @@ int sphb_reset_stats(sphb_ctx* c) {
     CU(c, cudaMemsetAsync(&c->sc->max_neighbors, 0, 2 * sizeof(unsigned), c->stream));   // max_neighbors, error_flags
     drain_events(c);
     c->stats = sphb_stats{};
+    return SPHB_OK;
+}
+
+int sphb_set_colors(sphb_ctx* c, size_t n, const float* rgb3) {
+    if (!c) return SPHB_E_INVALID;
+    if (!rgb3 && n) return fail(c, SPHB_E_INVALID, "rgb3 is NULL");
+    if (n > c->capacity) return fail(c, SPHB_E_CAPACITY, "%zu colours exceed the capacity %zu", n, c->capacity);
+    CU(c, cudaSetDevice(c->device));
+    if (!c->colors && c->capacity) CU(c, cudaMalloc(&c->colors, c->capacity * 3 * sizeof(float)));
+    if (n) CU(c, cudaMemcpyAsync(c->colors, rgb3, n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));   // the caller's array may go away
+    c->n_colors = n;
+    return SPHB_OK;
+}
+
+int sphb_export_instances(sphb_ctx* c, float* dst, int dst_on_device, const float* default_rgb) {
+    if (!c) return SPHB_E_INVALID;
+    if (c->slab_on) return fail(c, SPHB_E_INVALID, "slab mode: ids are global, use sphb_slab_download");
+    const size_t n = c->n;
+    if (n == 0) return SPHB_OK;
+    if (!dst) return fail(c, SPHB_E_INVALID, "dst is NULL");
+    CU(c, cudaSetDevice(c->device));
+    const float reference_default[3] = {0.0f, 0.5f, 1.0f};   // sph::Particle::color, reference particle.h:35
+    const float* rgb = default_rgb ? default_rgb : reference_default;
+    float* d_out = dst;
+    if (!dst_on_device) {
+        int rc = ensure_stage(c, n * 9 * sizeof(float));
+        if (rc) return rc;
+        d_out = reinterpret_cast<float*>(c->d_stage);
+    }
+    c->stats.kernel_launches += launch_export_instances(n, c->posm[c->cur], c->velid[c->cur], c->n_colors >= n ? c->colors : nullptr,
+                                                        rgb, d_out, c->stream);
+    CU(c, cudaGetLastError());
+    if (!dst_on_device) {
+        CU(c, cudaMemcpyAsync(dst, d_out, n * 9 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+    }
     return SPHB_OK;
 }
 

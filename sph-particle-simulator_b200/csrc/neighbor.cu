@@ -177,6 +177,23 @@ __global__ void __launch_bounds__(kThreads) k_unpermute(size_t n, const float4* 
     if (counts) counts[id] = nbr_count[s];
 }
 
+// The renderer's per-instance record (reference Renderer::update_particle_data, src/renderer.cpp:279-312): position (3),
+// velocity (3), colour (3) per particle in insertion order.  colours: per-id RGB uploaded once (Particle::color is never
+// touched by the physics, quirk Q8) or NULL for one default colour.
+__global__ void __launch_bounds__(kThreads) k_export_instances(size_t n, const float4* __restrict__ posm,
+                                                               const float4* __restrict__ velid, const float* __restrict__ colors,
+                                                               float3 default_color, float* __restrict__ out9) {
+    const size_t s = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    if (s >= n) return;
+    const float4 v = velid[s], p = posm[s];
+    const size_t id = __float_as_uint(v.w) & 0x7FFFFFFFu;
+    float* o = out9 + 9 * id;
+    o[0] = p.x; o[1] = p.y; o[2] = p.z;
+    o[3] = v.x; o[4] = v.y; o[5] = v.z;
+    if (colors) { o[6] = colors[3 * id]; o[7] = colors[3 * id + 1]; o[8] = colors[3 * id + 2]; }
+    else { o[6] = default_color.x; o[7] = default_color.y; o[8] = default_color.z; }
+}
+
 __global__ void __launch_bounds__(kThreads) k_diagnostics(size_t n, const float4* __restrict__ posm,
                                                           const float4* __restrict__ velid, const float2* __restrict__ rho_p,
                                                           DeviceScalars* sc) {
@@ -314,6 +331,14 @@ int launch_unpermute(size_t n, const float4* posm, const float4* velid, const fl
     if (n == 0) return 0;
     k_unpermute<<<blocks_for(n, kThreads), kThreads, 0, st>>>(n, posm, velid, rho_p, acc, refkeys, nbr_count, pos3, vel3,
                                                                rho, P, acc3, keys, perm, counts);
+    return 1;
+}
+
+int launch_export_instances(size_t n, const float4* posm, const float4* velid, const float* colors, const float default_color[3],
+                            float* out9, cudaStream_t st) {
+    if (n == 0) return 0;
+    k_export_instances<<<blocks_for(n, kThreads), kThreads, 0, st>>>(n, posm, velid, colors,
+                                                                     make_float3(default_color[0], default_color[1], default_color[2]), out9);
     return 1;
 }
 

@@ -175,6 +175,8 @@ int launch_max_speed(size_t n, const float4* velid, DeviceScalars* sc, cudaStrea
 int launch_unpermute(size_t n, const float4* posm, const float4* velid, const float2* rho_p, const float4* acc,
                      const uint64_t* refkeys, const uint32_t* nbr_count, float* pos3, float* vel3, float* rho, float* P,
                      float* acc3, uint64_t* keys, uint32_t* perm, uint32_t* counts, cudaStream_t st);
+int launch_export_instances(size_t n, const float4* posm, const float4* velid, const float* colors, const float default_color[3],
+                            float* out9, cudaStream_t st);
 int launch_diagnostics(size_t n, const float4* posm, const float4* velid, const float2* rho_p, DeviceScalars* sc,
                        cudaStream_t st);
 

@@ -339,6 +339,7 @@ void SPHEngine::push_to_device() const {
                                    offsetof(Particle, velocity), offsetof(Particle, mass)));
     host_changed_ = false;
     device_ahead_ = false;
+    colors_on_device_ = false;   // another particle set: the renderer colours follow with the next export
 }
 
 void SPHEngine::pull_from_device() const {
@@ -432,6 +433,25 @@ float SPHEngine::get_total_energy() const {
     double ke = 0.0;
     SPHB_CHECK(sphb_diagnostics(ctx_, nullptr, &ke, nullptr));
     return static_cast<float>(ke);
+}
+
+void SPHEngine::export_instance_data(float* dst, bool dst_on_device) const {
+    if (!initialized_ || particles_.size() == 0) return;
+    if (host_changed_) push_to_device();
+    if (!colors_on_device_) {   // Particle::color is host-side state the physics never touches: uploaded once per particle set
+        std::vector<float> rgb(particles_.size() * 3);
+        size_t k = 0;
+        for (const Particle& p : particles_) { rgb[k++] = p.color.r; rgb[k++] = p.color.g; rgb[k++] = p.color.b; }
+        SPHB_CHECK(sphb_set_colors(ctx_, particles_.size(), rgb.data()));
+        colors_on_device_ = true;
+    }
+    SPHB_CHECK(sphb_export_instances(ctx_, dst, dst_on_device ? 1 : 0, nullptr));
+}
+
+std::vector<float> SPHEngine::get_instance_data() const {
+    std::vector<float> out(particles_.size() * 9);
+    export_instance_data(out.data(), false);
+    return out;
 }
 
 SPHEngine::ReportDiagnostics SPHEngine::get_report_diagnostics() const {

@@ -190,6 +190,11 @@ public:
         float total_mass;        // sum(rho) h^3
     };
     ReportDiagnostics get_report_diagnostics() const;
+    // The renderer's instance buffer (Renderer::update_particle_data, src/renderer.cpp:279-312: position, velocity,
+    // Particle::color — 9 floats per particle, insertion order) written by one kernel.  dst_on_device: dst is device
+    // memory (a CUDA-mapped vertex buffer); otherwise host memory of size() * 9 floats.
+    void export_instance_data(float* dst, bool dst_on_device = false) const;
+    std::vector<float> get_instance_data() const;
     sphb_ctx* native_handle() const { return ctx_; }
 
 private:
@@ -206,6 +211,7 @@ private:
     bool initialized_ = false;
     mutable bool host_changed_ = true;   // device does not hold the host particles yet
     mutable bool device_ahead_ = false;  // device state is newer than the host AoS
+    mutable bool colors_on_device_ = false;
     mutable PerformanceStats perf_;
     int math_mode_ = 1;
     bool async_ = false;

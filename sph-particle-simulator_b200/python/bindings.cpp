@@ -7,6 +7,8 @@
 // registers them without a caster, so touching them raises TypeError there), and Simulator gains
 // set_math_mode / get_accelerations / compute_cfl_timestep.
 #include <pybind11/numpy.h>
+#include <cstring>
+
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
@@ -146,6 +148,14 @@ PYBIND11_MODULE(sph, m) {
         .def("set_async", &SPHEngine::set_async, py::arg("on"))
         .def("get_accelerations", [](const SPHEngine& e) { return vec3_array(e.get_accelerations()); })
         .def("compute_cfl_timestep", &SPHEngine::compute_cfl_timestep)
+        .def("get_instance_data",
+             [](const SPHEngine& e) {
+                 const std::vector<float> v = e.get_instance_data();
+                 py::array_t<float> a({static_cast<py::ssize_t>(v.size() / 9), static_cast<py::ssize_t>(9)});
+                 std::memcpy(a.mutable_data(), v.data(), v.size() * sizeof(float));
+                 return a;
+             },
+             "renderer instance records (N, 9): position, velocity, colour — one kernel instead of the per-frame AoS walk")
         .def("get_report_diagnostics",
              [](const SPHEngine& e) {
                  const SPHEngine::ReportDiagnostics d = e.get_report_diagnostics();

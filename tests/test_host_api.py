@@ -267,3 +267,48 @@ def test_reference_benchmark_dt_sequence_through_the_drop_in(sph):
     vel = sim.get_velocities().astype(np.float64)
     assert abs(d["max_velocity"] - np.sqrt((vel ** 2).sum(1)).max()) <= 1e-6 * d["max_velocity"]
     assert abs(d["average_density"] - sim.get_densities().astype(np.float64).mean()) <= 1e-5 * abs(d["average_density"])
+
+
+@pytest.mark.gpu
+def test_renderer_instance_records(sph, pkg):
+    """The renderer feed (reference Renderer::update_particle_data, src/renderer.cpp:279-312): position, velocity and
+    Particle::color of every particle in insertion order, from one export kernel — through the drop-in class (colours
+    of the generators: wall vs fluid) and through the C ABI (default colour, device destination)."""
+    import torch
+    sim = sph.Simulator(max_particles=30000)
+    sim.initialize(sph.SPHParameters())
+    wall = sph.create_boundary_box(np.array([0, 0.3, 0], np.float32), np.array([0.4, 0.6, 0.8], np.float32), 0.04, 0.001)
+    fluid = sph.create_fluid_block(np.array([-0.1, 0.2, 0], np.float32), np.array([0.2, 0.4, 0.8], np.float32), 0.04, 0.001)
+    sim.add_particles(wall); sim.add_particles(fluid)
+    sim.step(1e-4); sim.step(1e-4)
+    rec = sim.get_instance_data()
+    n = sim.get_particles().size()
+    assert rec.shape == (n, 9)
+    assert_bits(np.ascontiguousarray(rec[:, 0:3]), sim.get_positions(), "instance positions")
+    assert_bits(np.ascontiguousarray(rec[:, 3:6]), sim.get_velocities(), "instance velocities")
+    colors = np.array([[p.color[0], p.color[1], p.color[2]] for p in (list(wall) + list(fluid))], np.float32) if hasattr(wall[0], "color") and not isinstance(wall[0].color, (int, float)) else None
+    if colors is not None:
+        assert_bits(np.ascontiguousarray(rec[:, 6:9]), colors, "instance colours")
+    assert len(np.unique(rec[:, 6:9], axis=0)) >= 1
+    # C ABI: default colour, device destination (what a CUDA-mapped vertex buffer would be)
+    g = np.random.default_rng(3)
+    pos = g.uniform(-0.1, 0.1, size=(500, 3)).astype(np.float32)
+    vel = g.normal(size=(500, 3)).astype(np.float32)
+    ctx = pkg.Context(500, 0)
+    prm = dict(pkg.DEFAULT_PARAMS); prm.update(xmin=-1, xmax=1, ymin=-1, ymax=1, zmin=-1, zmax=1)
+    ctx.set_params(prm); ctx.upload(pos, vel, None)
+    ctx.step(1e-4)
+    host = ctx.export_instances()
+    s = ctx.download()
+    assert_bits(np.ascontiguousarray(host[:, 0:3]), s["pos"], "ABI instance positions")
+    assert_bits(np.ascontiguousarray(host[:, 3:6]), s["vel"], "ABI instance velocities")
+    assert (host[:, 6:9] == np.array([0.0, 0.5, 1.0], np.float32)).all()      # sph::Particle's default colour
+    dst = torch.zeros((500, 9), dtype=torch.float32, device="cuda:0")
+    rgb = g.uniform(size=(500, 3)).astype(np.float32)
+    ctx.set_colors(rgb)
+    ctx.export_instances(device_ptr=dst.data_ptr())
+    ctx.synchronize() if hasattr(ctx, "synchronize") else torch.cuda.synchronize()
+    dev = dst.cpu().numpy()
+    assert_bits(np.ascontiguousarray(dev[:, 0:6]), np.ascontiguousarray(host[:, 0:6]), "device destination")
+    assert_bits(np.ascontiguousarray(dev[:, 6:9]), rgb, "uploaded colours")
+    ctx.close()
