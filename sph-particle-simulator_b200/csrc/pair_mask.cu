@@ -166,33 +166,9 @@ __global__ void __launch_bounds__(kThreads, SPHB_FMASK_MINBLOCKS) k_force_mask16
         r.x = qa.x; r.y = qa.y; r.z = qa.z; r.A = qa.w; r.vx = qb.x; r.vy = qb.y; r.vz = qb.z; r.B = qb.w;
         return r;
     };
-    const float2 npxy = f2(-pi.x, -pi.y), nvxy = f2(-vi.x, -vi.y);
-    const float ninvh = pin(-a.k.inv_h);
-    // accumulators of -F_pressure / (sigma / h) and F_viscosity / (2 mu sigma / h^2): (x, y) packed, z scalar
-    float2 fpxy = f2(0.0f, 0.0f), fvxy = f2(0.0f, 0.0f);
-    float fpz = 0.0f, fvz = 0.0f;
-    // pair j -> i without a distance test (j was accepted by the density pass): force_pair_fast (pair_math.cuh) with
-    // the per-pair constant factors taken out of the sums and r = p_j - p_i (the sign is applied once at the end).
-    // 1/len uses max(d2, 1e-30): coincident particles (d2 = 0) get q = 0 and dW/dq(0) = 0, hence no pressure term,
-    // exactly like the reference's r_len < 1e-6 guard (sph_engine.cpp:403); a distinct pair closer than 1e-6
-    // contributes |dW/dq| <= 2e-6 / h instead of nothing — far below the fast-mode gates.
-    auto eval = [&](const ForceRec& q) {
-        const float2 rxy = __fadd2_rn(f2(q.x, q.y), npxy);
-        const float rz = q.z - pi.z;
-        const float d2 = fmaf(rz, rz, fmaf(rxy.y, rxy.y, rxy.x * rxy.x));
-        const float inv_len = fast_rsqrt(fmaxf(d2, 1e-30f));
-        const float t2 = fmaxf(fmaf(d2 * ninvh, inv_len, 2.0f), 0.0f);   // (2 - q)+
-        const float t1 = fmaxf(t2 - 1.0f, 0.0f);                          // (1 - q)+
-        const float gh = fmaf(-0.25f * t2, t2, t1 * t1);                  // dW/dq / (2 sigma) = (1-q)+^2 - (2-q)+^2 / 4
-        const float lq = fmaf(-4.0f, t1, t2);                             // d2W/dq2 / sigma
-        const float cp = fmaf(q.A, P_i, q.B) * (gh * inv_len);
-        fpxy = __ffma2_rn(f2(cp, cp), rxy, fpxy);
-        fpz = fmaf(cp, rz, fpz);
-        const float cv = q.A * lq;
-        const float2 uxy = __fadd2_rn(f2(q.vx, q.vy), nvxy);
-        fvxy = __ffma2_rn(f2(cv, cv), uxy, fvxy);
-        fvz = fmaf(cv, q.vz - vi.z, fvz);
-    };
+    ForceLane fl;
+    fl.init(pi, vi, P_i, a.k, (uint32_t)(a.n >> 62));
+    auto eval = [&](const ForceRec& q) { fl.eval(make_float4(q.x, q.y, q.z, q.A), make_float4(q.vx, q.vy, q.vz, q.B)); };
 
     const int e2 = a.grid.ext[2], e12 = a.grid.ext[1] * e2;
     uint32_t rel = (uint32_t)(R * e12 + R * e2);
@@ -241,14 +217,7 @@ __global__ void __launch_bounds__(kThreads, SPHB_FMASK_MINBLOCKS) k_force_mask16
         rel -= (uint32_t)e2;
         if (++d1 > R) { d1 = -R; rel -= (uint32_t)(e12 - (2 * R + 1) * e2); }
     }
-    ForceAccum f;
-    {
-        // F_p = -sum m_j term gradW with gradW along p_i - p_j = -r and gh = dW/dq / 2: the two signs cancel
-        const float sp = 2.0f * a.k.sig_h;
-        const float cvis = 2.0f * a.k.viscosity * a.k.sig_h2;
-        f.px = sp * fpxy.x; f.py = sp * fpxy.y; f.pz = sp * fpz;
-        f.vx = cvis * fvxy.x; f.vy = cvis * fvxy.y; f.vz = cvis * fvz;
-    }
+    ForceAccum f = fl.result(a.k);
     if (ovf) {
         // some column of this particle holds more candidates than its mask has bits: the candidates beyond the mask
         // are walked with the exact radius test

@@ -219,29 +219,9 @@ __global__ void __launch_bounds__(kThreadsS, SPHB_FSTAGE_MINBLOCKS) k_force_stag
     const float4* __restrict__ fa = pin(a.fa);
     const float4* __restrict__ fb = pin(a.fb);
     const uint32_t nslots = (uint32_t)a.n;
-    const float2 npxy = f2(-pi.x, -pi.y), nvxy = f2(-vi.x, -vi.y);
-    const float ninvh = hold(-a.k.inv_h, (uint32_t)(a.n >> 62));
-    // accumulators of -F_pressure / (sigma / h) and F_viscosity / (2 mu sigma / h^2): (x, y) packed, z scalar
-    float2 fpxy = f2(0.0f, 0.0f), fvxy = f2(0.0f, 0.0f);
-    float fpz = 0.0f, fvz = 0.0f;
-    // pair j -> i without a distance test (j was accepted by the density pass); see k_force_mask16 for the derivation
-    auto eval = [&](const float4& qa, const float4& qb) {   // qa = {x, y, z, A}, qb = {vx, vy, vz, B}
-        const float2 rxy = __fadd2_rn(f2(qa.x, qa.y), npxy);
-        const float rz = qa.z - pi.z;
-        const float d2 = fmaf(rz, rz, fmaf(rxy.y, rxy.y, rxy.x * rxy.x));
-        const float inv_len = fast_rsqrt(fmaxf(d2, 1e-30f));
-        const float t2 = fmaxf(fmaf(d2 * ninvh, inv_len, 2.0f), 0.0f);   // (2 - q)+
-        const float t1 = fmaxf(t2 - 1.0f, 0.0f);                          // (1 - q)+
-        const float gh = fmaf(-0.25f * t2, t2, t1 * t1);                  // dW/dq / (2 sigma) = (1-q)+^2 - (2-q)+^2 / 4
-        const float lq = fmaf(-4.0f, t1, t2);                             // d2W/dq2 / sigma
-        const float cp = fmaf(qa.w, P_i, qb.w) * (gh * inv_len);
-        fpxy = __ffma2_rn(f2(cp, cp), rxy, fpxy);
-        fpz = fmaf(cp, rz, fpz);
-        const float cv = qa.w * lq;
-        const float2 uxy = __fadd2_rn(f2(qb.x, qb.y), nvxy);
-        fvxy = __ffma2_rn(f2(cv, cv), uxy, fvxy);
-        fvz = fmaf(cv, qb.z - vi.z, fvz);
-    };
+    ForceLane fl;
+    fl.init(pi, vi, P_i, a.k, (uint32_t)(a.n >> 62));
+    auto eval = [&](const float4& qa, const float4& qb) { fl.eval(qa, qb); };
 
     const uint32_t* __restrict__ mrow = static_cast<const uint32_t*>(a.masks) + i;
     const size_t stride = a.mask_stride;
@@ -315,14 +295,7 @@ SPHB_UNROLL_N(SPHB_FSTAGE_GROUP_UNROLL)
     }
     if (!want) return;
 
-    ForceAccum f;
-    {
-        // F_p = -sum m_j term gradW with gradW along p_i - p_j = -r and gh = dW/dq / 2: the two signs cancel
-        const float sp = 2.0f * a.k.sig_h;
-        const float cvis = 2.0f * a.k.viscosity * a.k.sig_h2;
-        f.px = sp * fpxy.x; f.py = sp * fpxy.y; f.pz = sp * fpz;
-        f.vx = cvis * fvxy.x; f.vy = cvis * fvxy.y; f.vz = cvis * fvz;
-    }
+    ForceAccum f = fl.result(a.k);
     if (ovf) {
         // some column of this particle holds more candidates than its mask has bits: the candidates beyond the mask
         // are walked with the exact radius test

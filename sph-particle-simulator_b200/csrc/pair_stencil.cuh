@@ -199,6 +199,57 @@ struct DensityWalker {
     __device__ __forceinline__ float density(const PairConsts& k) const { return (rho0 + rho1) * (k.sigma * (4.0f / 6.0f)); }
 };
 
+// The force pass of ONE particle over accepted neighbours (no distance test: j was accepted by the density pass), shared
+// by the per-lane and the staged kernels so that both produce the same bits.  force_pair_fast (pair_math.cuh) with the
+// per-pair constant factors taken out of the sums, r = p_j - p_i (the sign is applied once at the end) and the two clamped
+// factors of the spline formed by saturating FFMAs: u = (2 - q)+ / 2, t = (1 - q)+ = sat(2 u - 1) (both in [0, 1]):
+//   dW/dq / (2 sigma) = t^2 - u^2,   d2W/dq2 / (2 sigma) = u - 2 t.
+// 1/len uses d2 + 1e-30: coincident particles (d2 = 0) get q = 0 and dW/dq(0) = 0, hence no pressure term, exactly like
+// the reference's r_len < 1e-6 guard (sph_engine.cpp:403) — the viscosity term keeps L(0) (quirk Q4); a distinct pair
+// closer than 1e-6 contributes |dW/dq| <= 2e-6 / h instead of nothing, far below the fast-mode gates.
+struct ForceLane {
+    float2 npxy, nvxy;
+    float pz, vz, P_i, nhinvh;
+    // accumulators of -F_pressure / (2 sigma / h) and F_viscosity / (4 mu sigma / h^2): (x, y) packed, z scalar
+    float2 fpxy, fvxy;
+    float fpz, fvz;
+
+    __device__ __forceinline__ void init(const float4& pi, const float4& vi, float P, const PairConsts& k, uint32_t zero) {
+        npxy = mk2(-pi.x, -pi.y); nvxy = mk2(-vi.x, -vi.y);
+        pz = pi.z; vz = vi.z; P_i = P;
+        nhinvh = hold(-0.5f * k.inv_h, zero);
+        fpxy = fvxy = mk2(0.0f, 0.0f);
+        fpz = fvz = 0.0f;
+    }
+    // qa = {x, y, z, A = m / (2 rho)}, qb = {vx, vy, vz, B = A P} of neighbour j
+    __device__ __forceinline__ void eval(const float4& qa, const float4& qb) {
+        const float2 rxy = __fadd2_rn(mk2(qa.x, qa.y), npxy);
+        const float rz = qa.z - pz;
+        const float d2 = fmaf(rz, rz, fmaf(rxy.y, rxy.y, rxy.x * rxy.x));
+        const float inv_len = fast_rsqrt(d2 + 1e-30f);
+        const float u = fma_sat(d2 * nhinvh, inv_len, 1.0f);      // (2 - q)+ / 2
+        const float t = fma_sat(u, 2.0f, -1.0f);                   // (1 - q)+
+        const float gh = fmaf(t, t, -(u * u));
+        const float lq = fmaf(t, -2.0f, u);
+        const float cp = fmaf(qa.w, P_i, qb.w) * (gh * inv_len);
+        fpxy = __ffma2_rn(mk2(cp, cp), rxy, fpxy);
+        fpz = fmaf(cp, rz, fpz);
+        const float cv = qa.w * lq;
+        const float2 uxy = __fadd2_rn(mk2(qb.x, qb.y), nvxy);
+        fvxy = __ffma2_rn(mk2(cv, cv), uxy, fvxy);
+        fvz = fmaf(cv, qb.z - vz, fvz);
+    }
+    // F_p = -sum m_j term gradW with gradW along p_i - p_j = -r and gh = dW/dq / (2 sigma): the two signs cancel
+    __device__ __forceinline__ ForceAccum result(const PairConsts& k) const {
+        ForceAccum f;
+        const float sp = 2.0f * k.sig_h;
+        const float cvis = 4.0f * k.viscosity * k.sig_h2;
+        f.px = sp * fpxy.x; f.py = sp * fpxy.y; f.pz = sp * fpz;
+        f.vx = cvis * fvxy.x; f.vy = cvis * fvxy.y; f.vz = cvis * fvz;
+        return f;
+    }
+};
+
 // 32-byte force-pass record of one particle, fetched with ONE 256-bit load (LDG.E.256, sm_100)
 __device__ __forceinline__ ForceRec load_rec(const ForceRec* __restrict__ p) {
     ForceRec r;
