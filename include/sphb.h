@@ -112,7 +112,15 @@ enum {
      * shared memory with asynchronous copies, one cell-column group ahead, and the lanes traverse them from there;
      * 2 (default) = the density pass staged, the force pass per lane (the faster combination as measured).
      * Identical results in all three, bit for bit.  Environment override of the default: SPHB_PAIR_MODE. */
-    SPHB_OPT_PAIR_MODE = 8
+    SPHB_OPT_PAIR_MODE = 8,
+    /* the smoothing kernel, in the order of the reference's KernelType (src/kernels.h:94-98): 0 = cubic spline (default —
+     * what SPHEngine constructs, sph_engine.cpp:17, 23, 162), 1 = Wendland C2, 2 = Gaussian: the other two classes behind
+     * create_kernel (src/kernels.cpp:166-236), which the reference engine could host unchanged because it calls
+     * W / gradW / laplacianW through a Kernel pointer (sph_engine.cpp:209, 232, 236).  1 and 2 run the tested-walk kernels
+     * (the bitmask hand-off kernels are specialised for the cubic spline).  Strict mode: Wendland C2 is bit-exact against
+     * the reference classes; the Gaussian agrees to the last bits of expf.  Unlike the reference's engine slot, the choice
+     * survives sphb_set_params. */
+    SPHB_OPT_KERNEL_TYPE = 9
 };
 
 /* ---- lifetime ---------------------------------------------------------------------------------
@@ -253,6 +261,51 @@ int sphb_get_cfl_state(sphb_ctx* ctx, float* max_v2, float* a0_xyz, int* a0_fres
 int sphb_set_cfl_state(sphb_ctx* ctx, float max_v2, const float* a0_xyz);
 int sphb_slab_download(sphb_ctx* ctx, size_t cap, uint32_t* ids, float* pos3, float* vel3, float* rho, float* pressure,
                        float* acc3, size_t* count);
+
+/* ---- several GPUs of one node behind ONE handle (csrc/multi.cu) -----------------------------------------
+ * "Multi-GPU: sphb_create_multi(ctx**, capacity, ndev, const int* devs) with the same calls".
+ * NEW, no reference counterpart (the reference is a single-process CPU program): one host thread drives one
+ * context per device with the slab protocol above — cuts of whole reference cells along one axis balanced by
+ * particle count at upload time, ONE exchange round per step (migration + two halo layers), records moved by
+ * peer-to-peer copies over NVLink (cudaMemcpyPeerAsync), no NCCL and no second process.  Every call mirrors
+ * the single-context call of the same name and keeps its contract: insertion order at the interface, host
+ * pointers, 0 / negative SPHB_E_* codes.  Strict mode reproduces the single-context results bit for bit for
+ * any number of devices; fast mode does when the single context is given the same SPHB_OPT_LAYOUT_MAJOR.
+ * `devices` may name the same ordinal more than once (several slabs on one GPU: how the path is tested on
+ * a one-GPU box).  ndev = 1 is the plain single-context path.  This is what lets sph::SPHEngine
+ * (reference sph_engine.h:89-141) own N GPUs: the host shell selects it with SPHB_DEVICES=0,1,... */
+typedef struct sphb_multi sphb_multi;
+enum {
+    /* slab axis: -1 (default) = the longest axis of the uploaded particles' bounding box, else 0 / 1 / 2 */
+    SPHB_OPT_MULTI_AXIS = 100
+};
+int sphb_create_multi(sphb_multi** out, size_t capacity, int ndev, const int* devices);
+void sphb_destroy_multi(sphb_multi* m);
+const char* sphb_multi_last_error(const sphb_multi* m);   /* m may be NULL: error of the last failed sphb_create_multi */
+int sphb_multi_device_count(const sphb_multi* m);
+/* any SPHB_OPT_* of the single context (applied to every device) or SPHB_OPT_MULTI_* */
+int sphb_multi_set_option(sphb_multi* m, int option, int64_t value);
+int sphb_multi_set_params(sphb_multi* m, const sphb_params* p);
+/* needs the parameters first: the slabs are cut in units of neighbor_search_radius */
+int sphb_multi_upload(sphb_multi* m, size_t n, const float* pos3, const float* vel3, const float* mass);
+int sphb_multi_upload_strided(sphb_multi* m, size_t n, const void* base, size_t stride, size_t off_pos, size_t off_vel,
+                              size_t off_mass);
+int sphb_multi_step(sphb_multi* m, float dt);             /* dt <= 0: the adaptive timestep from the global maxima */
+int sphb_multi_run_steps(sphb_multi* m, size_t n, float dt);
+int sphb_multi_synchronize(sphb_multi* m);
+int sphb_multi_size(sphb_multi* m, size_t* n);
+int sphb_multi_download(sphb_multi* m, float* pos3, float* vel3, float* rho, float* pressure, float* acc3);
+int sphb_multi_download_strided(sphb_multi* m, void* base, size_t stride, size_t off_pos, size_t off_vel, size_t off_density,
+                                size_t off_pressure);
+int sphb_multi_get_time(sphb_multi* m, float* current_time, uint64_t* step_count);
+int sphb_multi_set_time(sphb_multi* m, float current_time, uint64_t step_count);
+int sphb_multi_cfl_timestep(sphb_multi* m, float* dt);
+/* stage times: the maximum over the devices; kernel_launches: the sum; max_neighbors: the maximum */
+int sphb_multi_get_stats(sphb_multi* m, sphb_stats* out);
+int sphb_multi_reset_stats(sphb_multi* m);
+int sphb_multi_diagnostics(sphb_multi* m, double* sum_density, double* kinetic, float* max_speed);
+/* per device: particles owned and ghost copies held after the last step's exchange (arrays of ndev, may be NULL) */
+int sphb_multi_layout(sphb_multi* m, int32_t* cuts_ndev_plus_1, int* axis, uint64_t* owned, uint64_t* ghosts);
 
 #ifdef __cplusplus
 }

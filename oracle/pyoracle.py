@@ -110,6 +110,7 @@ class OracleLib:
         sig("get_stats", None, vp, _dp)
         sig("reset_stats", None, vp)
         sig("get_densities_raw", sz, vp, sz, _fp)
+        sig("set_kernel", C.c_int, vp, C.c_int)
         sig("kernel_W", f32, vp, f32, f32, f32)
         sig("kernel_gradW", None, vp, f32, f32, f32, _fp)
         sig("kernel_lapW", f32, vp, f32, f32, f32)
@@ -167,6 +168,12 @@ class Engine:
 
     def set_smoothing_length(self, h):
         self.L.set_smoothing_length(self.h, float(h))
+
+    def set_kernel(self, kernel_type: int):
+        """0 cubic spline (the engine's own), 1 Wendland C2, 2 Gaussian: create_kernel (reference kernels.cpp:224-236)
+        installed into the engine's kernel slot; initialize() / set_smoothing_length() put the cubic spline back."""
+        if self.L.set_kernel(self.h, int(kernel_type)) != 0:
+            raise ValueError(f"unknown kernel type {kernel_type}")
 
     def set_gravity(self, g):
         self.L.set_gravity(self.h, float(g))

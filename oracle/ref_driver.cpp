@@ -253,6 +253,16 @@ size_t ref_get_densities_raw(void* e, size_t cap, float* out) {
 }
 
 // Smoothing-kernel known-answer probes (kernels.cpp:140-153 through the engine's own kernel object).
+// create_kernel (kernels.cpp:224-236) installed into the engine's own kernel slot (sph_engine.h:42): the unmodified engine
+// then runs its density / force passes through the reference's own Wendland C2 / Gaussian classes (virtual calls at
+// sph_engine.cpp:209, 232, 236).  type: 0 cubic spline, 1 Wendland C2, 2 Gaussian (kernels.h KernelType order).
+int ref_set_kernel(void* e, int type) {
+    if (type < 0 || type > 2) return -1;
+    auto* eng = static_cast<SPHEngine*>(e);
+    const sph::KernelType kt = type == 0 ? sph::KernelType::CUBIC_SPLINE : (type == 1 ? sph::KernelType::WENDLAND_C2 : sph::KernelType::GAUSSIAN);
+    eng->kernel_ = sph::create_kernel(kt, eng->params_.smoothing_length);
+    return 0;
+}
 float ref_kernel_W(void* e, float x, float y, float z) { return static_cast<SPHEngine*>(e)->kernel_->W(glm::vec3(x, y, z)); }
 void ref_kernel_gradW(void* e, float x, float y, float z, float* out3) {
     glm::vec3 g = static_cast<SPHEngine*>(e)->kernel_->gradW(glm::vec3(x, y, z));

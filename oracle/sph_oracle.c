@@ -49,8 +49,12 @@ typedef struct {
     params_t prm;
     /* SpatialHash state (spatial_hash.h:13-16) */
     float cell_size, inv_cell;
-    /* CubicSplineKernel state (kernels.cpp:12-14, 23-36) */
-    float kh, kh_sq, sigma;
+    /* Kernel state: CubicSplineKernel (kernels.cpp:12-14, 23-36), WendlandC2Kernel (166-169), GaussianKernel (201-205).
+     * ktype: 0 = cubic spline (what SPHEngine constructs), 1 = Wendland C2, 2 = Gaussian — the engine holds a
+     * std::unique_ptr<Kernel> and calls W / gradW / laplacianW virtually (sph_engine.cpp:209, 232, 236), so the other
+     * two classes behind create_kernel (kernels.cpp:224-236) drop in without any other change. */
+    int ktype;
+    float kh, kh_sq, sigma, wnorm, gnorm, gssi;
     int initialized;
     float time;
     size_t step_count;
@@ -110,6 +114,9 @@ static void make_kernel(engine_t* e, float h) {
     e->kh = h;
     e->kh_sq = h * h;
     e->sigma = 1.0f / ((float)M_PI * h * h * h);
+    e->wnorm = 21.0f / (2.0f * (float)M_PI * h * h * h);          /* kernels.cpp:168 */
+    e->gssi = 1.0f / (h * h);                                      /* kernels.cpp:203 */
+    e->gnorm = 1.0f / powf((float)M_PI * h * h, 1.5f);             /* kernels.cpp:204 (std::pow(float, float)) */
 }
 
 /* ---------------------------------------------------------------- smoothing kernel (3-D cubic) */
@@ -119,7 +126,16 @@ static inline float len3(float x, float y, float z) { return sqrtf(x * x + y * y
 
 /* CubicSplineKernel::W → W_3d, kernels.cpp:140-143, 58-66 */
 static inline float kW(const engine_t* e, float rx, float ry, float rz) {
+    if (e->ktype == 2) {   /* GaussianKernel::W, kernels.cpp:207-210 */
+        float r_sq = rx * rx + ry * ry + rz * rz;
+        return e->gnorm * expf(-r_sq * e->gssi);
+    }
     float q = len3(rx, ry, rz) / e->kh;
+    if (e->ktype == 1) {   /* WendlandC2Kernel::W, kernels.cpp:171-177 */
+        if (q >= 2.0f) return 0.0f;
+        float tmp = 1.0f - 0.5f * q;
+        return e->wnorm * tmp * tmp * tmp * tmp * (2.0f * q + 1.0f);
+    }
     if (q >= 0.0f && q <= 1.0f) {
         return e->sigma * (2.0f / 3.0f - q * q + 0.5f * q * q * q);
     } else if (q > 1.0f && q <= 2.0f) {
@@ -131,6 +147,25 @@ static inline float kW(const engine_t* e, float rx, float ry, float rz) {
 
 /* CubicSplineKernel::gradW → gradW_3d, kernels.cpp:145-148, 96-108 */
 static inline void kgradW(const engine_t* e, float rx, float ry, float rz, float* gx, float* gy, float* gz) {
+    if (e->ktype == 2) {   /* GaussianKernel::gradW, kernels.cpp:212-216: ((((-2 s) norm) exp) * r */
+        float r_sq = rx * rx + ry * ry + rz * rz;
+        float exp_term = expf(-r_sq * e->gssi);
+        float s = -2.0f * e->gssi * e->gnorm * exp_term;
+        *gx = s * rx; *gy = s * ry; *gz = s * rz;
+        return;
+    }
+    if (e->ktype == 1) {   /* WendlandC2Kernel::gradW, kernels.cpp:179-190 */
+        float r_len = len3(rx, ry, rz);
+        *gx = 0.0f; *gy = 0.0f; *gz = 0.0f;
+        if (r_len < 1e-6f) return;
+        float q = r_len / e->kh;
+        if (q >= 2.0f) return;
+        float tmp = 1.0f - 0.5f * q;
+        float dW_dq = -5.0f * tmp * tmp * tmp * q;
+        float s = e->wnorm * dW_dq, d = r_len * e->kh;
+        *gx = s * (rx / d); *gy = s * (ry / d); *gz = s * (rz / d);
+        return;
+    }
     float q = len3(rx, ry, rz) / e->kh;
     float r_len = len3(rx, ry, rz);
     *gx = 0.0f; *gy = 0.0f; *gz = 0.0f;
@@ -149,7 +184,17 @@ static inline void kgradW(const engine_t* e, float rx, float ry, float rz, float
 
 /* CubicSplineKernel::laplacianW → laplacianW_3d, kernels.cpp:150-153, 130-138 */
 static inline float klapW(const engine_t* e, float rx, float ry, float rz) {
+    if (e->ktype == 2) {   /* GaussianKernel::laplacianW, kernels.cpp:218-222 */
+        float r_sq = rx * rx + ry * ry + rz * rz;
+        float exp_term = expf(-r_sq * e->gssi);
+        return 2.0f * e->gssi * e->gnorm * exp_term * (2.0f * e->gssi * r_sq - 3.0f);
+    }
     float q = len3(rx, ry, rz) / e->kh;
+    if (e->ktype == 1) {   /* WendlandC2Kernel::laplacianW, kernels.cpp:192-198 */
+        if (q >= 2.0f) return 0.0f;
+        float tmp = 1.0f - 0.5f * q;
+        return e->wnorm * (5.0f / e->kh_sq) * tmp * tmp * (5.0f * q - 3.0f);
+    }
     if (q >= 0.0f && q <= 1.0f) {
         return e->sigma * (-2.0f + 3.0f * q) / e->kh_sq;
     } else if (q > 1.0f && q <= 2.0f) {
@@ -553,6 +598,7 @@ void port_initialize(void* h, const float* p16) {
     unpack(p16, &e->prm);
     set_cell_size(e, e->prm.neighbor_search_radius);
     make_kernel(e, e->prm.smoothing_length);
+    e->ktype = 0;
     e->buffers_ready = 1;
     e->initialized = 1;
     port_reset_stats(h);
@@ -565,6 +611,7 @@ void port_set_smoothing_length(void* h, float hh) {
     e->prm.neighbor_search_radius = 2.0f * hh;
     set_cell_size(e, e->prm.neighbor_search_radius);
     make_kernel(e, hh);
+    e->ktype = 0;
 }
 
 /* SPHEngine::set_parameters, sph_engine.cpp:152-156 */
@@ -797,6 +844,14 @@ size_t port_get_densities_raw(void* h, size_t cap, float* out) {
     return e->cap;
 }
 
+/* create_kernel(type, h), kernels.cpp:224-236, installed where the engine keeps its kernel (sph_engine.h:42).  Like the
+ * reference, initialize() and set_smoothing_length() put the cubic spline back (sph_engine.cpp:23, 162). */
+int port_set_kernel(void* h, int type) {
+    engine_t* e = (engine_t*)h;
+    if (type < 0 || type > 2) return -1;
+    e->ktype = type;
+    return 0;
+}
 float port_kernel_W(void* h, float x, float y, float z) { return kW((engine_t*)h, x, y, z); }
 void port_kernel_gradW(void* h, float x, float y, float z, float* o) { kgradW((engine_t*)h, x, y, z, &o[0], &o[1], &o[2]); }
 float port_kernel_lapW(void* h, float x, float y, float z) { return klapW((engine_t*)h, x, y, z); }

@@ -8,4 +8,4 @@ of that ABI), ``host/`` (C++ SPHEngine shell with the reference's class surface)
 module ``sph`` with the reference's Python surface).
 """
 from . import capi  # noqa: F401
-from .capi import Context, SphbError, DEFAULT_PARAMS, PARAM_FIELDS  # noqa: F401
+from .capi import Context, MultiContext, SphbError, DEFAULT_PARAMS, PARAM_FIELDS  # noqa: F401

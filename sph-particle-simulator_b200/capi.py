@@ -35,6 +35,9 @@ OPT_PAIR_KERNEL = 5
 OPT_GRID_REFINE = 6
 OPT_LAYOUT_MAJOR = 7
 OPT_PAIR_MODE = 8
+OPT_KERNEL_TYPE = 9
+KERNEL_CUBIC_SPLINE, KERNEL_WENDLAND_C2, KERNEL_GAUSSIAN = 0, 1, 2
+OPT_MULTI_AXIS = 100
 MATH_STRICT = 0
 MATH_FAST = 1
 
@@ -48,6 +51,11 @@ ABI_SYMBOLS = (
     "sphb_set_slab", "sphb_upload_ids", "sphb_slab_append", "sphb_slab_exchange_pack", "sphb_slab_exchange_count",
     "sphb_slab_exchange_split", "sphb_get_cfl_state", "sphb_set_cfl_state",
     "sphb_slab_download",
+    "sphb_create_multi", "sphb_destroy_multi", "sphb_multi_last_error", "sphb_multi_device_count", "sphb_multi_set_option",
+    "sphb_multi_set_params", "sphb_multi_upload", "sphb_multi_upload_strided", "sphb_multi_step", "sphb_multi_run_steps",
+    "sphb_multi_synchronize", "sphb_multi_size", "sphb_multi_download", "sphb_multi_download_strided", "sphb_multi_get_time",
+    "sphb_multi_set_time", "sphb_multi_cfl_timestep", "sphb_multi_get_stats", "sphb_multi_reset_stats", "sphb_multi_diagnostics",
+    "sphb_multi_layout",
 )
 
 
@@ -128,6 +136,29 @@ def load_library() -> C.CDLL:
     L.sphb_slab_exchange_split.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, sz]
     L.sphb_slab_append.argtypes = [vp, vp, sz, C.c_int]
     L.sphb_slab_download.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, C.POINTER(sz)]
+    L.sphb_create_multi.argtypes = [C.POINTER(vp), sz, C.c_int, C.POINTER(C.c_int)]
+    L.sphb_destroy_multi.argtypes = [vp]
+    L.sphb_destroy_multi.restype = None
+    L.sphb_multi_last_error.restype = C.c_char_p
+    L.sphb_multi_last_error.argtypes = [vp]
+    L.sphb_multi_device_count.argtypes = [vp]
+    L.sphb_multi_set_option.argtypes = [vp, C.c_int, C.c_int64]
+    L.sphb_multi_set_params.argtypes = [vp, C.POINTER(SphbParams)]
+    L.sphb_multi_upload.argtypes = [vp, sz, vp, vp, vp]
+    L.sphb_multi_upload_strided.argtypes = [vp, sz, vp, sz, sz, sz, sz]
+    L.sphb_multi_step.argtypes = [vp, C.c_float]
+    L.sphb_multi_run_steps.argtypes = [vp, sz, C.c_float]
+    L.sphb_multi_synchronize.argtypes = [vp]
+    L.sphb_multi_size.argtypes = [vp, C.POINTER(sz)]
+    L.sphb_multi_download.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.sphb_multi_download_strided.argtypes = [vp, vp, sz, sz, sz, sz, sz]
+    L.sphb_multi_get_time.argtypes = [vp, fp, C.POINTER(C.c_uint64)]
+    L.sphb_multi_set_time.argtypes = [vp, C.c_float, C.c_uint64]
+    L.sphb_multi_cfl_timestep.argtypes = [vp, fp]
+    L.sphb_multi_get_stats.argtypes = [vp, C.POINTER(SphbStats)]
+    L.sphb_multi_reset_stats.argtypes = [vp]
+    L.sphb_multi_diagnostics.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), fp]
+    L.sphb_multi_layout.argtypes = [vp, vp, C.POINTER(C.c_int), vp, vp]
     _lib = L
     return L
 
@@ -367,3 +398,121 @@ class Context:
     def set_cfl_state(self, max_v2, a0):
         arr = (C.c_float * 3)(*[float(x) for x in a0])
         self._ck(self.L.sphb_set_cfl_state(self.h, C.c_float(float(max_v2)), arr))
+
+
+class MultiContext:
+    """One sphb_multi: ONE engine over several GPUs of a node (or several slabs on one GPU), driven from this process
+    through the C ABI alone (csrc/multi.cu) — no torch.distributed, no NCCL.  Same method names as :class:`Context`."""
+
+    def __init__(self, capacity: int, devices):
+        self.L = load_library()
+        self.capacity = int(capacity)
+        self.devices = [int(d) for d in devices]
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        h = C.c_void_p()
+        rc = self.L.sphb_create_multi(C.byref(h), self.capacity, len(self.devices), arr)
+        if rc != 0:
+            raise SphbError(rc, (self.L.sphb_multi_last_error(None) or b"").decode())
+        self.h = h
+
+    def _ck(self, rc: int):
+        if rc != 0:
+            raise SphbError(rc, (self.L.sphb_multi_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.sphb_destroy_multi(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def device_count(self) -> int:
+        return self.L.sphb_multi_device_count(self.h)
+
+    def set_option(self, opt: int, value: int):
+        self._ck(self.L.sphb_multi_set_option(self.h, opt, int(value)))
+
+    def set_params(self, params: dict):
+        p = SphbParams(**{k: float(params[k]) for k in PARAM_FIELDS})
+        self._ck(self.L.sphb_multi_set_params(self.h, C.byref(p)))
+
+    def synchronize(self):
+        self._ck(self.L.sphb_multi_synchronize(self.h))
+
+    def upload(self, pos, vel=None, mass=None):
+        pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+        n = pos.shape[0]
+        vel = None if vel is None else np.ascontiguousarray(vel, np.float32).reshape(n, 3)
+        mass = None if mass is None else np.ascontiguousarray(np.broadcast_to(np.asarray(mass, np.float32), (n,)))
+        self._ck(self.L.sphb_multi_upload(self.h, n, _ptr(pos), _ptr(vel), _ptr(mass)))
+
+    def upload_strided(self, n: int, base_ptr: int, stride: int, off_pos: int, off_vel: int, off_mass: int):
+        self._ck(self.L.sphb_multi_upload_strided(self.h, int(n), C.c_void_p(base_ptr), stride, off_pos, off_vel, off_mass))
+
+    @property
+    def size(self) -> int:
+        n = C.c_size_t()
+        self._ck(self.L.sphb_multi_size(self.h, C.byref(n)))
+        return n.value
+
+    def download(self, pos=True, vel=True, rho=True, pressure=True, acc=True) -> dict:
+        n = self.size
+        out = {}
+        if pos: out["pos"] = np.zeros((n, 3), np.float32)
+        if vel: out["vel"] = np.zeros((n, 3), np.float32)
+        if rho: out["rho"] = np.zeros(n, np.float32)
+        if pressure: out["P"] = np.zeros(n, np.float32)
+        if acc: out["acc"] = np.zeros((n, 3), np.float32)
+        self._ck(self.L.sphb_multi_download(self.h, _ptr(out.get("pos")), _ptr(out.get("vel")), _ptr(out.get("rho")),
+                                            _ptr(out.get("P")), _ptr(out.get("acc"))))
+        return out
+
+    def download_strided(self, base_ptr: int, stride: int, off_pos, off_vel, off_density, off_pressure):
+        self._ck(self.L.sphb_multi_download_strided(self.h, C.c_void_p(base_ptr), stride, int(off_pos), int(off_vel),
+                                                    int(off_density), int(off_pressure)))
+
+    def step(self, dt: float = 0.0):
+        self._ck(self.L.sphb_multi_step(self.h, float(dt)))
+
+    def run_steps(self, n: int, dt: float = 0.0):
+        self._ck(self.L.sphb_multi_run_steps(self.h, int(n), float(dt)))
+
+    def get_time(self):
+        t, s = C.c_float(), C.c_uint64()
+        self._ck(self.L.sphb_multi_get_time(self.h, C.byref(t), C.byref(s)))
+        return t.value, s.value
+
+    def set_time(self, t: float, step_count: int):
+        self._ck(self.L.sphb_multi_set_time(self.h, float(t), int(step_count)))
+
+    def cfl_timestep(self) -> float:
+        dt = C.c_float()
+        self._ck(self.L.sphb_multi_cfl_timestep(self.h, C.byref(dt)))
+        return dt.value
+
+    def stats(self) -> dict:
+        s = SphbStats()
+        self._ck(self.L.sphb_multi_get_stats(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in SphbStats._fields_}
+
+    def reset_stats(self):
+        self._ck(self.L.sphb_multi_reset_stats(self.h))
+
+    def diagnostics(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_float()
+        self._ck(self.L.sphb_multi_diagnostics(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def layout(self) -> dict:
+        """Cuts (reference cells on the slab axis), the axis and per-device owned / halo-copy counts of the last exchange."""
+        g = self.device_count
+        cuts = np.zeros(g + 1, np.int32)
+        owned, ghosts = np.zeros(g, np.uint64), np.zeros(g, np.uint64)
+        axis = C.c_int()
+        self._ck(self.L.sphb_multi_layout(self.h, _ptr(cuts), C.byref(axis), _ptr(owned), _ptr(ghosts)))
+        return {"cuts": cuts, "axis": axis.value, "owned": owned, "ghosts": ghosts}

@@ -41,6 +41,7 @@ struct sphb_ctx {
     int pair_mode = 2;       // R >= 4 mask kernels: 0 = per-lane global loads (pair_mask.cu), 1 = shared-memory staged (pair_stage.cu), 2 = staged density pass + per-lane force pass
     int layout_major = 0;    // fast-mode layout: physical axis that is most significant in the cell order (slab mode: the slab axis)
     int grid_refine = 4;     // internal cell = neighbor_search_radius / grid_refine (fast mode; strict always 1)
+    int kernel_type = 0;     // SPHB_OPT_KERNEL_TYPE: 0 cubic spline (what SPHEngine constructs), 1 Wendland C2, 2 Gaussian
 
     float4* posm[2] = {nullptr, nullptr};
     float4* velid[2] = {nullptr, nullptr};
@@ -265,7 +266,7 @@ int ensure_cell_table(sphb_ctx* c, const GridDesc& g) {
     return SPHB_OK;
 }
 
-PairConsts make_pair_consts(const sphb_params& p) {
+PairConsts make_pair_consts(const sphb_params& p, int kernel_type) {
     PairConsts k;
     const float h = p.smoothing_length;
     k.h = h;
@@ -273,6 +274,12 @@ PairConsts make_pair_consts(const sphb_params& p) {
     k.sigma = 1.0f / (static_cast<float>(M_PI) * h * h * h);  // kernels.cpp:27
     k.r2 = p.neighbor_search_radius * p.neighbor_search_radius;  // sph_engine.cpp:347
     k.w0 = k.sigma * (2.0f / 3.0f);                   // W(0): sigma * (2/3 - 0*0 + 0.5*0*0*0)
+    k.wnorm = 21.0f / (2.0f * static_cast<float>(M_PI) * h * h * h);             // kernels.cpp:168
+    k.gssi = 1.0f / (h * h);                                                      // kernels.cpp:203
+    k.gnorm = 1.0f / powf(static_cast<float>(M_PI) * h * h, 1.5f);                // kernels.cpp:204 (std::pow(float, float))
+    // W(0) of the other classes: Wendland norm * 1^4 * (2*0 + 1) (kernels.cpp:171-177), Gaussian norm * exp(-0) (207-210)
+    if (kernel_type == kKernelWendlandC2) k.w0 = k.wnorm;
+    if (kernel_type == kKernelGaussian) k.w0 = k.gnorm;
     k.rest_density = p.rest_density;
     k.gas_constant = p.gas_constant;
     k.viscosity = p.viscosity;
@@ -302,7 +309,7 @@ void free_all(sphb_ctx* c) {
     }
     cudaFree(c->cell_ticket); cudaFree(c->slot_src);
     cudaFree(c->masks); cudaFree(c->fab); cudaFree(c->colors);
-    cudaFree(c->rho_p); cudaFree(c->fa); cudaFree(c->fb); cudaFree(c->acc); cudaFree(c->nbr_count);
+    cudaFree(c->rho_p); cudaFree(c->fa); if (!SPHB_FORCE_REC32) cudaFree(c->fb); cudaFree(c->acc); cudaFree(c->nbr_count);
     cudaFree(c->cell_start);
     cudaFree(c->sc); cudaFree(c->d_stage); cudaFree(c->d_box); cudaFree(c->d_counts); cudaFree(c->sort_scratch);
     if (c->h_sc) cudaFreeHost(c->h_sc);
@@ -450,6 +457,10 @@ int sphb_set_option(sphb_ctx* c, int option, int64_t value) {
             if (value < 0 || value > 2) return fail(c, SPHB_E_INVALID, "layout major axis must be 0..2");
             c->layout_major = (int)value;
             return SPHB_OK;
+        case SPHB_OPT_KERNEL_TYPE:
+            if (value < 0 || value > 2) return fail(c, SPHB_E_INVALID, "kernel type must be 0 (cubic spline), 1 (Wendland C2) or 2 (Gaussian)");
+            c->kernel_type = (int)value;
+            return SPHB_OK;
         default:
             return fail(c, SPHB_E_INVALID, "unknown option %d", option);
     }
@@ -466,6 +477,7 @@ int sphb_get_option(const sphb_ctx* c, int option, int64_t* value) {
         case SPHB_OPT_GRID_REFINE: *value = c->grid_refine; return SPHB_OK;
         case SPHB_OPT_LAYOUT_MAJOR: *value = c->layout_major; return SPHB_OK;
         case SPHB_OPT_PAIR_MODE: *value = c->pair_mode; return SPHB_OK;
+        case SPHB_OPT_KERNEL_TYPE: *value = c->kernel_type; return SPHB_OK;
         default: return SPHB_E_INVALID;
     }
 }
@@ -652,16 +664,19 @@ int sphb_step(sphb_ctx* c, float dt) {
     // strict mode keeps the reference's cell size so the device layout IS the reference order; fast mode
     // may sort on a finer grid (fewer candidates per particle) and walk refine x as many cells per axis
     int refine = (c->math_mode == 0) ? 1 : c->grid_refine;
+    // Wendland C2 / Gaussian (SPHB_OPT_KERNEL_TYPE): the tested-walk kernels, on the grid that suits them (cells of nsr / 2)
+    const int pair_kernel = c->kernel_type != kKernelCubic ? 0 : c->pair_kernel;
+    if (c->kernel_type != kKernelCubic && refine > 2) refine = 2;
     // the mask kernels walk at most kMaskMaxRadius cells per axis: with a wider reference walk (SPHB_OPT_WALK_RADIUS 2 =
     // the reference's own 125-cell query) refine only as far as they support
-    if (c->math_mode != 0 && c->pair_kernel == 2 && c->walk_radius * refine > kMaskMaxRadius && c->walk_radius <= kMaskMaxRadius)
+    if (c->math_mode != 0 && pair_kernel == 2 && c->walk_radius * refine > kMaskMaxRadius && c->walk_radius <= kMaskMaxRadius)
         refine = kMaskMaxRadius / c->walk_radius;
     // pair-kernel variant 2 (bitmask hand-off) walks R = walk_radius * refine cells per axis, R in [2, 4], and uses
     // the fast-mode layout.  A refined cell table that would be too large falls back to coarser grids.
     int variant = 0, layout = -1;
     GridDesc g, gc;
     for (;; --refine) {
-        variant = (c->math_mode == 0) ? 0 : c->pair_kernel;
+        variant = (c->math_mode == 0) ? 0 : pair_kernel;
         const int Rw = c->walk_radius * refine;
         if (variant == 2 && (Rw < kMaskMinRadius || Rw > kMaskMaxRadius)) variant = 0;
         layout = (variant == 2) ? (c->slab_on ? c->slab.axis : c->layout_major) : -1;
@@ -688,7 +703,7 @@ int sphb_step(sphb_ctx* c, float dt) {
     // force-pass records: two arrays of 16-byte halves for the 16-bit mask kernels (conflict-free LDS.128 gathers when
     // staged) and the tested-walk kernels (strict mode, variant 0); ONE 32-byte record per particle (one LDG.E.256) for
     // the 64-bit mask kernels of pair_mask_wide.cu
-    const PairConsts pk = make_pair_consts(c->prm);
+    const PairConsts pk = make_pair_consts(c->prm, c->kernel_type);
     const int mode = (variant == 2 && c->walk_radius * refine >= 4) ? c->pair_mode : 0;
     const bool split = variant == 2 && c->walk_radius * refine >= 4;   // 16-bit mask kernels (pair_mask.cu, pair_stage.cu)
     if (variant == 2 && !split && !c->fab) {
@@ -698,10 +713,16 @@ int sphb_step(sphb_ctx* c, float dt) {
     }
     if ((variant != 2 || split) && !c->fa) {
         const size_t cap = c->capacity ? c->capacity : 1;
+#if SPHB_FORCE_REC32
+        CU(c, cudaMalloc(&c->fa, 2 * cap * sizeof(float4)));   // interleaved halves: fb = fa + 1, stride 2 (the tested-walk kernels use the
+        c->fb = c->fa + cap;                                    // same allocation as two plain arrays)
+        CU(c, cudaMemsetAsync(c->fa, 0, 2 * cap * sizeof(float4), c->stream));
+#else
         CU(c, cudaMalloc(&c->fa, cap * sizeof(float4)));
         CU(c, cudaMalloc(&c->fb, cap * sizeof(float4)));
         CU(c, cudaMemsetAsync(c->fa, 0, cap * sizeof(float4), c->stream));
         CU(c, cudaMemsetAsync(c->fb, 0, cap * sizeof(float4), c->stream));
+#endif
     }
     if (c->debug_capture) { rc = ensure_debug(c); if (rc) return rc; }
 
@@ -746,7 +767,7 @@ int sphb_step(sphb_ctx* c, float dt) {
     pa.cell_start = c->cell_start;
     pa.rho_p = c->rho_p;
     pa.fa = c->fa;
-    pa.fb = c->fb;
+    pa.fb = (SPHB_FORCE_REC32 && split) ? c->fa + 1 : c->fb;
     pa.acc = c->acc;
     pa.masks = c->masks;
     pa.mask_stride = c->mask_stride;
@@ -758,6 +779,7 @@ int sphb_step(sphb_ctx* c, float dt) {
     pa.walk_radius = c->walk_radius * refine;
     pa.strict = c->math_mode == 0;
     pa.variant = variant;
+    pa.kernel_type = c->kernel_type;
     pa.mode = mode;
     pa.slab_axis = c->slab_on ? c->slab.axis : -1;
     pa.rho_lo = c->slab_on ? c->slab.own_lo - 1 : 0;
@@ -979,7 +1001,8 @@ int sphb_set_slab(sphb_ctx* c, const sphb_slab* slab) {
     if (!c) return SPHB_E_INVALID;
     if (!slab) { c->slab_on = false; return SPHB_OK; }
     if (slab->axis < 0 || slab->axis > 2) return fail(c, SPHB_E_INVALID, "slab axis must be 0..2");
-    if (slab->own_hi <= slab->own_lo) return fail(c, SPHB_E_INVALID, "empty slab [%d, %d)", slab->own_lo, slab->own_hi);
+    // own_hi == own_lo: a rank that owns no cells (more ranks than the scene has cell layers to share); it never holds particles
+    if (slab->own_hi < slab->own_lo) return fail(c, SPHB_E_INVALID, "inverted slab [%d, %d)", slab->own_lo, slab->own_hi);
     if (slab->halo_layers < 2) return fail(c, SPHB_E_INVALID, "halo_layers must be >= 2 (density of the first ghost layer is recomputed locally)");
     if (slab->id_space == 0 || slab->id_space > (1ull << 31)) return fail(c, SPHB_E_INVALID, "id_space must be in [1, 2^31]");
     c->slab = *slab;

@@ -82,7 +82,9 @@ __device__ __forceinline__ unsigned face_bits(const float4& p, float inv_cell) {
 }
 
 // ---- one thread per particle, private tested walk (strict mode; fast-mode variant 0) -------------------------------------------------
-template <bool STRICT>
+// KT: the smoothing kernel (kKernelCubic = what SPHEngine constructs; Wendland C2 / Gaussian = the other classes behind
+// create_kernel, reference kernels.cpp:166-236 — pair_math.cuh)
+template <bool STRICT, int KT>
 __global__ void __launch_bounds__(kThreads, SPHB_DENSITY_MINBLOCKS) k_density_simple(PairArgs a) {
     const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
     unsigned count = 0;
@@ -107,7 +109,9 @@ __global__ void __launch_bounds__(kThreads, SPHB_DENSITY_MINBLOCKS) k_density_si
                 if (d2 <= r2) {
                     ++count;
                     if (STRICT) {
-                        if (j != (uint32_t)i) rho = __fadd_rn(rho, __fmul_rn(pj.w, w_strict(a.k, d2)));
+                        if (j != (uint32_t)i) rho = __fadd_rn(rho, __fmul_rn(pj.w, w_strict_k<KT>(a.k, d2)));
+                    } else if (KT != kKernelCubic) {
+                        rho += pj.w * w_fast_k<KT>(a.k, d2);
                     } else {
                         const float q = fast_sqrt(d2) * inv_h;
                         const float t2 = fmaxf(2.0f - q, 0.0f), t1 = fmaxf(1.0f - q, 0.0f);
@@ -116,7 +120,7 @@ __global__ void __launch_bounds__(kThreads, SPHB_DENSITY_MINBLOCKS) k_density_si
                 }
             }
         });
-        if (!STRICT) rho *= sig6;
+        if (!STRICT) rho *= (KT == kKernelCubic ? sig6 : w_norm_k<KT>(a.k));
         float P;
         if (STRICT) P = __fmul_rn(a.k.gas_constant, __fsub_rn(rho, a.k.rest_density));
         else P = a.k.gas_constant * (rho - a.k.rest_density);
@@ -135,7 +139,7 @@ __global__ void __launch_bounds__(kThreads, SPHB_DENSITY_MINBLOCKS) k_density_si
     if ((threadIdx.x & 31) == 0 && count > *(volatile unsigned int*)&a.sc->max_neighbors) atomicMax(&a.sc->max_neighbors, count);
 }
 
-template <bool STRICT>
+template <bool STRICT, int KT>
 __global__ void __launch_bounds__(kThreads, SPHB_FORCE_MINBLOCKS) k_force_simple(PairArgs a) {
     const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= a.n) return;
@@ -158,8 +162,10 @@ __global__ void __launch_bounds__(kThreads, SPHB_FORCE_MINBLOCKS) k_force_simple
             if (d2 <= r2 && (!STRICT || j != (uint32_t)i)) {   // fast: the self pair contributes 0 (r = 0, v_j - v_i = 0)
                 const float4 vj = __ldg(&a.fb[j]);
                 if (STRICT) {
-                    force_pair_strict(a.k, f, rx, ry, rz, d2, __fsub_rn(vj.x, vi.x), __fsub_rn(vj.y, vi.y),
-                                      __fsub_rn(vj.z, vi.z), P_i, pj.w, vj.w);
+                    force_pair_strict_k<KT>(a.k, f, rx, ry, rz, d2, __fsub_rn(vj.x, vi.x), __fsub_rn(vj.y, vi.y),
+                                            __fsub_rn(vj.z, vi.z), P_i, pj.w, vj.w);
+                } else if (KT != kKernelCubic) {
+                    force_pair_fast_k<KT>(a.k, f, rx, ry, rz, d2, vj.x - vi.x, vj.y - vi.y, vj.z - vi.z, P_i, pj.w, vj.w);
                 } else {
                     force_pair_fast(a.k, f, rx, ry, rz, d2, vj.x - vi.x, vj.y - vi.y, vj.z - vi.z, P_i, pj.w, vj.w);
                 }
@@ -175,8 +181,14 @@ int launch_density(const PairArgs& a, cudaStream_t st) {
     if (a.n == 0) return 0;
     if (a.variant == 2 && !a.strict) return launch_density_mask(a, st);
     const unsigned nb = (unsigned)((a.n + kThreads - 1) / kThreads);
-    if (a.strict) k_density_simple<true><<<nb, kThreads, 0, st>>>(a);   // strict always takes the scalar reference-order kernel
-    else k_density_simple<false><<<nb, kThreads, 0, st>>>(a);
+    // strict always takes the scalar reference-order kernel
+#define SPHB_LAUNCH_DS(KT) if (a.strict) k_density_simple<true, KT><<<nb, kThreads, 0, st>>>(a); else k_density_simple<false, KT><<<nb, kThreads, 0, st>>>(a)
+    switch (a.kernel_type) {
+        case kKernelWendlandC2: SPHB_LAUNCH_DS(kKernelWendlandC2); break;
+        case kKernelGaussian: SPHB_LAUNCH_DS(kKernelGaussian); break;
+        default: SPHB_LAUNCH_DS(kKernelCubic); break;
+    }
+#undef SPHB_LAUNCH_DS
     return 1;
 }
 
@@ -184,8 +196,13 @@ int launch_force(const PairArgs& a, cudaStream_t st) {
     if (a.n == 0) return 0;
     if (a.variant == 2 && !a.strict) return launch_force_mask(a, st);
     const unsigned nb = (unsigned)((a.n + kThreads - 1) / kThreads);
-    if (a.strict) k_force_simple<true><<<nb, kThreads, 0, st>>>(a);
-    else k_force_simple<false><<<nb, kThreads, 0, st>>>(a);
+#define SPHB_LAUNCH_FS(KT) if (a.strict) k_force_simple<true, KT><<<nb, kThreads, 0, st>>>(a); else k_force_simple<false, KT><<<nb, kThreads, 0, st>>>(a)
+    switch (a.kernel_type) {
+        case kKernelWendlandC2: SPHB_LAUNCH_FS(kKernelWendlandC2); break;
+        case kKernelGaussian: SPHB_LAUNCH_FS(kKernelGaussian); break;
+        default: SPHB_LAUNCH_FS(kKernelCubic); break;
+    }
+#undef SPHB_LAUNCH_FS
     return 1;
 }
 

@@ -139,8 +139,8 @@ SPHB_UNROLL_N(SPHB_DMASK_GROUP_UNROLL)
         const float4 v = a.velid[i];
         const float A = pi.w / (2.0f * rho);
         // force-pass records in two arrays of 16-byte halves (the layout the staged kernels gather without bank conflicts)
-        a.fa[i] = make_float4(pi.x, pi.y, pi.z, A);
-        a.fb[i] = make_float4(v.x, v.y, v.z, A * P);
+        a.fa[kRecStride * i] = make_float4(pi.x, pi.y, pi.z, A);
+        a.fb[kRecStride * i] = make_float4(v.x, v.y, v.z, A * P);
         if (a.nbr_count) a.nbr_count[i] = count;
     }
     count = __reduce_max_sync(0xffffffffu, count);
@@ -159,9 +159,15 @@ __global__ void __launch_bounds__(kThreads, SPHB_FMASK_MINBLOCKS) k_force_mask16
     const uint32_t c = center_cell(a.grid, pi);
     const uint32_t* __restrict__ cs = a.cell_start;
     const float4* __restrict__ fa = pin(a.fa);
+#if SPHB_FORCE_REC32
+    auto load2 = [&](uint32_t j) -> ForceRec {
+        const float4* q = fa + 2u * j;
+        const float4 qa = __ldg(q), qb = __ldg(q + 1);
+#else
     const float4* __restrict__ fb = pin(a.fb);
     auto load2 = [&](uint32_t j) -> ForceRec {
         const float4 qa = __ldg(fa + j), qb = __ldg(fb + j);
+#endif
         ForceRec r;
         r.x = qa.x; r.y = qa.y; r.z = qa.z; r.A = qa.w; r.vx = qb.x; r.vy = qb.y; r.vz = qb.z; r.B = qb.w;
         return r;

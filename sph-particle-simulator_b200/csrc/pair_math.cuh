@@ -102,6 +102,66 @@ __device__ __forceinline__ float4 accel_strict(const PairConsts& k, const ForceA
     return a;
 }
 
+// ---- the other kernel classes behind create_kernel (reference src/kernels.cpp:166-236) -------------
+// The reference engine calls W / gradW / laplacianW through a Kernel pointer (sph_engine.cpp:209, 232, 236), so Wendland
+// C2 and the Gaussian drop into the same density / force sums.  STRICT: the classes' own operation order, every op a
+// round-to-nearest intrinsic — bit-identical for Wendland C2; the Gaussian calls expf, whose CUDA and glibc
+// implementations differ in the last bit, so it is held to a tolerance instead (tests/test_gpu_parity.py).
+// KT = kKernelCubic forwards to the functions above.
+template <int KT>
+__device__ __forceinline__ float w_strict_k(const PairConsts& k, float d2) {
+    if (KT == kKernelCubic) return w_strict(k, d2);
+    if (KT == kKernelGaussian)   // norm * exp(-r_sq * sigma_sq_inv)   (kernels.cpp:207-210)
+        return __fmul_rn(k.gnorm, expf(__fmul_rn(-d2, k.gssi)));
+    // Wendland C2 (kernels.cpp:171-177): q >= 2 -> 0; tmp = 1 - 0.5 q; norm * tmp * tmp * tmp * tmp * (2 q + 1)
+    const float q = __fdiv_rn(__fsqrt_rn(d2), k.h);
+    if (q >= 2.0f) return 0.0f;
+    const float tmp = __fsub_rn(1.0f, __fmul_rn(0.5f, q));
+    const float t4 = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(k.wnorm, tmp), tmp), tmp), tmp);
+    return __fmul_rn(t4, __fadd_rn(__fmul_rn(2.0f, q), 1.0f));
+}
+
+template <int KT>
+__device__ __forceinline__ void force_pair_strict_k(const PairConsts& k, ForceAccum& f, float rx, float ry, float rz, float d2,
+                                                    float ux, float uy, float uz, float P_i, float m_j, float rho_j) {
+    if (KT == kKernelCubic) { force_pair_strict(k, f, rx, ry, rz, d2, ux, uy, uz, P_i, m_j, rho_j); return; }
+    const float r_len = __fsqrt_rn(d2);
+    const float P_j = __fmul_rn(k.gas_constant, __fsub_rn(rho_j, k.rest_density));
+    float gx = 0.0f, gy = 0.0f, gz = 0.0f, lap = 0.0f;
+    if (KT == kKernelGaussian) {
+        const float e = expf(__fmul_rn(-d2, k.gssi));
+        // gradW = -2 s norm exp * r (kernels.cpp:212-216); laplacianW = 2 s norm exp (2 s r_sq - 3) (218-222)
+        const float s = __fmul_rn(__fmul_rn(__fmul_rn(-2.0f, k.gssi), k.gnorm), e);
+        gx = __fmul_rn(s, rx); gy = __fmul_rn(s, ry); gz = __fmul_rn(s, rz);
+        lap = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(2.0f, k.gssi), k.gnorm), e),
+                        __fsub_rn(__fmul_rn(__fmul_rn(2.0f, k.gssi), d2), 3.0f));
+    } else {
+        const float q = __fdiv_rn(r_len, k.h);
+        if (!(q >= 2.0f)) {
+            const float tmp = __fsub_rn(1.0f, __fmul_rn(0.5f, q));
+            if (!(r_len < 1e-6f)) {   // gradW (kernels.cpp:179-190): norm * (-5 tmp tmp tmp q) * (r / (r_len h))
+                const float dW_dq = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(-5.0f, tmp), tmp), tmp), q);
+                const float s = __fmul_rn(k.wnorm, dW_dq), d = __fmul_rn(r_len, k.h);
+                gx = __fmul_rn(s, __fdiv_rn(rx, d)); gy = __fmul_rn(s, __fdiv_rn(ry, d)); gz = __fmul_rn(s, __fdiv_rn(rz, d));
+            }
+            // laplacianW (kernels.cpp:192-198): norm * (5 / h_sq) * tmp * tmp * (5 q - 3)
+            lap = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(k.wnorm, __fdiv_rn(5.0f, k.h_sq)), tmp), tmp),
+                            __fsub_rn(__fmul_rn(5.0f, q), 3.0f));
+        }
+    }
+    if (!(r_len < 1e-6f)) {   // compute_pressure_force's own guard (sph_engine.cpp:403)
+        const float pressure_term = __fdiv_rn(__fadd_rn(P_i, P_j), __fmul_rn(2.0f, rho_j));
+        const float sc = __fmul_rn(m_j, pressure_term);
+        f.px = __fsub_rn(f.px, __fmul_rn(sc, gx));
+        f.py = __fsub_rn(f.py, __fmul_rn(sc, gy));
+        f.pz = __fsub_rn(f.pz, __fmul_rn(sc, gz));
+    }
+    const float sv = __fmul_rn(__fdiv_rn(m_j, rho_j), k.viscosity);
+    f.vx = __fadd_rn(f.vx, __fmul_rn(__fmul_rn(sv, ux), lap));
+    f.vy = __fadd_rn(f.vy, __fmul_rn(__fmul_rn(sv, uy), lap));
+    f.vz = __fadd_rn(f.vz, __fmul_rn(__fmul_rn(sv, uz), lap));
+}
+
 // ---- fast -----------------------------------------------------------------------------------------
 __device__ __forceinline__ float fast_sqrt(float x) {
     float y;
@@ -136,6 +196,42 @@ __device__ __forceinline__ void force_pair_fast(const PairConsts& k, ForceAccum&
     const float cp = (A_j * P_i + B_j) * (k.sig_h * gq * inv_len);
     f.px -= cp * rx; f.py -= cp * ry; f.pz -= cp * rz;
     const float cv = (2.0f * k.viscosity * k.sig_h2) * (A_j * lq);
+    f.vx += cv * ux; f.vy += cv * uy; f.vz += cv * uz;
+}
+
+// Wendland C2 / Gaussian in fast math (FMA contraction, MUFU sqrt / rsqrt / ex2): W without the normalisation constant
+// (the caller multiplies the sum once) and the pair force with the same folded inputs as force_pair_fast.
+template <int KT>
+__device__ __forceinline__ float w_fast_k(const PairConsts& k, float d2) {   // W / wnorm (Wendland), W / gnorm (Gaussian)
+    if (KT == kKernelGaussian) return __expf(-d2 * k.gssi);
+    const float q = fast_sqrt(d2) * k.inv_h;
+    const float tmp = fmaxf(1.0f - 0.5f * q, 0.0f);   // (1 - q/2)+: exactly 0 beyond the support
+    const float t2 = tmp * tmp;
+    return (t2 * t2) * (2.0f * q + 1.0f);
+}
+template <int KT>
+__device__ __forceinline__ float w_norm_k(const PairConsts& k) { return KT == kKernelGaussian ? k.gnorm : k.wnorm; }
+
+template <int KT>
+__device__ __forceinline__ void force_pair_fast_k(const PairConsts& k, ForceAccum& f, float rx, float ry, float rz, float d2,
+                                                  float ux, float uy, float uz, float P_i, float A_j, float B_j) {
+    const bool apart = d2 >= 1e-12f;                 // r_len >= 1e-6 (sph_engine.cpp:403)
+    float gf, lap;                                   // gradW = gf * r, laplacianW = lap
+    if (KT == kKernelGaussian) {
+        const float e = k.gnorm * __expf(-d2 * k.gssi);
+        gf = apart ? -2.0f * k.gssi * e : 0.0f;
+        lap = 2.0f * k.gssi * e * (2.0f * k.gssi * d2 - 3.0f);
+    } else {
+        const float inv_len = apart ? fast_rsqrt(d2) : 0.0f;
+        const float q = (d2 * inv_len) * k.inv_h;    // coincident: q = 0, like the reference's length 0
+        const float tmp = fmaxf(1.0f - 0.5f * q, 0.0f);
+        const float t2 = tmp * tmp;
+        gf = (k.wnorm * k.inv_h) * (-5.0f * t2 * tmp * q) * inv_len;
+        lap = (5.0f * k.wnorm * k.inv_h * k.inv_h) * t2 * (5.0f * q - 3.0f);
+    }
+    const float cp = (A_j * P_i + B_j) * gf;
+    f.px -= cp * rx; f.py -= cp * ry; f.pz -= cp * rz;
+    const float cv = (2.0f * k.viscosity) * (A_j * lap);
     f.vx += cv * ux; f.vy += cv * uy; f.vz += cv * uz;
 }
 

@@ -61,7 +61,13 @@ struct PairConsts {
     float sig_h2;       // sigma / h_sq
     float neg_zero;     // -0.0f, deliberately a RUN-TIME value: exact packed squares are formed as fma(d, d, -0) (pair_mask.cu)
     float r2_next;      // nextafterf(r2, +inf): d2 <= r2 <=> d2 - r2_next < 0 (sign-bit radius test of pair_mask.cu)
+    // the other kernel classes behind create_kernel (SPHB_OPT_KERNEL_TYPE; tested-walk kernels of pair.cu only)
+    float wnorm;        // WendlandC2Kernel::norm_factor_ = 21 / (2 pi h h h)   (kernels.cpp:168)
+    float gssi;         // GaussianKernel::sigma_sq_inv_ = 1 / (h h)            (kernels.cpp:203)
+    float gnorm;        // GaussianKernel::norm_ = 1 / pow(pi h h, 1.5)         (kernels.cpp:204)
 };
+// Kernel::W and friends (reference src/kernels.h:94-98 KernelType order)
+constexpr int kKernelCubic = 0, kKernelWendlandC2 = 1, kKernelGaussian = 2;
 
 struct IntegrateConsts {
     float damping;
@@ -123,6 +129,14 @@ struct __align__(32) ForceRec {
     float vx, vy, vz, B;
 };
 
+// Force-pass records of the 16-bit mask kernels: SPHB_FORCE_REC32 = 1 keeps the two 16-byte halves of a particle next to
+// each other (fb = fa + 1, stride 2): one address computation per neighbour and both loads in one 32-byte sector;
+// 0 = two separate arrays.
+#ifndef SPHB_FORCE_REC32
+#define SPHB_FORCE_REC32 0
+#endif
+constexpr int kRecStride = SPHB_FORCE_REC32 ? 2 : 1;
+
 struct PairArgs {
     size_t n;
     const float4* posm;        // x, y, z, mass   (cell-sorted)
@@ -146,6 +160,7 @@ struct PairArgs {
     int walk_radius;
     int strict;
     int variant;
+    int kernel_type;           // kKernelCubic / kKernelWendlandC2 / kKernelGaussian (the latter two: tested-walk kernels only)
     int mode;                  // variant 2, R >= 4: 0 = pair_mask.cu, 1 = pair_stage.cu, 2 = staged density + per-lane force (SPHB_OPT_PAIR_MODE)
     // slab mode (slab_axis >= 0): density is evaluated for particles whose reference cell on the axis lies in
     // [rho_lo, rho_hi) (owned + one halo layer); force only for owned particles (id word bit 31 clear)

@@ -250,22 +250,47 @@ static sphb_params to_abi(const SPHParameters& p) {
 }
 
 void SPHEngine::die(const char* what) const {
-    throw std::runtime_error(std::string(what) + ": " + sphb_last_error(ctx_));
+    throw std::runtime_error(std::string(what) + ": " + (multi_ ? sphb_multi_last_error(multi_) : sphb_last_error(ctx_)));
 }
 
 #define SPHB_CHECK(call) do { if ((call) != SPHB_OK) die(#call); } while (0)
+// one device: sphb_<fn>(ctx_, ...); several (SPHB_DEVICES=0,1,...): sphb_multi_<fn>(multi_, ...) — same contracts (include/sphb.h)
+#define DEV(fn, ...) (multi_ ? sphb_multi_##fn(multi_, ##__VA_ARGS__) : sphb_##fn(ctx_, ##__VA_ARGS__))
 
 // reference sph_engine.cpp:13-18.  The device context is created here; without a usable CUDA device
 // construction throws — there is no CPU fallback.
 SPHEngine::SPHEngine(size_t max_particles) : particles_(max_particles) {
     int device = 0;
     if (const char* env = std::getenv("SPHB_DEVICE")) device = std::atoi(env);
-    if (sphb_create(&ctx_, max_particles, device) != SPHB_OK)
-        throw std::runtime_error(std::string("SPHEngine: ") + sphb_last_error(nullptr));
-    sphb_set_option(ctx_, SPHB_OPT_STAGE_TIMING, 1);   // PerformanceStats stage times come from CUDA events
+    // SPHB_DEVICES=0,1,2,3: this engine owns several GPUs (slab decomposition behind the C ABI, sphb_create_multi)
+    std::vector<int> devices;
+    if (const char* env = std::getenv("SPHB_DEVICES")) {
+        for (const char* q = env; *q;) {
+            char* end = nullptr;
+            const long v = std::strtol(q, &end, 10);
+            if (end == q) break;
+            devices.push_back((int)v);
+            if (*end != ',') break;
+            q = end + 1;
+        }
+    }
+    if (devices.size() > 1) {
+        if (sphb_create_multi(&multi_, max_particles, (int)devices.size(), devices.data()) != SPHB_OK)
+            throw std::runtime_error(std::string("SPHEngine: ") + sphb_multi_last_error(nullptr));
+    } else {
+        if (devices.size() == 1) device = devices[0];
+        if (sphb_create(&ctx_, max_particles, device) != SPHB_OK)
+            throw std::runtime_error(std::string("SPHEngine: ") + sphb_last_error(nullptr));
+    }
+    DEV(set_option, SPHB_OPT_STAGE_TIMING, 1);   // PerformanceStats stage times come from CUDA events
 }
 
-SPHEngine::~SPHEngine() { sphb_destroy(ctx_); }
+SPHEngine::~SPHEngine() {
+    if (multi_) sphb_destroy_multi(multi_);
+    else sphb_destroy(ctx_);
+}
+
+int SPHEngine::device_count() const { return multi_ ? sphb_multi_device_count(multi_) : 1; }
 
 // reference sph_engine.cpp:20-33.  params are taken verbatim: the cell size follows
 // neighbor_search_radius, NOT 2h (quirk Q1).
@@ -282,7 +307,7 @@ void SPHEngine::tune_grid(float spacing) {
     int refine = (int)(r + 0.5f);
     if (refine < 1) refine = 1;
     if (refine > 6) refine = 6;
-    sphb_set_option(ctx_, SPHB_OPT_GRID_REFINE, refine);
+    DEV(set_option, SPHB_OPT_GRID_REFINE, refine);
 }
 
 void SPHEngine::initialize_dam_break() {
@@ -324,18 +349,18 @@ void SPHEngine::clear_particles() {
     device_ahead_ = false;
     host_changed_ = true;
     step_count_ = 0;
-    SPHB_CHECK(sphb_set_time(ctx_, 0.0f, 0));
+    SPHB_CHECK(DEV(set_time, 0.0f, 0));
 }
 
 void SPHEngine::push_params() const {
     const sphb_params q = to_abi(params_);
-    SPHB_CHECK(sphb_set_params(ctx_, &q));
+    SPHB_CHECK(DEV(set_params, &q));
 }
 
 void SPHEngine::push_to_device() const {
     if (!host_changed_) return;
     push_params();   // default-mass fallback of the ABI is not used: every record carries its mass
-    SPHB_CHECK(sphb_upload_strided(ctx_, particles_.size(), particles_.data(), sizeof(Particle), offsetof(Particle, position),
+    SPHB_CHECK(DEV(upload_strided, particles_.size(), particles_.data(), sizeof(Particle), offsetof(Particle, position),
                                    offsetof(Particle, velocity), offsetof(Particle, mass)));
     host_changed_ = false;
     device_ahead_ = false;
@@ -344,7 +369,7 @@ void SPHEngine::push_to_device() const {
 
 void SPHEngine::pull_from_device() const {
     if (!device_ahead_) return;
-    SPHB_CHECK(sphb_download_strided(ctx_, particles_.data(), sizeof(Particle), offsetof(Particle, position),
+    SPHB_CHECK(DEV(download_strided, particles_.data(), sizeof(Particle), offsetof(Particle, position),
                                      offsetof(Particle, velocity), offsetof(Particle, density), offsetof(Particle, pressure)));
     device_ahead_ = false;
 }
@@ -354,11 +379,11 @@ void SPHEngine::step(float dt) {
     if (!initialized_ || particles_.size() == 0) return;
     push_to_device();
     push_params();
-    SPHB_CHECK(sphb_step(ctx_, dt));
+    SPHB_CHECK(DEV(step, dt));
     // The reference's step() returns when the step is done and its callers time it with wall clocks
     // (benchmarks/performance_test.cpp:118-126), so the shell synchronises by default; set_async(true) keeps the
     // C ABI's enqueue-and-return behaviour.
-    if (!async_) SPHB_CHECK(sphb_synchronize(ctx_));
+    if (!async_) SPHB_CHECK(DEV(synchronize));
     device_ahead_ = true;
     ++step_count_;
 }
@@ -377,7 +402,7 @@ const ParticleSystem& SPHEngine::get_particles() const {
 
 float SPHEngine::get_current_time() const {
     float t = 0.0f;
-    SPHB_CHECK(sphb_get_time(ctx_, &t, nullptr));
+    SPHB_CHECK(DEV(get_time, &t, nullptr));
     return t;
 }
 
@@ -400,7 +425,7 @@ void SPHEngine::set_boundaries(float xmin, float xmax, float ymin, float ymax, f
 
 const SPHEngine::PerformanceStats& SPHEngine::get_performance_stats() const {
     sphb_stats s;
-    SPHB_CHECK(sphb_get_stats(ctx_, &s));
+    SPHB_CHECK(DEV(get_stats, &s));
     perf_.total_time = s.total_time;
     perf_.neighbor_search_time = s.neighbor_search_time;
     perf_.density_computation_time = s.density_computation_time;
@@ -412,7 +437,7 @@ const SPHEngine::PerformanceStats& SPHEngine::get_performance_stats() const {
 }
 
 void SPHEngine::reset_performance_stats() {
-    SPHB_CHECK(sphb_reset_stats(ctx_));
+    SPHB_CHECK(DEV(reset_stats));
     perf_ = PerformanceStats{};
 }
 
@@ -422,7 +447,7 @@ void SPHEngine::reset_performance_stats() {
 float SPHEngine::get_total_mass() const {
     if (host_changed_) push_to_device();
     double sum_rho = 0.0;
-    SPHB_CHECK(sphb_diagnostics(ctx_, &sum_rho, nullptr, nullptr));
+    SPHB_CHECK(DEV(diagnostics, &sum_rho, nullptr, nullptr));
     const float h = params_.smoothing_length;
     return static_cast<float>(sum_rho) * (h * h * h);
 }
@@ -431,13 +456,28 @@ float SPHEngine::get_total_mass() const {
 float SPHEngine::get_total_energy() const {
     if (host_changed_) push_to_device();
     double ke = 0.0;
-    SPHB_CHECK(sphb_diagnostics(ctx_, nullptr, &ke, nullptr));
+    SPHB_CHECK(DEV(diagnostics, nullptr, &ke, nullptr));
     return static_cast<float>(ke);
 }
 
 void SPHEngine::export_instance_data(float* dst, bool dst_on_device) const {
     if (!initialized_ || particles_.size() == 0) return;
     if (host_changed_) push_to_device();
+    if (multi_) {   // several devices: the records are assembled on the host from the gathered positions and velocities
+        if (dst_on_device) throw std::runtime_error("export_instance_data: a device destination needs a single-device engine");
+        const size_t n = particles_.size();
+        std::vector<float> p(3 * n), v(3 * n);
+        SPHB_CHECK(sphb_multi_download(multi_, p.data(), v.data(), nullptr, nullptr, nullptr));
+        size_t i = 0;
+        for (const Particle& q : particles_) {
+            float* r = dst + 9 * i;
+            r[0] = p[3 * i]; r[1] = p[3 * i + 1]; r[2] = p[3 * i + 2];
+            r[3] = v[3 * i]; r[4] = v[3 * i + 1]; r[5] = v[3 * i + 2];
+            r[6] = q.color.r; r[7] = q.color.g; r[8] = q.color.b;
+            ++i;
+        }
+        return;
+    }
     if (!colors_on_device_) {   // Particle::color is host-side state the physics never touches: uploaded once per particle set
         std::vector<float> rgb(particles_.size() * 3);
         size_t k = 0;
@@ -460,7 +500,7 @@ SPHEngine::ReportDiagnostics SPHEngine::get_report_diagnostics() const {
     if (host_changed_) push_to_device();
     double sum_rho = 0.0, ke = 0.0;
     float vmax = 0.0f;
-    SPHB_CHECK(sphb_diagnostics(ctx_, &sum_rho, &ke, &vmax));
+    SPHB_CHECK(DEV(diagnostics, &sum_rho, &ke, &vmax));
     const float h = params_.smoothing_length;
     d.total_mass = static_cast<float>(sum_rho) * (h * h * h);
     const float initial = particles_.size() * params_.particle_mass;
@@ -489,14 +529,14 @@ void SPHEngine::compute_conservation_errors(double& mass_error, double& energy_e
 std::vector<glm::vec3> SPHEngine::get_positions() const {
     if (!device_ahead_) return particles_.get_positions();
     std::vector<glm::vec3> out(particles_.size());
-    SPHB_CHECK(sphb_download(ctx_, reinterpret_cast<float*>(out.data()), nullptr, nullptr, nullptr, nullptr));
+    SPHB_CHECK(DEV(download, reinterpret_cast<float*>(out.data()), nullptr, nullptr, nullptr, nullptr));
     return out;
 }
 
 std::vector<glm::vec3> SPHEngine::get_velocities() const {
     if (!device_ahead_) return particles_.get_velocities();
     std::vector<glm::vec3> out(particles_.size());
-    SPHB_CHECK(sphb_download(ctx_, nullptr, reinterpret_cast<float*>(out.data()), nullptr, nullptr, nullptr));
+    SPHB_CHECK(DEV(download, nullptr, reinterpret_cast<float*>(out.data()), nullptr, nullptr, nullptr));
     return out;
 }
 
@@ -504,21 +544,21 @@ std::vector<glm::vec3> SPHEngine::get_velocities() const {
 std::vector<float> SPHEngine::get_densities() const {
     std::vector<float> out(initialized_ ? particles_.capacity() : 0, 0.0f);
     if (!out.empty() && step_count_ > 0 && !host_changed_ && particles_.size() > 0)
-        SPHB_CHECK(sphb_download(ctx_, nullptr, nullptr, out.data(), nullptr, nullptr));
+        SPHB_CHECK(DEV(download, nullptr, nullptr, out.data(), nullptr, nullptr));
     return out;
 }
 
 std::vector<float> SPHEngine::get_pressures() const {
     std::vector<float> out(initialized_ ? particles_.capacity() : 0, 0.0f);
     if (!out.empty() && step_count_ > 0 && !host_changed_ && particles_.size() > 0)
-        SPHB_CHECK(sphb_download(ctx_, nullptr, nullptr, nullptr, out.data(), nullptr));
+        SPHB_CHECK(DEV(download, nullptr, nullptr, nullptr, out.data(), nullptr));
     return out;
 }
 
 std::vector<glm::vec3> SPHEngine::get_accelerations() const {
     std::vector<glm::vec3> out(particles_.size());
     if (!host_changed_ && !out.empty())
-        SPHB_CHECK(sphb_download(ctx_, nullptr, nullptr, nullptr, nullptr, reinterpret_cast<float*>(out.data())));
+        SPHB_CHECK(DEV(download, nullptr, nullptr, nullptr, nullptr, reinterpret_cast<float*>(out.data())));
     return out;
 }
 
@@ -526,7 +566,7 @@ float SPHEngine::compute_cfl_timestep() const {
     if (host_changed_) push_to_device();
     push_params();
     float dt = 0.0f;
-    SPHB_CHECK(sphb_cfl_timestep(ctx_, &dt));
+    SPHB_CHECK(DEV(cfl_timestep, &dt));
     return dt;
 }
 
@@ -540,9 +580,13 @@ void SPHEngine::validate_simulation() const {
         std::cerr << "Warning: Average neighbor count (" << avg << ") may affect simulation stability\n";
 }
 
+void SPHEngine::set_kernel_type(int type) {
+    SPHB_CHECK(DEV(set_option, SPHB_OPT_KERNEL_TYPE, type));
+}
+
 void SPHEngine::set_math_mode(int mode) {
     math_mode_ = mode;
-    SPHB_CHECK(sphb_set_option(ctx_, SPHB_OPT_MATH_MODE, mode));
+    SPHB_CHECK(DEV(set_option, SPHB_OPT_MATH_MODE, mode));
 }
 
 }  // namespace sph

@@ -16,6 +16,7 @@
 #include <vector>
 
 struct sphb_ctx;
+struct sphb_multi;
 
 namespace sph {
 
@@ -173,6 +174,9 @@ public:
     // ---- additions (not in the reference) --------------------------------------------------------
     // 0 = bit-exact reference arithmetic, 1 = fast (default); see include/sphb.h SPHB_OPT_MATH_MODE
     void set_math_mode(int mode);
+    // the smoothing kernel, reference KernelType order (kernels.h:94-98): 0 cubic spline (what the reference engine
+    // hard-wires), 1 Wendland C2, 2 Gaussian — the other classes behind create_kernel; see SPHB_OPT_KERNEL_TYPE
+    void set_kernel_type(int type);
     // accelerations of the last step in insertion order (the reference keeps them private)
     std::vector<glm::vec3> get_accelerations() const;
     // the CFL timestep the next adaptive step would take (reference: private compute_cfl_timestep)
@@ -195,7 +199,9 @@ public:
     // memory (a CUDA-mapped vertex buffer); otherwise host memory of size() * 9 floats.
     void export_instance_data(float* dst, bool dst_on_device = false) const;
     std::vector<float> get_instance_data() const;
-    sphb_ctx* native_handle() const { return ctx_; }
+    sphb_ctx* native_handle() const { return ctx_; }          // NULL when the engine owns several devices
+    sphb_multi* native_multi_handle() const { return multi_; }
+    int device_count() const;
 
 private:
     void push_to_device() const;     // host AoS → device, if the host side changed
@@ -206,7 +212,8 @@ private:
 
     mutable ParticleSystem particles_;
     SPHParameters params_;
-    sphb_ctx* ctx_ = nullptr;
+    sphb_ctx* ctx_ = nullptr;       // one device (default)
+    sphb_multi* multi_ = nullptr;   // several devices (environment SPHB_DEVICES=0,1,...)
     size_t step_count_ = 0;
     bool initialized_ = false;
     mutable bool host_changed_ = true;   // device does not hold the host particles yet

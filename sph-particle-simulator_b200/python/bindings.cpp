@@ -145,9 +145,12 @@ PYBIND11_MODULE(sph, m) {
         .def("get_pressures", [](const SPHEngine& e) { return float_array(e.get_pressures()); })
         // additions
         .def("set_math_mode", &SPHEngine::set_math_mode, py::arg("mode"))
+        .def("set_kernel_type", &SPHEngine::set_kernel_type, py::arg("type"),
+             "0 cubic spline (default), 1 Wendland C2, 2 Gaussian (reference KernelType order)")
         .def("set_async", &SPHEngine::set_async, py::arg("on"))
         .def("get_accelerations", [](const SPHEngine& e) { return vec3_array(e.get_accelerations()); })
         .def("compute_cfl_timestep", &SPHEngine::compute_cfl_timestep)
+        .def("device_count", &SPHEngine::device_count, "GPUs this engine owns (environment SPHB_DEVICES=0,1,... at construction; default 1)")
         .def("get_instance_data",
              [](const SPHEngine& e) {
                  const std::vector<float> v = e.get_instance_data();

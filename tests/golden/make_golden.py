@@ -35,11 +35,14 @@ def sha(a: np.ndarray) -> str:
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-def run_scene(params, pos, vel, mass, dts, capacity=None, keep_steps=None):
-    """Step the reference; returns per-step dicts (state after the step + keys/counts of that step)."""
+def run_scene(params, pos, vel, mass, dts, capacity=None, keep_steps=None, kernel_type=0):
+    """Step the reference; returns per-step dicts (state after the step + keys/counts of that step).
+    kernel_type != 0: the reference's Wendland C2 (1) / Gaussian (2) class installed in the engine's kernel slot."""
     n = pos.shape[0]
     e = po.Engine(KIND, capacity or n)
     e.initialize(params)
+    if kernel_type:
+        e.set_kernel(kernel_type)
     e.add_particles(pos, vel, mass)
     out = []
     for k, dt in enumerate(dts):
@@ -241,5 +244,26 @@ def main():
     print("scalars.json written")
 
 
+def kernel_goldens():
+    """Section 6: the unmodified reference engine stepping through its OTHER kernel classes
+    (create_kernel: Wendland C2, Gaussian — kernels.cpp:166-236), on the inputs of two committed fixtures: the jittered
+    cloud (per-particle masses, velocities) and the 13 k dam break (lattice + walls).  Run alone:
+        python tests/golden/make_golden.py kernels"""
+    if not po.available(KIND):
+        raise SystemExit("oracle/_ref/liboracle_strict.so missing: make -f oracle/Makefile ref")
+    for kt, tag in ((1, "wendland"), (2, "gaussian")):
+        for src, steps, keep in (("cloud600", 3, {0, 2}), ("dam_break_13k_tame", 2, {1})):
+            with np.load(HERE / f"{src}.npz") as z:
+                prm = {k: np.float32(v) for k, v in zip(po.PARAM_NAMES, z["params"])}
+                pos, vel, mass, dt = z["pos"], z["vel"], z["mass"], float(z["dts"][0])
+            short = src.replace("_tame", "")
+            save(f"{short}_{tag}", prm, pos, vel, mass, [dt] * steps, kernel_type=np.int32(kt),
+                 **run_scene(prm, pos, vel, mass, [dt] * steps, keep_steps=keep, kernel_type=kt))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "kernels":
+        kernel_goldens()
+    else:
+        main()
+        kernel_goldens()

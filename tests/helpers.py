@@ -20,6 +20,10 @@ STEP_FIXTURES = (
 )
 
 
+# the reference engine stepping through its other kernel classes (tests/golden/make_golden.py section 6); "kernel_type" inside
+KERNEL_FIXTURES = ("cloud600_wendland", "cloud600_gaussian", "dam_break_13k_wendland", "dam_break_13k_gaussian")
+
+
 def load_golden(name: str) -> dict:
     with np.load(GOLDEN / f"{name}.npz") as z:
         return {k: z[k] for k in z.files}

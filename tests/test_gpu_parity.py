@@ -11,7 +11,7 @@ import json
 import numpy as np
 import pytest
 
-from helpers import GOLDEN, STEP_FIXTURES, assert_bits, golden_steps, load_golden, params_from, rel_err, stable_perm
+from helpers import GOLDEN, KERNEL_FIXTURES, STEP_FIXTURES, assert_bits, golden_steps, load_golden, params_from, rel_err, stable_perm
 
 pytestmark = pytest.mark.gpu
 
@@ -86,6 +86,75 @@ def test_fast_mode_single_step_tolerance(pkg, name, variant):
     want = {f: g[f"s{k0}_{f}"] for f in ("rho", "P", "acc", "pos", "vel")}
     L = float(max(prm["xmax"] - prm["xmin"], prm["ymax"] - prm["ymin"], prm["zmax"] - prm["zmin"]))
     check_fast(got, want, L, name)
+    ctx.close()
+
+
+@pytest.mark.parametrize("strict", [True, False])
+@pytest.mark.parametrize("name", KERNEL_FIXTURES)
+def test_other_kernel_classes_vs_reference_golden(pkg, name, strict):
+    """Wendland C2 / Gaussian (reference kernels.cpp:166-236) as template parameters of the tested-walk
+    pair kernels (SPHB_OPT_KERNEL_TYPE), against golden vectors of the UNMODIFIED reference engine stepping with those
+    classes in its kernel slot.  Keys, permutation and neighbour counts: bit-exact.  Strict Wendland C2: every field
+    bit-exact.  Strict Gaussian: the classes call expf, whose glibc and CUDA implementations differ in the last bit —
+    held to 2e-6 relative.  Fast mode: the fast-mode gates."""
+    g = load_golden(name)
+    kt = int(g["kernel_type"])
+    prm = params_from(g["params"])
+    n = g["pos"].shape[0]
+    ctx = make_ctx(pkg, n, prm, strict=strict, OPT_KERNEL_TYPE=kt)
+    assert ctx.get_option(pkg.capi.OPT_KERNEL_TYPE) == kt
+    ctx.upload(g["pos"], g["vel"], g["mass"])
+    keep = golden_steps(g)
+    L = float(max(prm["xmax"] - prm["xmin"], prm["ymax"] - prm["ymin"], prm["zmax"] - prm["zmin"]))
+    for k, dt in enumerate(g["dts"]):
+        ctx.step(float(dt))
+        if k not in keep:
+            continue
+        d = ctx.debug_dump()
+        s = ctx.download()
+        want = {f: g[f"s{k}_{f}"] for f in ("rho", "P", "acc", "pos", "vel")}
+        exact = strict and kt == pkg.capi.KERNEL_WENDLAND_C2
+        if exact or k == 0:
+            assert_bits(d["keys"], g[f"s{k}_keys"], f"{name} step {k} keys")
+            assert_bits(d["perm"], stable_perm(g[f"s{k}_keys"]), f"{name} step {k} sorted permutation")
+            assert_bits(d["nbr_count"], g[f"s{k}_counts"], f"{name} step {k} neighbour counts")
+        if exact:
+            for f in want:
+                assert_bits(s[f], want[f], f"{name} step {k} {f}")
+            assert np.float32(ctx.get_time()[0]) == g[f"s{k}_time"]
+        elif strict:
+            assert rel_err(s["rho"], want["rho"]) <= 2e-6 * (k + 1), f"{name} step {k} rho {rel_err(s['rho'], want['rho'])}"
+            assert rel_err(s["acc"], want["acc"]) <= 2e-5 * (k + 1), f"{name} step {k} acc {rel_err(s['acc'], want['acc'])}"
+            assert np.abs(s["pos"].astype(np.float64) - want["pos"]).max() <= 1e-7 * L
+        else:
+            scale = 1 if k == 0 else 10          # SURVEY §8c: N steps 10x looser
+            assert rel_err(s["rho"], want["rho"]) <= scale * TOL_RHO, f"{name} step {k} rho {rel_err(s['rho'], want['rho'])}"
+            assert np.abs(s["acc"].astype(np.float64) - want["acc"]).max() <= scale * TOL_ACC * np.abs(want["acc"]).max(), f"{name} step {k} acc"
+            assert np.abs(s["pos"].astype(np.float64) - want["pos"]).max() <= scale * TOL_POS * L
+    ctx.close()
+
+
+def test_kernel_type_option_guards(pkg):
+    """Unknown kernel types are refused; the cubic spline stays the default and the bitmask kernels stay its path."""
+    from sph_b200 import scenes
+    pos, mass, prm, dt = scenes.dam_break_scene(0.025)
+    ctx = make_ctx(pkg, len(pos), prm, strict=False)
+    assert ctx.get_option(pkg.capi.OPT_KERNEL_TYPE) == pkg.capi.KERNEL_CUBIC_SPLINE
+    with pytest.raises(pkg.SphbError):
+        ctx.set_option(pkg.capi.OPT_KERNEL_TYPE, 3)
+    ctx.upload(pos, None, mass)
+    ctx.step(dt)
+    cubic = ctx.download()
+    ctx.set_option(pkg.capi.OPT_KERNEL_TYPE, pkg.capi.KERNEL_WENDLAND_C2)
+    ctx.upload(pos, None, mass)
+    ctx.step(dt)
+    wend = ctx.download()
+    # Wendland C2 carries 21/2 : 2/3 of the cubic spline's (2/3-normalised) weight at the origin: densities must differ
+    assert rel_err(wend["rho"], cubic["rho"]) > 0.1
+    ctx.set_option(pkg.capi.OPT_KERNEL_TYPE, pkg.capi.KERNEL_CUBIC_SPLINE)
+    ctx.upload(pos, None, mass)
+    ctx.step(dt)
+    assert_bits(ctx.download()["rho"], cubic["rho"], "back to the cubic spline")
     ctx.close()
 
 

@@ -119,15 +119,23 @@ def test_simulator_default_dam_break_vs_oracle(sph, po):
 
 
 @pytest.mark.gpu
-def test_simulator_public_api_scene_and_quirks(sph, po):
+@pytest.mark.parametrize("devices", [None, "0,0", "0,0,0"])
+def test_simulator_public_api_scene_and_quirks(sph, po, devices, monkeypatch):
     """Scene built through the public API (create_boundary_box + create_fluid_block + add_particles,
-    set_smoothing_length, set_boundaries), adaptive stepping, capacity truncation, re-initialisation."""
+    set_smoothing_length, set_boundaries), adaptive stepping, capacity truncation, re-initialisation.
+    devices: the same engine owning several slabs (SPHB_DEVICES → sphb_create_multi behind the host shell; ordinal 0
+    repeated so that a one-GPU box runs it) must give the same bits."""
+    if devices:
+        monkeypatch.setenv("SPHB_DEVICES", devices)
+    else:
+        monkeypatch.delenv("SPHB_DEVICES", raising=False)
     dx = 0.02
     m = 1.5 * 1000 * dx ** 3
     prm = sph.SPHParameters()
     prm.gas_constant = 100.0 * m / 1000.0; prm.viscosity = 1e-3 * m; prm.particle_mass = m; prm.damping = 0.999
     prm.timestep = 0.25 * 2 * dx / 10.0
     sim = sph.Simulator(max_particles=13000)                         # 13 200 generated → 200 dropped (Q14)
+    assert sim.device_count() == (len(devices.split(",")) if devices else 1)
     sim.set_math_mode(0)
     sim.initialize(prm)
     c, s = np.array([0, 0.3, 0], np.float32), np.array([0.4, 0.6, 0.8], np.float32)

@@ -1,0 +1,195 @@
+"""GPU: ONE engine over several devices behind the C ABI (sphb_create_multi, csrc/multi.cu) against the
+single-context run — bit for bit in strict mode and, with the same cell-order major axis, in fast mode.
+
+On a one-GPU box the device list names ordinal 0 several times (several slabs on one GPU: the same code path,
+device copies instead of peer copies); with >= 2 GPUs the real peer-to-peer path runs as well.  The reference
+has no multi-device path: the arbiter is the single-context run, itself pinned to the oracle in
+tests/test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+from helpers import assert_bits, load_golden, params_from
+
+pytestmark = pytest.mark.gpu
+
+
+def device_lists():
+    import torch
+    n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    lists = [[0, 0], [0, 0, 0]]
+    if n >= 2:
+        lists.append([0, 1])
+    if n >= 4:
+        lists.append([0, 1, 2, 3])
+    return lists
+
+
+def single_run(pkg, params, pos, vel, mass, dt, steps, strict, layout_major):
+    capi = pkg.capi
+    ctx = pkg.Context(len(pos), 0)
+    ctx.set_option(capi.OPT_MATH_MODE, capi.MATH_STRICT if strict else capi.MATH_FAST)
+    ctx.set_option(capi.OPT_LAYOUT_MAJOR, layout_major)
+    ctx.set_params(params)
+    ctx.upload(pos, vel, mass)
+    dts = []
+    for _ in range(steps):
+        t0 = ctx.get_time()[0]
+        ctx.step(dt)
+        dts.append(np.float32(ctx.get_time()[0]) - np.float32(t0))
+    out = ctx.download()
+    out["time"] = ctx.get_time()
+    out["diag"] = ctx.diagnostics()
+    out["max_neighbors"] = ctx.stats()["max_neighbors"]
+    ctx.close()
+    return out
+
+
+def multi_run(pkg, devices, params, pos, vel, mass, dt, steps, strict, axis=-1):
+    capi = pkg.capi
+    m = pkg.MultiContext(len(pos), devices)
+    m.set_option(capi.OPT_MATH_MODE, capi.MATH_STRICT if strict else capi.MATH_FAST)
+    m.set_option(capi.OPT_MULTI_AXIS, axis)
+    m.set_params(params)
+    m.upload(pos, vel, mass)
+    for _ in range(steps):
+        m.step(dt)
+    out = m.download()
+    out["time"] = m.get_time()
+    out["diag"] = m.diagnostics()
+    out["layout"] = m.layout()
+    out["max_neighbors"] = m.stats()["max_neighbors"]
+    assert m.size == len(pos)
+    m.close()
+    return out
+
+
+@pytest.mark.parametrize("strict", [True, False])
+def test_multi_equals_single_dam_break(pkg, strict):
+    from sph_b200 import scenes
+    pos, mass, params, dt = scenes.dam_break_scene(0.02)
+    for devs in device_lists():
+        got = multi_run(pkg, devs, params, pos, None, mass, dt, 6, strict)
+        axis = got["layout"]["axis"]
+        assert axis == 2                                   # the dam is longest along z (0.8)
+        want = single_run(pkg, params, pos, None, mass, dt, 6, strict, axis)
+        for f in ("pos", "vel", "rho", "P", "acc"):
+            assert_bits(got[f], want[f], f"devices={devs} strict={strict} {f}")
+        assert got["time"] == want["time"]
+        assert got["max_neighbors"] == want["max_neighbors"]
+        lay = got["layout"]
+        assert int(lay["owned"].sum()) == len(pos) and (lay["ghosts"] > 0).all()
+        # fp64 sums over different partitions: equal to rounding
+        np.testing.assert_allclose(got["diag"][0], want["diag"][0], rtol=1e-12)
+        np.testing.assert_allclose(got["diag"][1], want["diag"][1], rtol=1e-12)
+        assert got["diag"][2] == want["diag"][2]
+
+
+def test_multi_migration_and_explicit_axis(pkg):
+    """Particles streaming along the slab axis (several cells per step, bouncing off the walls), slabs along x."""
+    g = load_golden("cloud600")
+    params = {k: float(v) for k, v in params_from(g["params"]).items()}
+    vel = g["vel"].copy()
+    vel[:, 0] = np.where(np.arange(600) % 2 == 0, 45.0, -45.0).astype(np.float32)
+    want = single_run(pkg, params, g["pos"], vel, g["mass"], 1e-3, 12, True, 0)
+    for devs in [d for d in device_lists() if len(d) == 2]:   # the cloud spans 5 cells: two slabs of >= 2 cells
+        got = multi_run(pkg, devs, params, g["pos"], vel, g["mass"], 1e-3, 12, True, axis=0)
+        assert got["layout"]["axis"] == 0
+        for f in ("pos", "vel", "rho", "P", "acc"):
+            assert_bits(got[f], want[f], f"devices={devs} {f}")
+
+
+@pytest.mark.parametrize("name", ["fast_cloud", "light_zero_mixed"])
+def test_multi_adaptive_timestep(pkg, po, name):
+    """dt <= 0: the CFL rule (compute_cfl_timestep, reference sph_engine.cpp:312-333) from the maxima over all devices
+    and the acceleration of particle 0 from the device that advanced it.  On the CFL-limited golden cases of the
+    unmodified reference (both branches: dt_cfl, dt_force) every dt, every time and the final state are the
+    reference's bits; the query announces the dt the next step takes."""
+    import hashlib, json
+    from helpers import GOLDEN, cfl_case_inputs
+    from sph_b200 import scenes
+    case = json.loads((GOLDEN / "scalars.json").read_text())["cfl_cases"][name]
+    prm, pos, vel, mass, n = cfl_case_inputs(po, scenes, name, case)
+    prm = {k: float(v) for k, v in prm.items()}
+    capi = pkg.capi
+    for devs in device_lists():
+        m = pkg.MultiContext(n, devs)
+        m.set_option(capi.OPT_MATH_MODE, capi.MATH_STRICT)
+        m.set_params(prm)
+        m.upload(pos, vel, mass)
+        for k, (want_dt, want_t) in enumerate(zip(case["dts"], case["times"])):
+            assert np.float32(m.cfl_timestep()) == np.float32(want_dt), f"{name} {devs} step {k} ({case['branch'][k]} branch)"
+            m.step(0.0)
+            assert np.float32(m.get_time()[0]) == np.float32(want_t)
+        got = m.download()
+        m.close()
+        for f in ("pos", "vel", "rho"):
+            assert hashlib.sha256(np.ascontiguousarray(got[f]).tobytes()).hexdigest() == case[f"final_{f}_sha256"], f"{name} {devs} final {f}"
+
+
+def test_multi_strided_records_and_errors(pkg):
+    """The 76-byte Particle records of the host shell go in and come back through the strided calls; call-order and
+    capacity errors are reported, not thrown."""
+    from sph_b200 import scenes
+    capi = pkg.capi
+    pos, mass, params, dt = scenes.dam_break_scene(0.025)
+    n = len(pos)
+    rec = np.zeros((n, 19), np.float32)                   # float slots of sph::Particle: position 0..2, velocity 3..5, density 9, pressure 10, mass 11
+    rec[:, 0:3] = pos
+    rec[:, 11] = mass
+    m = pkg.MultiContext(n, [0, 0])
+    with pytest.raises(pkg.SphbError):
+        m.upload(pos, None, mass)                          # parameters first: the slabs are cut in units of the search radius
+    m.set_option(capi.OPT_MATH_MODE, capi.MATH_STRICT)
+    m.set_params(params)
+    m.upload_strided(n, rec.ctypes.data, 76, 0, 12, 44)
+    m.step(dt)
+    out = np.zeros_like(rec)
+    m.download_strided(out.ctypes.data, 76, 0, 12, 36, 40)
+    got = m.download()
+    assert_bits(out[:, 0:3], got["pos"], "strided pos")
+    assert_bits(out[:, 3:6], got["vel"], "strided vel")
+    assert_bits(out[:, 9], got["rho"], "strided rho")
+    assert_bits(out[:, 10], got["P"], "strided P")
+    want = single_run(pkg, params, pos, None, mass, dt, 1, True, 2)
+    assert_bits(got["rho"], want["rho"], "rho")
+    with pytest.raises(pkg.SphbError):
+        m.upload(np.zeros((n + 1, 3), np.float32))         # over capacity
+    m.close()
+    with pytest.raises(pkg.SphbError):
+        pkg.MultiContext(100, [])                          # no devices
+    # a scene too thin to be cut (8 particles in one cell layer, 3 devices) is not refused: one slab owns it, the other
+    # devices own an empty range and hold nothing
+    thin = pkg.MultiContext(8, [0, 0, 0])
+    thin.set_option(capi.OPT_MATH_MODE, capi.MATH_STRICT)
+    thin.set_params(params)
+    tp = (np.zeros((8, 3), np.float32) + 0.01 + np.arange(8, dtype=np.float32)[:, None] * 1e-3).astype(np.float32)
+    thin.upload(tp, None, np.full(8, 1e-3, np.float32))
+    thin.step(dt); thin.step(dt)
+    lay = thin.layout()
+    assert lay["owned"].tolist() == [0, 0, 8] and lay["ghosts"].tolist() == [0, 0, 0]
+    one = pkg.Context(8, 0)
+    one.set_option(capi.OPT_MATH_MODE, capi.MATH_STRICT)
+    one.set_params(params)
+    one.upload(tp, None, np.full(8, 1e-3, np.float32))
+    one.step(dt); one.step(dt)
+    a, b = thin.download(), one.download()
+    for f in ("pos", "vel", "rho", "acc"):
+        assert_bits(a[f], b[f], f"thin {f}")
+    assert thin.get_time() == one.get_time()
+    thin.close(); one.close()
+
+
+def test_multi_one_device_is_the_plain_context(pkg):
+    from sph_b200 import scenes
+    pos, mass, params, dt = scenes.dam_break_scene(0.025)
+    got = multi_run(pkg, [0], params, pos, None, mass, dt, 3, False)
+    capi = pkg.capi
+    ctx = pkg.Context(len(pos), 0)
+    ctx.set_params(params)
+    ctx.upload(pos, None, mass)
+    for _ in range(3):
+        ctx.step(dt)
+    want = ctx.download()
+    ctx.close()
+    for f in ("pos", "vel", "rho", "P", "acc"):
+        assert_bits(got[f], want[f], f)

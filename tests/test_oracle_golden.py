@@ -5,16 +5,19 @@ import json
 import numpy as np
 import pytest
 
-from helpers import GOLDEN, STEP_FIXTURES, assert_bits, golden_steps, load_golden, params_from
+from helpers import GOLDEN, KERNEL_FIXTURES, STEP_FIXTURES, assert_bits, golden_steps, load_golden, params_from
 
 
-@pytest.mark.parametrize("name", STEP_FIXTURES)
+@pytest.mark.parametrize("name", STEP_FIXTURES + KERNEL_FIXTURES)
 def test_port_matches_reference_golden(po, name):
+    """KERNEL_FIXTURES: the reference engine with its Wendland C2 / Gaussian class in the kernel slot (kernels.cpp:166-236)."""
     g = load_golden(name)
     prm = params_from(g["params"])
     n = g["pos"].shape[0]
     e = po.Engine("port", n)
     e.initialize(prm)
+    if "kernel_type" in g:
+        e.set_kernel(int(g["kernel_type"]))
     e.add_particles(g["pos"], g["vel"], g["mass"])
     keep = golden_steps(g)
     for k, dt in enumerate(g["dts"]):

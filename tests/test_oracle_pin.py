@@ -69,3 +69,32 @@ def test_generators(strict):
             assert_bits(pa, pb, gen.__name__); assert_bits(ma, mb, gen.__name__)
     pa, _ = po.gen_fluid_drop((0, 0.5, 0), 0.1, 0.004, 1.0, kind="strict"); pb, _ = po.gen_fluid_drop((0, 0.5, 0), 0.1, 0.004, 1.0, kind="port")
     assert_bits(pa, pb, "drop")
+
+
+@pytest.mark.parametrize("kernel_type", [1, 2])
+def test_other_kernel_classes_bit_exact(strict, kernel_type):
+    """the reference's Wendland C2 / Gaussian classes (kernels.cpp:166-222), installed in the engine's kernel
+    slot by create_kernel, against the port's restatement: W / gradW / laplacianW at random separations and at the special
+    points, then two engine steps; initialize() and set_smoothing_length() put the cubic spline back in both."""
+    po = strict
+    a, b = po.Engine("strict", 9000), po.Engine("port", 9000)
+    for e in (a, b):
+        e.initialize_fluid_drop()
+        e.set_kernel(kernel_type)
+    h = float(a.get_parameters()["smoothing_length"])
+    rng = np.random.default_rng(5)
+    rs = (rng.uniform(-1, 1, (3000, 3)) * 2.2 * h).astype(np.float32).tolist() + [[0, 0, 0], [2 * h, 0, 0], [h, 0, 0], [1e-7, 0, 0], [0, 3 * h, 0]]
+    assert_bits(np.array([a.kernel_W(r) for r in rs], np.float32), np.array([b.kernel_W(r) for r in rs], np.float32), "W")
+    assert_bits(np.array([a.kernel_gradW(r) for r in rs], np.float32), np.array([b.kernel_gradW(r) for r in rs], np.float32), "gradW")
+    assert_bits(np.array([a.kernel_lapW(r) for r in rs], np.float32), np.array([b.kernel_lapW(r) for r in rs], np.float32), "lapW")
+    for k in range(2):
+        a.step(0.0005); b.step(0.0005)
+        sa, sb = a.state(), b.state()
+        for f in ("rho", "P", "acc", "pos", "vel"):
+            assert_bits(sa[f], sb[f], f"kernel {kernel_type} step {k} {f}")
+    for e in (a, b):
+        e.set_smoothing_length(h)
+    assert np.float32(a.kernel_W((0, 0, 0))) == np.float32(b.kernel_W((0, 0, 0)))
+    sigma = np.float32(1.0) / (np.float32(np.pi) * np.float32(h) * np.float32(h) * np.float32(h))
+    assert np.float32(b.kernel_W((0, 0, 0))) == sigma * np.float32(2.0 / 3.0)       # the cubic spline again (sph_engine.cpp:162)
+    a.close(); b.close()
