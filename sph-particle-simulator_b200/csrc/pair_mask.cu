@@ -45,6 +45,9 @@ constexpr int kThreads = SPHB_MASK_THREADS;
 #ifndef SPHB_FORCE_PIPE
 #define SPHB_FORCE_PIPE 0
 #endif
+#ifndef SPHB_FORCE_PREFETCH
+#define SPHB_FORCE_PREFETCH 0
+#endif
 #define SPHB_PRAGMA(x) _Pragma(#x)
 #define SPHB_UNROLL_N(n) SPHB_PRAGMA(unroll n)
 
@@ -67,7 +70,11 @@ template <typename T> __device__ __forceinline__ T* pin(T* p) { return p; }
 // index of the highest set bit (FLO)
 __device__ __forceinline__ uint32_t top_bit(uint32_t w) {
     uint32_t b;
+#if SPHB_FORCE_REC32
+    asm volatile("bfind.u32 %0, %1;" : "=r"(b) : "r"(w));   // volatile: ptxas otherwise issues the FLO twice per pop under register pressure
+#else
     asm("bfind.u32 %0, %1;" : "=r"(b) : "r"(w));
+#endif
     return b;
 }
 // bit `pos` as a mask (one BMSK instead of materialising a constant and shifting it)
@@ -158,12 +165,15 @@ __global__ void __launch_bounds__(kThreads, SPHB_FMASK_MINBLOCKS) k_force_mask16
     const float P_i = a.rho_p[i].y;
     const uint32_t c = center_cell(a.grid, pi);
     const uint32_t* __restrict__ cs = a.cell_start;
-    const float4* __restrict__ fa = pin(a.fa);
 #if SPHB_FORCE_REC32
+    // (held like the float constants of ForceLane: XOR with a run-time zero keeps ptxas from re-reading the kernel parameter
+    // from the constant bank on every pop)
+    const float4* __restrict__ fa = reinterpret_cast<const float4*>(reinterpret_cast<uintptr_t>(a.fa) ^ (uintptr_t)(a.n >> 62));
     auto load2 = [&](uint32_t j) -> ForceRec {
-        const float4* q = fa + 2u * j;
+        const float4* q = fa + 2 * (size_t)j;
         const float4 qa = __ldg(q), qb = __ldg(q + 1);
 #else
+    const float4* __restrict__ fa = pin(a.fa);
     const float4* __restrict__ fb = pin(a.fb);
     auto load2 = [&](uint32_t j) -> ForceRec {
         const float4 qa = __ldg(fa + j), qb = __ldg(fb + j);
@@ -182,12 +192,21 @@ __global__ void __launch_bounds__(kThreads, SPHB_FMASK_MINBLOCKS) k_force_mask16
     const uint32_t* __restrict__ mrow = static_cast<const uint32_t*>(a.masks) + i;
     const size_t stride = a.mask_stride;
     unsigned ovf = 0;
+#if SPHB_FORCE_PREFETCH
+    uint32_t w_next = __ldcs(mrow);   // the mask rows stream from DRAM: each word is requested one group ahead of its use
+#endif
 #pragma unroll 1
     for (int g = 0; g <= kGroups; ++g) {
         const int reach = column_reach<R>(g);
         if (reach >= 0) {   // warp-uniform; a column and its mirror have the same reach
+#if SPHB_FORCE_PREFETCH
+            uint32_t w = w_next;
+            mrow += stride;
+            if (g < kGroups) w_next = __ldcs(mrow);   // a non-empty group is always followed by a row (at least the centre's)
+#else
             uint32_t w = __ldcs(mrow);
             mrow += stride;
+#endif
             if (g == kGroups) { ovf = w >> 31; w &= 0xFFFFu; }
             // candidate q of column g is bit 15 - q, of its mirror bit 31 - q: slot = base - bit
             const uint32_t baseA = __ldg(cs + (c - rel - (uint32_t)reach)) + 15u;
