@@ -373,23 +373,33 @@ def validate_single(pkg, po, capi, local, stream, sample_scene, pair_kernel):
     ctx.set_option(capi.OPT_DEBUG_CAPTURE, 1)
     ctx.set_params(params)
     ctx.upload(pos, None, mass)
+    # neighbour SETS are compared where both codes see the same positions (the first step); after that the fast path's
+    # positions differ from the strict reference's in the last bits and the exact q = 2 ties of the lattice flip
+    eng.step(dt); ctx.step(dt)
+    cnt_ok = bool(np.array_equal(ctx.debug_dump(keys=False, perm=False)["nbr_count"], eng.neighbor_counts()))
     steps = 2
-    for _ in range(steps):
+    for _ in range(steps - 1):
         eng.step(dt); ctx.step(dt)
     want, got = eng.state(), ctx.download()
-    cnt_ok = bool(np.array_equal(ctx.debug_dump(keys=False, perm=False)["nbr_count"], eng.neighbor_counts()))
     rho_rel = float(np.abs(got["rho"].astype(np.float64) - want["rho"]).max() / np.abs(want["rho"]).max())
     L = float(max(params["xmax"] - params["xmin"], params["ymax"] - params["ymin"], params["zmax"] - params["zmin"]))
     pos_abs = float(np.abs(got["pos"].astype(np.float64) - want["pos"]).max())
     sum_rho, ke, vmax = ctx.diagnostics()
     h = float(np.float32(params["smoothing_length"]))
-    mass_rel = abs(sum_rho * h ** 3 - eng.total_mass()) / abs(eng.total_mass())
-    ke_rel = abs(ke - eng.total_energy()) / max(abs(eng.total_energy()), 1e-30)
-    ok = cnt_ok and rho_rel <= 2 * 2e-5 and pos_abs <= 2 * 1e-6 * L and mass_rel <= 1e-4 and ke_rel <= 1e-3
+    # diagnostics against fp64 sums of the reference's own per-particle fields; the reference's get_total_mass is a serial
+    # fp32 accumulate (sph_engine.cpp:187-190) that carries ~1e-3 at 3.5e5 terms, reported next to it
+    ref_sum_rho = float(want["rho"].astype(np.float64).sum())
+    ref_ke = float((0.5 * want["mass"].astype(np.float64) * (want["vel"].astype(np.float64) ** 2).sum(1)).sum())
+    mass_rel = abs(sum_rho - ref_sum_rho) / abs(ref_sum_rho)
+    ke_rel = abs(ke - ref_ke) / max(abs(ref_ke), 1e-30)
+    mass_ref_fp32 = abs(sum_rho * h ** 3 - eng.total_mass()) / abs(eng.total_mass())
+    ok = cnt_ok and rho_rel <= 2 * 2e-5 and pos_abs <= 2 * 1e-6 * L and mass_rel <= 1e-5 and ke_rel <= 1e-3
     eng.close(); ctx.close()
-    return {"ok": bool(ok), "against": f"reference CPU code ({kind}) on {sample_scene} (N={n}), {steps} steps", "neighbour_counts_equal": cnt_ok,
-            "rho_max_rel": rho_rel, "pos_max_abs_over_L": pos_abs / L, "mass_diag_rel": mass_rel, "kinetic_rel": ke_rel,
-            "gates": "counts bit-exact; rho rel <= 4e-5, pos <= 2e-6 L (2 steps: 2 x the single-step gates), sum(rho) h^3 rel <= 1e-4, KE rel <= 1e-3"}
+    return {"ok": bool(ok), "against": f"reference CPU code ({kind}) on {sample_scene} (N={n}), {steps} steps",
+            "neighbour_counts_equal_step1": cnt_ok, "rho_max_rel": rho_rel, "pos_max_abs_over_L": pos_abs / L, "sum_rho_rel": mass_rel,
+            "kinetic_rel": ke_rel, "total_mass_vs_reference_fp32_accumulate_rel": mass_ref_fp32,
+            "gates": "neighbour counts of the first step bit-exact; rho rel <= 4e-5, pos <= 2e-6 L (2 steps: 2 x the single-step gates); "
+                     "sum(rho) rel <= 1e-5 and KE rel <= 1e-3 against fp64 sums of the reference's per-particle fields"}
 
 
 def validate_slabs(run, steps=3):

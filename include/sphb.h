@@ -120,7 +120,12 @@ enum {
      * (the bitmask hand-off kernels are specialised for the cubic spline).  Strict mode: Wendland C2 is bit-exact against
      * the reference classes; the Gaussian agrees to the last bits of expf.  Unlike the reference's engine slot, the choice
      * survives sphb_set_params. */
-    SPHB_OPT_KERNEL_TYPE = 9
+    SPHB_OPT_KERNEL_TYPE = 9,
+    /* 1 (default): steps whose launch sequence repeats exactly (same particle count, parameters, dt argument, grid and
+     * buffers; no stage timing, no debug capture) are replayed from a CUDA graph — one launch call per step instead of
+     * nine, which is what the step time of small scenes (the reference's own 1 000 - 10 000 particle benchmarks) consists
+     * of.  Results are identical: the graph holds the very same kernels.  0 = always launch directly. */
+    SPHB_OPT_STEP_GRAPHS = 10
 };
 
 /* ---- lifetime ---------------------------------------------------------------------------------

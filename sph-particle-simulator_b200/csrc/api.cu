@@ -92,10 +92,29 @@ struct sphb_ctx {
     std::vector<EventSet> ev_pool;
     size_t ev_used = 0;
 
+    // CUDA graphs of repeating steps (sphb_step), one per parity of the double-buffered arrays
+    struct StepGraph {
+        cudaGraphExec_t exec = nullptr;
+        std::vector<unsigned char> key, seen;   // configuration the graph was captured for / seen at the last eligible step
+        uint64_t launches = 0;
+    };
+    StepGraph graphs[2];
+    cudaStream_t capture_stream = nullptr;      // graphs are captured here and launched into `stream`
+    int use_graphs = 1;                         // SPHB_OPT_STEP_GRAPHS
+
     char err[512] = "";
 };
 
 namespace {
+
+// bytes of everything a step's launches depend on (compared to decide whether a captured graph can be replayed)
+struct StepKey {
+    std::vector<unsigned char> bytes;
+    template <typename T> void add(const T& v) {
+        const unsigned char* p = reinterpret_cast<const unsigned char*>(&v);
+        bytes.insert(bytes.end(), p, p + sizeof(T));
+    }
+};
 
 int fail(sphb_ctx* c, int code, const char* fmt, ...) {
     va_list ap;
@@ -304,12 +323,14 @@ IntegrateConsts make_integrate_consts(const sphb_params& p) {
 
 void free_all(sphb_ctx* c) {
     cudaSetDevice(c->device);
+    for (auto& sg : c->graphs) if (sg.exec) { cudaGraphExecDestroy(sg.exec); sg.exec = nullptr; }
+    if (c->capture_stream) { cudaStreamDestroy(c->capture_stream); c->capture_stream = nullptr; }
     for (int i = 0; i < 2; ++i) {
         cudaFree(c->posm[i]); cudaFree(c->velid[i]); cudaFree(c->refkeys[i]); cudaFree(c->dbg_keys[i]); cudaFree(c->dbg_vals[i]);
     }
     cudaFree(c->cell_ticket); cudaFree(c->slot_src);
     cudaFree(c->masks); cudaFree(c->fab); cudaFree(c->colors);
-    cudaFree(c->rho_p); cudaFree(c->fa); if (!SPHB_FORCE_REC32) cudaFree(c->fb); cudaFree(c->acc); cudaFree(c->nbr_count);
+    cudaFree(c->rho_p); cudaFree(c->fa); cudaFree(c->fb); cudaFree(c->acc); cudaFree(c->nbr_count);
     cudaFree(c->cell_start);
     cudaFree(c->sc); cudaFree(c->d_stage); cudaFree(c->d_box); cudaFree(c->d_counts); cudaFree(c->sort_scratch);
     if (c->h_sc) cudaFreeHost(c->h_sc);
@@ -457,6 +478,9 @@ int sphb_set_option(sphb_ctx* c, int option, int64_t value) {
             if (value < 0 || value > 2) return fail(c, SPHB_E_INVALID, "layout major axis must be 0..2");
             c->layout_major = (int)value;
             return SPHB_OK;
+        case SPHB_OPT_STEP_GRAPHS:
+            c->use_graphs = value ? 1 : 0;
+            return SPHB_OK;
         case SPHB_OPT_KERNEL_TYPE:
             if (value < 0 || value > 2) return fail(c, SPHB_E_INVALID, "kernel type must be 0 (cubic spline), 1 (Wendland C2) or 2 (Gaussian)");
             c->kernel_type = (int)value;
@@ -478,6 +502,7 @@ int sphb_get_option(const sphb_ctx* c, int option, int64_t* value) {
         case SPHB_OPT_LAYOUT_MAJOR: *value = c->layout_major; return SPHB_OK;
         case SPHB_OPT_PAIR_MODE: *value = c->pair_mode; return SPHB_OK;
         case SPHB_OPT_KERNEL_TYPE: *value = c->kernel_type; return SPHB_OK;
+        case SPHB_OPT_STEP_GRAPHS: *value = c->use_graphs; return SPHB_OK;
         default: return SPHB_E_INVALID;
     }
 }
@@ -713,16 +738,10 @@ int sphb_step(sphb_ctx* c, float dt) {
     }
     if ((variant != 2 || split) && !c->fa) {
         const size_t cap = c->capacity ? c->capacity : 1;
-#if SPHB_FORCE_REC32
-        CU(c, cudaMalloc(&c->fa, 2 * cap * sizeof(float4)));   // interleaved halves: fb = fa + 1, stride 2 (the tested-walk kernels use the
-        c->fb = c->fa + cap;                                    // same allocation as two plain arrays)
-        CU(c, cudaMemsetAsync(c->fa, 0, 2 * cap * sizeof(float4), c->stream));
-#else
         CU(c, cudaMalloc(&c->fa, cap * sizeof(float4)));
         CU(c, cudaMalloc(&c->fb, cap * sizeof(float4)));
         CU(c, cudaMemsetAsync(c->fa, 0, cap * sizeof(float4), c->stream));
         CU(c, cudaMemsetAsync(c->fb, 0, cap * sizeof(float4), c->stream));
-#endif
     }
     if (c->debug_capture) { rc = ensure_debug(c); if (rc) return rc; }
 
@@ -733,67 +752,8 @@ int sphb_step(sphb_ctx* c, float dt) {
     cudaEvent_t* ev = c->stage_timing ? next_event_set(c) : nullptr;
     const bool timing = ev != nullptr;
 
-    if (timing) cudaEventRecord(ev[0], st);
     const int in = c->cur, outb = c->cur ^ 1;
-    // counting sort by cell: count (+ the step's dt) -> scan -> scatter -> reorder (ids ascending inside each cell)
-    size_t scratch_off = 0;
-    const size_t table_bytes = cell_table_bytes(g, &scratch_off);
-    CU(c, cudaMemsetAsync(c->cell_start, 0, table_bytes, st));
-    launches += launch_cell_count(n, c->posm[in], c->velid[in], g, c->cell_ticket, c->cell_start,
-                                  c->debug_capture ? c->refkeys[in] : nullptr, dbg_ref_sort ? c->dbg_keys[0] : nullptr, gc, c->sc,
-                                  dt, ic, st);
-    launches += launch_scan_exclusive(c->cell_start, (size_t)g.ncells + 1, reinterpret_cast<unsigned char*>(c->cell_start) + scratch_off, st);
-    launches += launch_cell_scatter(n, c->cell_ticket, c->cell_start, c->slot_src, st);
-    launches += launch_reorder(n, c->slot_src, c->cell_ticket, c->cell_start, c->posm[in], c->velid[in],
-                               c->debug_capture ? c->refkeys[in] : nullptr, c->posm[outb], c->velid[outb],
-                               c->debug_capture ? c->refkeys[outb] : nullptr, st);
-    c->cur = outb;
-    if (timing) cudaEventRecord(ev[1], st);
-    c->dbg_sorted = -1;
-    if (dbg_ref_sort) {   // debug only: the reference-order permutation, by the same radix sort over (reference cell, id)
-        SortBuffers ds;
-        ds.keys[0] = c->dbg_keys[0]; ds.keys[1] = c->dbg_keys[1];
-        ds.vals[0] = c->dbg_vals[0]; ds.vals[1] = c->dbg_vals[1];
-        int o = 0;
-        launches += launch_radix_sort_onesweep(ds, n, 0, gc.id_bits + gc.cell_bits, &o, c->sort_scratch, st);
-        c->dbg_sorted = o;
-        c->dbg_id_bits = gc.id_bits;
-    }
-
-    PairArgs pa;
-    pa.n = n;
-    pa.posm = c->posm[c->cur];
-    pa.velid = c->velid[c->cur];
-    pa.cell_start = c->cell_start;
-    pa.rho_p = c->rho_p;
-    pa.fa = c->fa;
-    pa.fb = (SPHB_FORCE_REC32 && split) ? c->fa + 1 : c->fb;
-    pa.acc = c->acc;
-    pa.masks = c->masks;
-    pa.mask_stride = c->mask_stride;
-    pa.fab = c->fab;
-    pa.nbr_count = c->debug_capture ? c->nbr_count : nullptr;
-    pa.sc = c->sc;
-    pa.grid = g;
-    pa.k = pk;
-    pa.walk_radius = c->walk_radius * refine;
-    pa.strict = c->math_mode == 0;
-    pa.variant = variant;
-    pa.kernel_type = c->kernel_type;
-    pa.mode = mode;
-    pa.slab_axis = c->slab_on ? c->slab.axis : -1;
-    pa.rho_lo = c->slab_on ? c->slab.own_lo - 1 : 0;
-    pa.rho_hi = c->slab_on ? c->slab.own_hi + 1 : 0;
-    {
-        const int ld = launch_density(pa, st);
-        if (timing) cudaEventRecord(ev[2], st);
-        const int lf = ld < 0 ? ld : launch_force(pa, st);
-        if (ld < 0 || lf < 0)
-            return fail(c, SPHB_E_CUDA, "the staged pair kernels cannot be configured on this device (%s); set SPHB_OPT_PAIR_MODE 0",
-                        cudaGetErrorString(cudaGetLastError()));
-        launches += (uint64_t)(ld + lf);
-    }
-    if (timing) cudaEventRecord(ev[3], st);
+    int dbg_sorted = -1;
     // after the clamp every position lies inside the AABB (particle.cpp:122-153), so the next step can size its
     // cell table from the bounds without looking at the device.  When that table would be far larger than the
     // particle count (sparse scene, e.g. a drop in a big box) the integrate kernel also reduces the bounding box
@@ -812,13 +772,124 @@ int sphb_step(sphb_ctx* c, float dt) {
         }
         track_box = cells > 8.0 * (double)n;   // slab mode: sphb_slab_append adds the boxes of arriving records
     }
-    if (track_box) {
-        const int init[6] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, (int)0x80000000, (int)0x80000000, (int)0x80000000};
-        CU(c, cudaMemcpyAsync(c->d_box, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    // Everything the step puts on the stream, in order: clear + counting sort, the pair passes, the fused integration.
+    auto enqueue = [&]() -> int {
+        if (timing) cudaEventRecord(ev[0], st);
+        // counting sort by cell: count (+ the step's dt) -> scan -> scatter -> reorder (ids ascending inside each cell)
+        size_t scratch_off = 0;
+        const size_t table_bytes = cell_table_bytes(g, &scratch_off);
+        CU(c, cudaMemsetAsync(c->cell_start, 0, table_bytes, st));
+        launches += launch_cell_count(n, c->posm[in], c->velid[in], g, c->cell_ticket, c->cell_start,
+                                      c->debug_capture ? c->refkeys[in] : nullptr, dbg_ref_sort ? c->dbg_keys[0] : nullptr, gc, c->sc,
+                                      dt, ic, st);
+        launches += launch_scan_exclusive(c->cell_start, (size_t)g.ncells + 1, reinterpret_cast<unsigned char*>(c->cell_start) + scratch_off, st);
+        launches += launch_cell_scatter(n, c->cell_ticket, c->cell_start, c->slot_src, st);
+        launches += launch_reorder(n, c->slot_src, c->cell_ticket, c->cell_start, c->posm[in], c->velid[in],
+                                   c->debug_capture ? c->refkeys[in] : nullptr, c->posm[outb], c->velid[outb],
+                                   c->debug_capture ? c->refkeys[outb] : nullptr, st);
+        if (timing) cudaEventRecord(ev[1], st);
+        if (dbg_ref_sort) {   // debug only: the reference-order permutation, by the same radix sort over (reference cell, id)
+            SortBuffers ds;
+            ds.keys[0] = c->dbg_keys[0]; ds.keys[1] = c->dbg_keys[1];
+            ds.vals[0] = c->dbg_vals[0]; ds.vals[1] = c->dbg_vals[1];
+            int o = 0;
+            launches += launch_radix_sort_onesweep(ds, n, 0, gc.id_bits + gc.cell_bits, &o, c->sort_scratch, st);
+            dbg_sorted = o;
+        }
+
+        PairArgs pa;
+        pa.n = n;
+        pa.posm = c->posm[outb];
+        pa.velid = c->velid[outb];
+        pa.cell_start = c->cell_start;
+        pa.rho_p = c->rho_p;
+        pa.fa = c->fa;
+        pa.fb = c->fb;
+        pa.acc = c->acc;
+        pa.masks = c->masks;
+        pa.mask_stride = c->mask_stride;
+        pa.fab = c->fab;
+        pa.nbr_count = c->debug_capture ? c->nbr_count : nullptr;
+        pa.sc = c->sc;
+        pa.grid = g;
+        pa.k = pk;
+        pa.walk_radius = c->walk_radius * refine;
+        pa.strict = c->math_mode == 0;
+        pa.variant = variant;
+        pa.kernel_type = c->kernel_type;
+        pa.mode = mode;
+        pa.slab_axis = c->slab_on ? c->slab.axis : -1;
+        pa.rho_lo = c->slab_on ? c->slab.own_lo - 1 : 0;
+        pa.rho_hi = c->slab_on ? c->slab.own_hi + 1 : 0;
+        {
+            const int ld = launch_density(pa, st);
+            if (timing) cudaEventRecord(ev[2], st);
+            const int lf = ld < 0 ? ld : launch_force(pa, st);
+            if (ld < 0 || lf < 0)
+                return fail(c, SPHB_E_CUDA, "the staged pair kernels cannot be configured on this device (%s); set SPHB_OPT_PAIR_MODE 0",
+                            cudaGetErrorString(cudaGetLastError()));
+            launches += (uint64_t)(ld + lf);
+        }
+        if (timing) cudaEventRecord(ev[3], st);
+        if (track_box) {
+            const int init[6] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, (int)0x80000000, (int)0x80000000, (int)0x80000000};
+            CU(c, cudaMemcpyAsync(c->d_box, init, sizeof(init), cudaMemcpyHostToDevice, st));
+        }
+        launches += launch_integrate(n, c->posm[outb], c->velid[outb], c->acc, ic, c->sc, track_box ? c->d_box : nullptr, st);
+        if (timing) cudaEventRecord(ev[4], st);
+        CU(c, cudaGetLastError());
+        return SPHB_OK;
+    };
+    // Steps whose launches repeat exactly (same particle count, grid, parameters, buffers — every fixed-dt or
+    // adaptive-dt step of a resident simulation without per-step read-backs) are replayed from a CUDA graph: one launch
+    // call instead of nine, which is what a small scene's step time consists of.  Two graphs, one per parity of the
+    // double-buffered arrays; a configuration is captured the second time it comes up in a row, so callers that change
+    // something every step (slab mode: the particle count) simply keep launching directly.
+    const bool graph_ok = c->use_graphs && !timing && !c->debug_capture && !track_box;
+    if (graph_ok) {
+        StepKey key;
+        key.add(n); key.add(dt); key.add(in); key.add(st); key.add(g); key.add(pk); key.add(ic);
+        key.add(variant); key.add(mode); key.add(refine); key.add(c->walk_radius); key.add(c->math_mode); key.add(c->kernel_type);
+        key.add(c->slab_on ? c->slab.axis : -1); key.add(c->slab_on ? c->slab.own_lo : 0); key.add(c->slab_on ? c->slab.own_hi : 0);
+        key.add(c->posm[0]); key.add(c->posm[1]); key.add(c->velid[0]); key.add(c->velid[1]); key.add(c->rho_p); key.add(c->acc);
+        key.add(c->fa); key.add(c->fb); key.add(c->fab); key.add(c->masks); key.add(c->mask_stride); key.add(c->cell_start);
+        key.add(c->cell_ticket); key.add(c->slot_src); key.add(c->sc);
+        sphb_ctx::StepGraph& sg = c->graphs[in];
+        if (sg.exec && sg.key == key.bytes) {
+            CU(c, cudaGraphLaunch(sg.exec, st));
+            launches = sg.launches;
+        } else if (sg.seen == key.bytes) {
+            if (sg.exec) { cudaGraphExecDestroy(sg.exec); sg.exec = nullptr; }
+            // captured on a stream of our own (the caller's may be the legacy default stream, which cannot be captured;
+            // capturing executes nothing) and launched into the caller's stream
+            if (!c->capture_stream) CU(c, cudaStreamCreateWithFlags(&c->capture_stream, cudaStreamNonBlocking));
+            const cudaStream_t user_stream = st;
+            st = c->capture_stream;
+            CU(c, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            rc = enqueue();
+            cudaGraph_t graph = nullptr;
+            const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            st = user_stream;
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (ce != cudaSuccess) return fail(c, SPHB_E_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ce));
+            const cudaError_t ie = cudaGraphInstantiate(&sg.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ie != cudaSuccess) { sg.exec = nullptr; return fail(c, SPHB_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ie)); }
+            sg.key = key.bytes;
+            sg.launches = launches;
+            CU(c, cudaGraphLaunch(sg.exec, st));
+        } else {
+            sg.seen = key.bytes;
+            rc = enqueue();
+            if (rc) return rc;
+        }
+    } else {
+        rc = enqueue();
+        if (rc) return rc;
     }
-    launches += launch_integrate(n, c->posm[c->cur], c->velid[c->cur], c->acc, ic, c->sc, track_box ? c->d_box : nullptr, st);
-    if (timing) cudaEventRecord(ev[4], st);
-    CU(c, cudaGetLastError());
+    c->cur = outb;
+    c->dbg_sorted = dbg_sorted;
+    if (dbg_sorted >= 0) c->dbg_id_bits = gc.id_bits;
 
     c->box_tracking = track_box;
     if (track_box) {

@@ -45,9 +45,6 @@ constexpr int kThreads = SPHB_MASK_THREADS;
 #ifndef SPHB_FORCE_PIPE
 #define SPHB_FORCE_PIPE 0
 #endif
-#ifndef SPHB_FORCE_PREFETCH
-#define SPHB_FORCE_PREFETCH 0
-#endif
 #define SPHB_PRAGMA(x) _Pragma(#x)
 #define SPHB_UNROLL_N(n) SPHB_PRAGMA(unroll n)
 
@@ -70,11 +67,7 @@ template <typename T> __device__ __forceinline__ T* pin(T* p) { return p; }
 // index of the highest set bit (FLO)
 __device__ __forceinline__ uint32_t top_bit(uint32_t w) {
     uint32_t b;
-#if SPHB_FORCE_REC32
-    asm volatile("bfind.u32 %0, %1;" : "=r"(b) : "r"(w));   // volatile: ptxas otherwise issues the FLO twice per pop under register pressure
-#else
     asm("bfind.u32 %0, %1;" : "=r"(b) : "r"(w));
-#endif
     return b;
 }
 // bit `pos` as a mask (one BMSK instead of materialising a constant and shifting it)
@@ -146,8 +139,8 @@ SPHB_UNROLL_N(SPHB_DMASK_GROUP_UNROLL)
         const float4 v = a.velid[i];
         const float A = pi.w / (2.0f * rho);
         // force-pass records in two arrays of 16-byte halves (the layout the staged kernels gather without bank conflicts)
-        a.fa[kRecStride * i] = make_float4(pi.x, pi.y, pi.z, A);
-        a.fb[kRecStride * i] = make_float4(v.x, v.y, v.z, A * P);
+        a.fa[i] = make_float4(pi.x, pi.y, pi.z, A);
+        a.fb[i] = make_float4(v.x, v.y, v.z, A * P);
         if (a.nbr_count) a.nbr_count[i] = count;
     }
     count = __reduce_max_sync(0xffffffffu, count);
@@ -165,19 +158,10 @@ __global__ void __launch_bounds__(kThreads, SPHB_FMASK_MINBLOCKS) k_force_mask16
     const float P_i = a.rho_p[i].y;
     const uint32_t c = center_cell(a.grid, pi);
     const uint32_t* __restrict__ cs = a.cell_start;
-#if SPHB_FORCE_REC32
-    // (held like the float constants of ForceLane: XOR with a run-time zero keeps ptxas from re-reading the kernel parameter
-    // from the constant bank on every pop)
-    const float4* __restrict__ fa = reinterpret_cast<const float4*>(reinterpret_cast<uintptr_t>(a.fa) ^ (uintptr_t)(a.n >> 62));
-    auto load2 = [&](uint32_t j) -> ForceRec {
-        const float4* q = fa + 2 * (size_t)j;
-        const float4 qa = __ldg(q), qb = __ldg(q + 1);
-#else
     const float4* __restrict__ fa = pin(a.fa);
     const float4* __restrict__ fb = pin(a.fb);
     auto load2 = [&](uint32_t j) -> ForceRec {
         const float4 qa = __ldg(fa + j), qb = __ldg(fb + j);
-#endif
         ForceRec r;
         r.x = qa.x; r.y = qa.y; r.z = qa.z; r.A = qa.w; r.vx = qb.x; r.vy = qb.y; r.vz = qb.z; r.B = qb.w;
         return r;
@@ -192,21 +176,12 @@ __global__ void __launch_bounds__(kThreads, SPHB_FMASK_MINBLOCKS) k_force_mask16
     const uint32_t* __restrict__ mrow = static_cast<const uint32_t*>(a.masks) + i;
     const size_t stride = a.mask_stride;
     unsigned ovf = 0;
-#if SPHB_FORCE_PREFETCH
-    uint32_t w_next = __ldcs(mrow);   // the mask rows stream from DRAM: each word is requested one group ahead of its use
-#endif
 #pragma unroll 1
     for (int g = 0; g <= kGroups; ++g) {
         const int reach = column_reach<R>(g);
         if (reach >= 0) {   // warp-uniform; a column and its mirror have the same reach
-#if SPHB_FORCE_PREFETCH
-            uint32_t w = w_next;
-            mrow += stride;
-            if (g < kGroups) w_next = __ldcs(mrow);   // a non-empty group is always followed by a row (at least the centre's)
-#else
             uint32_t w = __ldcs(mrow);
             mrow += stride;
-#endif
             if (g == kGroups) { ovf = w >> 31; w &= 0xFFFFu; }
             // candidate q of column g is bit 15 - q, of its mirror bit 31 - q: slot = base - bit
             const uint32_t baseA = __ldg(cs + (c - rel - (uint32_t)reach)) + 15u;

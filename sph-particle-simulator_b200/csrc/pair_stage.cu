@@ -82,11 +82,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // records [lo, lo + count) of src -> dst[0 .. count), count <= 64: at most two copies per lane
-// (stride: records of src per particle — kRecStride for the force-pass records)
-__device__ __forceinline__ void stage_range(const float4* dst, const float4* __restrict__ src, uint32_t lo, uint32_t count, uint32_t lane,
-                                            uint32_t stride = 1u) {
-    if (lane < count) cp_async16(dst + lane, src + (size_t)(lo + lane) * stride);
-    if (lane + 32u < count) cp_async16(dst + lane + 32u, src + (size_t)(lo + lane + 32u) * stride);
+__device__ __forceinline__ void stage_range(const float4* dst, const float4* __restrict__ src, uint32_t lo, uint32_t count, uint32_t lane) {
+    if (lane < count) cp_async16(dst + lane, src + lo + lane);
+    if (lane + 32u < count) cp_async16(dst + lane + 32u, src + lo + lane + 32u);
 }
 
 // TRUNC: the search radius cuts the kernel support short (see k_density_mask16)
@@ -183,8 +181,8 @@ SPHB_UNROLL_N(SPHB_DSTAGE_GROUP_UNROLL)
             const float A = pi.w / (2.0f * rho);
             // force-pass records, in two arrays of 16-byte halves: staged at a 16-byte stride they are gathered by
             // LDS.128 without bank conflicts (32-byte records: two-way conflicts on every access)
-            a.fa[kRecStride * i] = make_float4(pi.x, pi.y, pi.z, A);
-            a.fb[kRecStride * i] = make_float4(v.x, v.y, v.z, A * P);
+            a.fa[i] = make_float4(pi.x, pi.y, pi.z, A);
+            a.fb[i] = make_float4(v.x, v.y, v.z, A * P);
             if (a.nbr_count) a.nbr_count[i] = count;
         }
     }
@@ -245,8 +243,8 @@ __global__ void __launch_bounds__(kThreadsS, SPHB_FSTAGE_MINBLOCKS) k_force_stag
         const uint32_t hi = min(__reduce_max_sync(0xffffffffu, use ? start + (uint32_t)kMaskBits : 0u), nslots);
         if (hi <= lo) return 0u;             // no lane has a bit in this column
         if (hi - lo > (uint32_t)kCapF) return 0xffffffffu;
-        stage_range(dst, fa, lo, hi - lo, lane, (uint32_t)kRecStride);
-        stage_range(dst + 2 * kCapF, fb, lo, hi - lo, lane, (uint32_t)kRecStride);
+        stage_range(dst, fa, lo, hi - lo, lane);
+        stage_range(dst + 2 * kCapF, fb, lo, hi - lo, lane);
         return lo;
     };
 
@@ -289,7 +287,7 @@ SPHB_UNROLL_N(SPHB_FSTAGE_GROUP_UNROLL)
                 const uint32_t b = top_bit(w);
                 w ^= bit_at(b);
                 const uint32_t j = (b >= 16u ? baseB : baseA) - b;
-                eval(__ldg(fa + (size_t)kRecStride * j), __ldg(fb + (size_t)kRecStride * j));
+                eval(__ldg(fa + j), __ldg(fb + j));
             }
         }
         w = w1; sA = sA1; sB = sB1; loA = nloA; loB = nloB;
@@ -311,7 +309,7 @@ SPHB_UNROLL_N(SPHB_FSTAGE_GROUP_UNROLL)
                 const float rx = __fsub_rn(pi.x, pj.x), ry = __fsub_rn(pi.y, pj.y), rz = __fsub_rn(pi.z, pj.z);
                 const float d2 = dist2_exact(rx, ry, rz);
                 if (d2 <= r2) {
-                    const float4 qa = __ldg(fa + (size_t)kRecStride * j), qb = __ldg(fb + (size_t)kRecStride * j);
+                    const float4 qa = __ldg(fa + j), qb = __ldg(fb + j);
                     force_pair_fast(a.k, f, rx, ry, rz, d2, qb.x - vi.x, qb.y - vi.y, qb.z - vi.z, P_i, qa.w, qb.w);
                 }
             }

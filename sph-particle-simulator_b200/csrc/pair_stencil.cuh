@@ -7,10 +7,6 @@
 
 #include "pair_math.cuh"
 
-#ifndef SPHB_FORCE_T_DIRECT
-#define SPHB_FORCE_T_DIRECT 0
-#endif
-
 namespace sphb {
 
 namespace {
@@ -213,7 +209,7 @@ struct DensityWalker {
 // closer than 1e-6 contributes |dW/dq| <= 2e-6 / h instead of nothing, far below the fast-mode gates.
 struct ForceLane {
     float2 npxy, nvxy;
-    float pz, vz, P_i, nhinvh, ninvh;
+    float pz, vz, P_i, nhinvh;
     // accumulators of -F_pressure / (2 sigma / h) and F_viscosity / (4 mu sigma / h^2): (x, y) packed, z scalar
     float2 fpxy, fvxy;
     float fpz, fvz;
@@ -222,7 +218,6 @@ struct ForceLane {
         npxy = mk2(-pi.x, -pi.y); nvxy = mk2(-vi.x, -vi.y);
         pz = pi.z; vz = vi.z; P_i = P;
         nhinvh = hold(-0.5f * k.inv_h, zero);
-        ninvh = hold(-k.inv_h, zero);
         fpxy = fvxy = mk2(0.0f, 0.0f);
         fpz = fvz = 0.0f;
     }
@@ -232,14 +227,8 @@ struct ForceLane {
         const float rz = qa.z - pz;
         const float d2 = fmaf(rz, rz, fmaf(rxy.y, rxy.y, rxy.x * rxy.x));
         const float inv_len = fast_rsqrt(d2 + 1e-30f);
-#if SPHB_FORCE_T_DIRECT
-        const float len = d2 * inv_len;
-        const float u = fma_sat(len, nhinvh, 1.0f);                // (2 - q)+ / 2
-        const float t = fma_sat(len, ninvh, 1.0f);                 // (1 - q)+
-#else
         const float u = fma_sat(d2 * nhinvh, inv_len, 1.0f);      // (2 - q)+ / 2
         const float t = fma_sat(u, 2.0f, -1.0f);                   // (1 - q)+
-#endif
         const float gh = fmaf(t, t, -(u * u));
         const float lq = fmaf(t, -2.0f, u);
         const float cp = fmaf(qa.w, P_i, qb.w) * (gh * inv_len);

@@ -129,14 +129,6 @@ struct __align__(32) ForceRec {
     float vx, vy, vz, B;
 };
 
-// Force-pass records of the 16-bit mask kernels: SPHB_FORCE_REC32 = 1 keeps the two 16-byte halves of a particle next to
-// each other (fb = fa + 1, stride 2): one address computation per neighbour and both loads in one 32-byte sector;
-// 0 = two separate arrays.
-#ifndef SPHB_FORCE_REC32
-#define SPHB_FORCE_REC32 0
-#endif
-constexpr int kRecStride = SPHB_FORCE_REC32 ? 2 : 1;
-
 struct PairArgs {
     size_t n;
     const float4* posm;        // x, y, z, mass   (cell-sorted)
