@@ -282,7 +282,14 @@ int sphb_slab_download(sphb_ctx* ctx, size_t cap, uint32_t* ids, float* pos3, fl
 typedef struct sphb_multi sphb_multi;
 enum {
     /* slab axis: -1 (default) = the longest axis of the uploaded particles' bounding box, else 0 / 1 / 2 */
-    SPHB_OPT_MULTI_AXIS = 100
+    SPHB_OPT_MULTI_AXIS = 100,
+    /* ghost layers per slab face (default 2 = the minimum: the first layer's density is recomputed locally from the second);
+     * takes effect at the next upload */
+    SPHB_OPT_MULTI_HALO_LAYERS = 101,
+    /* load balance: when an exchange leaves one device with more than 1.5x its even share AND more than this many
+     * particles above it (default 32768), the slabs are re-cut for the current positions before the next step (one
+     * round trip of positions and velocities through the host; results do not depend on where the cuts are) */
+    SPHB_OPT_MULTI_REBALANCE_MIN = 102
 };
 int sphb_create_multi(sphb_multi** out, size_t capacity, int ndev, const int* devices);
 void sphb_destroy_multi(sphb_multi* m);

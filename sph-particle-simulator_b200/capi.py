@@ -39,6 +39,8 @@ OPT_KERNEL_TYPE = 9
 OPT_STEP_GRAPHS = 10
 KERNEL_CUBIC_SPLINE, KERNEL_WENDLAND_C2, KERNEL_GAUSSIAN = 0, 1, 2
 OPT_MULTI_AXIS = 100
+OPT_MULTI_HALO_LAYERS = 101
+OPT_MULTI_REBALANCE_MIN = 102
 MATH_STRICT = 0
 MATH_FAST = 1
 

@@ -38,18 +38,23 @@ struct sphb_multi {
     std::vector<int32_t> cuts;
     int axis = -1;                            // -1: the longest axis of the uploaded particles' bounding box
     int slab_axis = -1;                       // the axis the current cuts are on
+    int layers = 2;                           // halo layers per face (SPHB_OPT_MULTI_HALO_LAYERS)
     int active = 0;                           // slabs that own cells (the last `active` devices; the others own an empty range)
     sphb_params prm{};
     bool have_params = false, planned = false;
     float a0[3] = {0.0f, 0.0f, 0.0f};
     uint64_t step_count = 0;
     std::vector<uint64_t> owned, ghosts;      // per device, after the last exchange (before the first: the uploaded shares)
+    std::vector<float> h_mass;                // per-particle masses as uploaded (empty: the default mass) — needed to re-cut the slabs
+    bool want_rebalance = false;              // the last exchange left the devices unbalanced: re-cut before the next step
+    uint64_t rebalances = 0;
+    uint64_t rebalance_min = 32768;           // ... and at least this many particles above it (SPHB_OPT_MULTI_REBALANCE_MIN)
     std::string err;
 };
 
 namespace {
 
-constexpr int kLayers = 2;
+constexpr int kLayers = 2;   // halo layers per face (SPHB_OPT_MULTI_HALO_LAYERS overrides: wider halos for diagnosis)
 
 int mfail(sphb_multi* m, int code, const char* fmt, ...) {
     char buf[512];
@@ -157,6 +162,41 @@ thread_local std::string g_create_error;
 
 }  // namespace
 
+extern "C" int sphb_multi_upload(sphb_multi* m, size_t n, const float* pos3, const float* vel3, const float* mass);
+extern "C" int sphb_multi_download(sphb_multi* m, float* pos3, float* vel3, float* rho, float* pressure, float* acc3);
+
+namespace {
+
+// Re-cut the slabs for the CURRENT positions (one round trip of positions and velocities through the host; rare — only
+// when the flow has left one device with 1.5x its even share).  Results do not depend on where the cuts are (every step
+// re-sorts owned + halo particles by (cell, global id)); time, step count and the adaptive-dt state are carried over.
+int rebalance(sphb_multi* m) {
+    const size_t n = m->n_total;
+    std::vector<float> p(3 * n), v(3 * n);
+    int rc = sphb_multi_download(m, p.data(), v.data(), nullptr, nullptr, nullptr);
+    if (rc != SPHB_OK) return rc;
+    float t = 0.0f;
+    MCTX(m, m->ndev - 1, sphb_get_time(m->ctx[(size_t)m->ndev - 1], &t, nullptr));
+    float a0[3] = {m->a0[0], m->a0[1], m->a0[2]};
+    for (int d = 0; d < m->ndev; ++d) {   // the acceleration of particle 0 lives on the device that advanced it last
+        float v2 = 0.0f, a[3] = {0.0f, 0.0f, 0.0f};
+        int fresh = 0;
+        MCTX(m, d, sphb_get_cfl_state(m->ctx[d], &v2, a, &fresh));
+        if (fresh) { a0[0] = a[0]; a0[1] = a[1]; a0[2] = a[2]; }
+    }
+    const uint64_t steps = m->step_count, reb = m->rebalances;
+    rc = sphb_multi_upload(m, n, p.data(), v.data(), m->h_mass.empty() ? nullptr : m->h_mass.data());
+    if (rc != SPHB_OK) return rc;
+    for (int d = 0; d < m->ndev; ++d) MCTX(m, d, sphb_set_time(m->ctx[d], t, steps));
+    m->step_count = steps;
+    m->a0[0] = a0[0]; m->a0[1] = a0[1]; m->a0[2] = a0[2];
+    m->rebalances = reb + 1;
+    m->want_rebalance = false;
+    return SPHB_OK;
+}
+
+}  // namespace
+
 extern "C" {
 
 const char* sphb_multi_last_error(const sphb_multi* m) { return m ? m->err.c_str() : g_create_error.c_str(); }
@@ -226,6 +266,16 @@ int sphb_multi_device_count(const sphb_multi* m) { return m ? m->ndev : 0; }
 
 int sphb_multi_set_option(sphb_multi* m, int option, int64_t value) {
     if (!m) return SPHB_E_INVALID;
+    if (option == SPHB_OPT_MULTI_HALO_LAYERS) {
+        if (value < 2 || value > 8) return mfail(m, SPHB_E_INVALID, "halo layers must be 2..8");
+        m->layers = (int)value;
+        return SPHB_OK;
+    }
+    if (option == SPHB_OPT_MULTI_REBALANCE_MIN) {
+        if (value < 0) return mfail(m, SPHB_E_INVALID, "rebalance threshold must be >= 0");
+        m->rebalance_min = (uint64_t)value;
+        return SPHB_OK;
+    }
     if (option == SPHB_OPT_MULTI_AXIS) {
         if (value < -1 || value > 2) return mfail(m, SPHB_E_INVALID, "slab axis must be -1 (automatic), 0, 1 or 2");
         m->axis = (int)value;
@@ -263,6 +313,8 @@ int sphb_multi_upload(sphb_multi* m, size_t n, const float* pos3, const float* v
         for (int d = 0; d < m->ndev; ++d) MCTX(m, d, sphb_upload_ids(m->ctx[d], 0, nullptr, nullptr, nullptr, nullptr));
         return SPHB_OK;
     }
+    if (mass) { if (mass != m->h_mass.data()) m->h_mass.assign(mass, mass + n); } else m->h_mass.clear();
+    m->want_rebalance = false;
     float bmin[3] = {pos3[0], pos3[1], pos3[2]}, bmax[3] = {pos3[0], pos3[1], pos3[2]};
     for (size_t i = 0; i < n; ++i)
         for (int a = 0; a < 3; ++a) {
@@ -279,7 +331,7 @@ int sphb_multi_upload(sphb_multi* m, size_t n, const float* pos3, const float* v
     const float inv = 1.0f / m->prm.neighbor_search_radius;
     std::vector<int> cells(n);
     for (size_t i = 0; i < n; ++i) cells[i] = ref_cell(pos3[3 * i + axis], inv);
-    m->active = plan_cuts(cells, m->ndev, kLayers, &m->cuts);
+    m->active = plan_cuts(cells, m->ndev, m->layers, &m->cuts);
     const float lo[3] = {std::min(bmin[0], m->prm.xmin), std::min(bmin[1], m->prm.ymin), std::min(bmin[2], m->prm.zmin)};
     const float hi[3] = {std::max(bmax[0], m->prm.xmax), std::max(bmax[1], m->prm.ymax), std::max(bmax[2], m->prm.zmax)};
     std::vector<std::vector<uint32_t>> mine((size_t)m->ndev);
@@ -297,7 +349,7 @@ int sphb_multi_upload(sphb_multi* m, size_t n, const float* pos3, const float* v
             if (mass) ms[j] = mass[i];
         }
         sphb_slab sl;
-        sl.axis = axis; sl.own_lo = m->cuts[(size_t)d]; sl.own_hi = m->cuts[(size_t)d + 1]; sl.halo_layers = kLayers;
+        sl.axis = axis; sl.own_lo = m->cuts[(size_t)d]; sl.own_hi = m->cuts[(size_t)d + 1]; sl.halo_layers = m->layers;
         sl.id_space = std::max<uint64_t>(m->capacity, 2);
         for (int a = 0; a < 3; ++a) { sl.box_min[a] = lo[a]; sl.box_max[a] = hi[a]; }
         MCTX(m, d, sphb_set_slab(m->ctx[d], &sl));
@@ -315,6 +367,10 @@ int sphb_multi_step(sphb_multi* m, float dt) {
     const int G = m->ndev;
     if (G == 1) { MCTX(m, 0, sphb_step(m->ctx[0], dt)); m->step_count++; return SPHB_OK; }
     if (!m->planned) return mfail(m, SPHB_E_INVALID, "no particles uploaded");
+    if (m->want_rebalance) {
+        const int rc = rebalance(m);
+        if (rc != SPHB_OK) return rc;
+    }
     const int32_t* cuts = m->cuts.data();
     // count: enqueue on every device, then ONE host wait for all of them
     for (int d = 0; d < G; ++d) {
@@ -353,6 +409,12 @@ int sphb_multi_step(sphb_multi* m, float dt) {
             return mfail(m, SPHB_E_CAPACITY, "device %d would hold %llu particles and halo copies, more than its share (%zu)", m->devs[dst],
                          (unsigned long long)(own + gh), m->cap_ctx);
         if (off > m->xcap) return mfail(m, SPHB_E_CAPACITY, "device %d receives %zu records, more than the exchange buffer (%zu)", m->devs[dst], off, m->xcap);
+    }
+    {   // load balance: the cuts were planned for the uploaded positions; re-cut when one device holds 1.5x its even share
+        uint64_t most = 0;
+        for (int d = 0; d < G; ++d) most = std::max(most, m->owned[(size_t)d]);
+        const uint64_t even = m->n_total / (uint64_t)std::max(1, m->active);
+        if (most * 2 > even * 3 && most > even + m->rebalance_min) m->want_rebalance = true;
     }
     for (int src = 0; src < G; ++src) {
         MCU(m, cudaSetDevice(m->devs[src]));

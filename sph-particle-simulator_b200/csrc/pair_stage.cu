@@ -111,6 +111,13 @@ __global__ void __launch_bounds__(kThreadsS, SPHB_DSTAGE_MINBLOCKS) k_density_st
     }
     __syncthreads();
     unsigned count = 0;
+#ifdef SPHB_POISON_UNWANTED
+    if (SLAB && !want && i_raw < a.n) {   // debug build: the records of particles whose density is not evaluated here must never be read
+        const float4 v = a.velid[i];
+        a.fa[i] = make_float4(pi.x, pi.y, pi.z, __int_as_float(0x7fc00000));
+        a.fb[i] = make_float4(v.x, v.y, v.z, __int_as_float(0x7fc00000));
+    }
+#endif
     if (__any_sync(0xffffffffu, want)) {   // slab mode: whole warps of outer-halo particles leave here
         const uint32_t c = center_cell(a.grid, pi);
         const uint32_t* __restrict__ cs = pin(a.cell_start);

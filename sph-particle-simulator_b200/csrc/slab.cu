@@ -20,9 +20,10 @@ constexpr unsigned kFull = 0xffffffffu;
 
 inline unsigned blocks_for(size_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
 
-__device__ __forceinline__ int axis_cell(const float4& p, int axis, float ref_inv_cell) {
+// position on the slab axis in units of reference cells; its floor is the reference cell (spatial_hash.h:30-36)
+__device__ __forceinline__ float axis_scaled(const float4& p, int axis, float ref_inv_cell) {
     const float c = axis == 0 ? p.x : (axis == 1 ? p.y : p.z);
-    return __float2int_rd(__fmul_rn(c, ref_inv_cell));
+    return __fmul_rn(c, ref_inv_cell);
 }
 
 // destination rank of a reference cell: the interval [cuts[d], cuts[d+1]) containing it (clamped to the ends)
@@ -67,7 +68,11 @@ __global__ void __launch_bounds__(kThreads) k_slab_export(size_t n, const float4
     float4 v;
     if (s < n) {
         v = velid[s];
+#ifdef SPHB_DEBUG_EXPORT_GHOSTS   // debug builds only (tools/debug): halo copies are exported too, their ids keep bit 31
+        key = 0;
+#else
         if (!(__float_as_uint(v.w) & kGhostBit)) key = 0;
+#endif
     }
     const size_t k = grouped_slot(key, cursor);
     if (key < 0) return;
@@ -93,11 +98,23 @@ __global__ void __launch_bounds__(kThreads) k_pack_upload_ids(size_t n, const fl
 // to each adjacent rank whose halo layers contain its cell.  Keys: 2*r = "owned by r", 2*r+1 = "ghost for r".
 struct Route { int owner, ghost_lo, ghost_hi; };   // ranks; -1 = none
 
-__device__ __forceinline__ Route route_of(const SlabCuts& sc, int cell, int layers) {
+// A neighbour needs the particles of `layers` reference cells beyond its face — and a sliver more: the refined internal
+// cells are 0.1 % larger than neighbor_search_radius / refine (make_grid), so the stencil walk of a first-layer halo
+// particle reaches up to 0.002 cells past the last layer.  Candidates there are always rejected by the radius test, but
+// the packed density pass splits its sum over even / odd candidates of a run, so a rejected candidate at the start of a
+// run still decides which partial sum its successors enter: without the sliver a halo particle's density could differ
+// from the single-context one in the last bit once particles drift off the lattice planes.  kHaloSliver = 1/64 cell.
+#ifndef SPHB_HALO_SLIVER
+#define SPHB_HALO_SLIVER 0.015625f
+#endif
+constexpr float kHaloSliver = SPHB_HALO_SLIVER;
+
+__device__ __forceinline__ Route route_of(const SlabCuts& sc, float scaled, int layers) {
     Route r;
+    const int cell = __float2int_rd(scaled);
     r.owner = dest_of(sc, cell);
-    r.ghost_lo = (r.owner > 0 && cell < sc.cuts[r.owner] + layers) ? r.owner - 1 : -1;
-    r.ghost_hi = (r.owner < sc.nranks - 1 && cell >= sc.cuts[r.owner + 1] - layers) ? r.owner + 1 : -1;
+    r.ghost_lo = (r.owner > 0 && scaled < (float)(sc.cuts[r.owner] + layers) + kHaloSliver) ? r.owner - 1 : -1;
+    r.ghost_hi = (r.owner < sc.nranks - 1 && scaled >= (float)(sc.cuts[r.owner + 1] - layers) - kHaloSliver) ? r.owner + 1 : -1;
     return r;
 }
 
@@ -111,7 +128,7 @@ __global__ void __launch_bounds__(kThreads) k_exchange_count(size_t n, const flo
                                                              float ref_inv_cell, int layers, unsigned int* __restrict__ counts) {
     const size_t s = (size_t)blockIdx.x * kThreads + threadIdx.x;
     Route r = {-1, -1, -1};
-    if (s < n && !(__float_as_uint(velid[s].w) & kGhostBit)) r = route_of(sc, axis_cell(posm[s], axis, ref_inv_cell), layers);
+    if (s < n && !(__float_as_uint(velid[s].w) & kGhostBit)) r = route_of(sc, axis_scaled(posm[s], axis, ref_inv_cell), layers);
     grouped_count(r.owner >= 0 ? 2 * r.owner : -1, counts);
     grouped_count(r.ghost_lo >= 0 ? 2 * r.ghost_lo + 1 : -1, counts);
     grouped_count(r.ghost_hi >= 0 ? 2 * r.ghost_hi + 1 : -1, counts);
@@ -129,7 +146,7 @@ __global__ void __launch_bounds__(kThreads) k_exchange_split(size_t n, const flo
         v = velid[s];
         if (!(__float_as_uint(v.w) & kGhostBit)) {
             p = posm[s];
-            r = route_of(sc, axis_cell(p, axis, ref_inv_cell), layers);
+            r = route_of(sc, axis_scaled(p, axis, ref_inv_cell), layers);
         }
     }
     const int k0 = r.owner >= 0 ? 2 * r.owner : -1;

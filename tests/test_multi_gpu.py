@@ -193,3 +193,82 @@ def test_multi_one_device_is_the_plain_context(pkg):
     ctx.close()
     for f in ("pos", "vel", "rho", "P", "acc"):
         assert_bits(got[f], want[f], f)
+
+
+def test_fast_mode_halo_sliver(pkg):
+    """Fast mode: a first-layer halo particle's stencil walk reaches 0.2 % of a cell past the second halo layer (the refined
+    internal cells are 0.1 % larger than neighbor_search_radius / refine).  Candidates there are always rejected, but the
+    packed density pass splits its sum over even / odd candidates of a run, so a rejected candidate at the START of a run
+    decides the rounding of the halo particle's density and, through it, of the forces on the owned particles next to
+    it.  The exchange therefore ships a sliver beyond the last layer (csrc/slab.cu kHaloSliver).  Reproduced with the cut
+    at z = 0: the lattice plane two cells below the cut is pushed 0.001 cells further down (third layer, but inside the
+    reach of the refined stencil of the plane one cell below the cut), the plane at 1.75 cells is moved into the same
+    internal cells (accepted neighbours of that halo plane, interleaved with the absent particles in its runs), and the
+    plane one cell below is lifted to 0.80 cells so that it exerts sizeable forces on the owned planes above the cut.  Without
+    the sliver some of the upper slab's first-layer accelerations differ in the last bit (the test fails on such a build:
+    tools/gpu_jobs/r3m.sh)."""
+    from sph_b200 import scenes
+    capi = pkg.capi
+    pos, mass, prm, dt = scenes.dam_break_scene(0.02)
+    nsr = np.float32(prm["neighbor_search_radius"])
+    pos = pos.copy()
+    z = pos[:, 2] / nsr
+    two_below, one_below, between = np.abs(z + 2.0) < 1e-4, np.abs(z + 1.0) < 1e-4, np.abs(z + 1.75) < 1e-4
+    assert two_below.sum() > 100 and one_below.sum() > 100 and between.sum() > 100
+    pos[two_below, 2] -= np.float32(1e-3) * nsr     # third layer, absent from the upper slab without the sliver
+    pos[between, 2] -= np.float32(0.01) * nsr       # accepted neighbours of the lifted plane that share internal cells (runs) with them
+    pos[one_below, 2] += np.float32(0.20) * nsr     # first-layer halo of the upper slab, 0.8 cells below the cut
+    rng = np.random.default_rng(3)
+    pos[:, :2] += (rng.uniform(-1, 1, size=(len(pos), 2)) * 1e-4).astype(np.float32)   # off the exact q = 2 ties in x, y
+    m = pkg.MultiContext(len(pos), [0, 0])
+    m.set_option(capi.OPT_MATH_MODE, capi.MATH_FAST)
+    m.set_option(capi.OPT_MULTI_AXIS, 2)
+    m.set_params(prm)
+    m.upload(pos, None, mass)
+    for _ in range(3):
+        m.step(dt)
+    got = m.download()
+    assert m.layout()["cuts"].tolist()[1] == 0
+    m.close()
+    want = single_run(pkg, prm, pos, None, mass, dt, 3, False, 2)
+    for f in ("rho", "acc", "pos", "vel"):
+        assert_bits(got[f], want[f], f)
+
+
+def test_multi_rebalances_when_the_flow_piles_up(pkg):
+    """Everything streams towards one face of the slab axis: one device ends up with (almost) all particles, the engine
+    re-cuts the slabs for the current positions (threshold lowered so that the 600-particle cloud triggers it) and the
+    results stay those of the single context bit for bit — adaptive dt included, whose particle-0 state is carried over."""
+    g = load_golden("cloud600")
+    params = {k: float(v) for k, v in params_from(g["params"]).items()}
+    vel = g["vel"].copy()
+    vel[:, 2] = 30.0
+    capi = pkg.capi
+    m = pkg.MultiContext(600, [0, 0])
+    m.set_option(capi.OPT_MATH_MODE, capi.MATH_STRICT)
+    m.set_option(capi.OPT_MULTI_AXIS, 2)
+    m.set_option(capi.OPT_MULTI_REBALANCE_MIN, 0)
+    m.set_params(params)
+    m.upload(g["pos"], vel, g["mass"])
+    cuts0 = m.layout()["cuts"].copy()
+    moved = False
+    for k in range(14):
+        m.step(1e-3 if k % 3 else 0.0)
+        moved = moved or not np.array_equal(m.layout()["cuts"], cuts0)
+    got = m.download()
+    t_multi = m.get_time()
+    lay = m.layout()
+    m.close()
+    assert moved, "the slabs were never re-cut"
+    assert int(lay["owned"].sum()) == 600 and lay["owned"].min() > 100          # balanced again
+    ctx = pkg.Context(600, 0)
+    ctx.set_option(capi.OPT_MATH_MODE, capi.MATH_STRICT)
+    ctx.set_params(params)
+    ctx.upload(g["pos"], vel, g["mass"])
+    for k in range(14):
+        ctx.step(1e-3 if k % 3 else 0.0)
+    want = ctx.download()
+    assert t_multi == ctx.get_time()
+    ctx.close()
+    for f in ("pos", "vel", "rho", "P", "acc"):
+        assert_bits(got[f], want[f], f"after re-cutting: {f}")

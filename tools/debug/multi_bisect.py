@@ -19,7 +19,8 @@ dx = scenes.dam_break_dx_for(G * scenes.dam_break_count(dx), dx / G ** (1.0 / 3.
 pos, mass, params, dt = scenes.dam_break_scene(dx)
 n = len(pos)
 refine = int(max(1, min(6, round(float(params["neighbor_search_radius"]) / dx))))
-m = pkg.MultiContext(n, devices); m.set_option(capi.OPT_GRID_REFINE, refine); m.set_params(params); m.upload(pos, None, mass)
+import os
+m = pkg.MultiContext(n, devices); m.set_option(capi.OPT_GRID_REFINE, refine); m.set_option(capi.OPT_MULTI_HALO_LAYERS, int(os.environ.get("LAYERS", "2"))); m.set_params(params); m.upload(pos, None, mass)
 one = pkg.Context(n, devices[0]); one.set_option(capi.OPT_GRID_REFINE, refine); one.set_option(capi.OPT_LAYOUT_MAJOR, 2); one.set_params(params); one.upload(pos, None, mass)
 nsr = float(params["neighbor_search_radius"])
 done = 0
