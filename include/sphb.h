@@ -125,7 +125,14 @@ enum {
      * buffers; no stage timing, no debug capture) are replayed from a CUDA graph — one launch call per step instead of
      * nine, which is what the step time of small scenes (the reference's own 1 000 - 10 000 particle benchmarks) consists
      * of.  Results are identical: the graph holds the very same kernels.  0 = always launch directly. */
-    SPHB_OPT_STEP_GRAPHS = 10
+    SPHB_OPT_STEP_GRAPHS = 10,
+    /* fast mode, pair kernel 2, internal walk radius >= 4: lanes that share one particle in the density and force passes
+     * (1 = default, 2, 4, 8).  With one thread per particle a SMALL scene (the reference's own drivers run 1 000 - 20 000
+     * particles) is bound by the serial neighbour walk of a single thread while most of the GPU idles; with L lanes the
+     * column groups of a particle are dealt to L lanes and the partial sums meet in shuffle reductions (pair_split.cu).
+     * Same neighbour sets and per-pair arithmetic; the per-particle sums are associated differently (fast-mode
+     * tolerances).  The host shell selects 8 for particle sets of up to 16 384 and 4 up to 131 072. */
+    SPHB_OPT_LANES_PER_PARTICLE = 11
 };
 
 /* ---- lifetime ---------------------------------------------------------------------------------

@@ -37,6 +37,7 @@ OPT_LAYOUT_MAJOR = 7
 OPT_PAIR_MODE = 8
 OPT_KERNEL_TYPE = 9
 OPT_STEP_GRAPHS = 10
+OPT_LANES_PER_PARTICLE = 11
 KERNEL_CUBIC_SPLINE, KERNEL_WENDLAND_C2, KERNEL_GAUSSIAN = 0, 1, 2
 OPT_MULTI_AXIS = 100
 OPT_MULTI_HALO_LAYERS = 101

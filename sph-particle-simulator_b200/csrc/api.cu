@@ -20,7 +20,7 @@ using namespace sphb;
 
 namespace {
 thread_local char g_create_error[512] = "";
-constexpr uint64_t kMaxCells = 1ull << 28;
+constexpr uint64_t kMaxCells = 1ull << 30;   // dense cell table of up to 4 GB (a 100 M-particle scene on one GPU needs 3.1e8 internal cells)
 constexpr int kMaxCoord = 1 << 20;  // |cell coordinate| limit for an injective reference key
 }  // namespace
 
@@ -41,6 +41,7 @@ struct sphb_ctx {
     int pair_mode = 2;       // R >= 4 mask kernels: 0 = per-lane global loads (pair_mask.cu), 1 = shared-memory staged (pair_stage.cu), 2 = staged density pass + per-lane force pass
     int layout_major = 0;    // fast-mode layout: physical axis that is most significant in the cell order (slab mode: the slab axis)
     int grid_refine = 4;     // internal cell = neighbor_search_radius / grid_refine (fast mode; strict always 1)
+    int lanes = 1;           // SPHB_OPT_LANES_PER_PARTICLE: lanes sharing one particle in the bitmask pair kernels (small scenes)
     int kernel_type = 0;     // SPHB_OPT_KERNEL_TYPE: 0 cubic spline (what SPHEngine constructs), 1 Wendland C2, 2 Gaussian
 
     float4* posm[2] = {nullptr, nullptr};
@@ -481,6 +482,10 @@ int sphb_set_option(sphb_ctx* c, int option, int64_t value) {
         case SPHB_OPT_STEP_GRAPHS:
             c->use_graphs = value ? 1 : 0;
             return SPHB_OK;
+        case SPHB_OPT_LANES_PER_PARTICLE:
+            if (value != 1 && value != 2 && value != 4 && value != 8) return fail(c, SPHB_E_INVALID, "lanes per particle must be 1, 2, 4 or 8");
+            c->lanes = (int)value;
+            return SPHB_OK;
         case SPHB_OPT_KERNEL_TYPE:
             if (value < 0 || value > 2) return fail(c, SPHB_E_INVALID, "kernel type must be 0 (cubic spline), 1 (Wendland C2) or 2 (Gaussian)");
             c->kernel_type = (int)value;
@@ -503,6 +508,7 @@ int sphb_get_option(const sphb_ctx* c, int option, int64_t* value) {
         case SPHB_OPT_PAIR_MODE: *value = c->pair_mode; return SPHB_OK;
         case SPHB_OPT_KERNEL_TYPE: *value = c->kernel_type; return SPHB_OK;
         case SPHB_OPT_STEP_GRAPHS: *value = c->use_graphs; return SPHB_OK;
+        case SPHB_OPT_LANES_PER_PARTICLE: *value = c->lanes; return SPHB_OK;
         default: return SPHB_E_INVALID;
     }
 }
@@ -797,7 +803,7 @@ int sphb_step(sphb_ctx* c, float dt) {
             dbg_sorted = o;
         }
 
-        PairArgs pa;
+        PairArgs pa{};
         pa.n = n;
         pa.posm = c->posm[outb];
         pa.velid = c->velid[outb];
@@ -817,6 +823,7 @@ int sphb_step(sphb_ctx* c, float dt) {
         pa.strict = c->math_mode == 0;
         pa.variant = variant;
         pa.kernel_type = c->kernel_type;
+        pa.lanes = split ? c->lanes : 1;
         pa.mode = mode;
         pa.slab_axis = c->slab_on ? c->slab.axis : -1;
         pa.rho_lo = c->slab_on ? c->slab.own_lo - 1 : 0;
@@ -849,7 +856,7 @@ int sphb_step(sphb_ctx* c, float dt) {
     if (graph_ok) {
         StepKey key;
         key.add(n); key.add(dt); key.add(in); key.add(st); key.add(g); key.add(pk); key.add(ic);
-        key.add(variant); key.add(mode); key.add(refine); key.add(c->walk_radius); key.add(c->math_mode); key.add(c->kernel_type);
+        key.add(variant); key.add(mode); key.add(c->lanes); key.add(refine); key.add(c->walk_radius); key.add(c->math_mode); key.add(c->kernel_type);
         key.add(c->slab_on ? c->slab.axis : -1); key.add(c->slab_on ? c->slab.own_lo : 0); key.add(c->slab_on ? c->slab.own_hi : 0);
         key.add(c->posm[0]); key.add(c->posm[1]); key.add(c->velid[0]); key.add(c->velid[1]); key.add(c->rho_p); key.add(c->acc);
         key.add(c->fa); key.add(c->fb); key.add(c->fab); key.add(c->masks); key.add(c->mask_stride); key.add(c->cell_start);

@@ -10,7 +10,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
 OBJ="$HERE/build"
 mkdir -p "$OBJ"
 pids=()
-for f in api scan_sort neighbor pair pair_mask pair_mask_wide pair_stage integrate slab multi; do
+for f in api scan_sort neighbor pair pair_mask pair_mask_wide pair_stage pair_split integrate slab multi; do
   if [ ! -f "$OBJ/$f.o" ] || [ "$HERE/$f.cu" -nt "$OBJ/$f.o" ] || [ -n "$(find "$HERE" "$ROOT/include" -maxdepth 1 \( -name '*.cuh' -o -name '*.h' \) -newer "$OBJ/$f.o" 2>/dev/null)" ]; then
     "$NVCC" "${FLAGS[@]}" -Xptxas -v -c "$HERE/$f.cu" -o "$OBJ/$f.o" 2> "$OBJ/$f.ptxas.log" &
     pids+=($!)
@@ -19,5 +19,5 @@ done
 rc=0
 for p in "${pids[@]:-}"; do [ -z "$p" ] || wait "$p" || rc=1; done
 if [ $rc -ne 0 ]; then cat "$OBJ"/*.ptxas.log | grep -E 'error|Error' -A3 >&2 || true; exit 1; fi
-"$NVCC" -shared -gencode arch=compute_100a,code=sm_100a -ccbin /usr/bin/g++ -o "$OUT" "$OBJ"/api.o "$OBJ"/scan_sort.o "$OBJ"/neighbor.o "$OBJ"/pair.o "$OBJ"/pair_mask.o "$OBJ"/pair_mask_wide.o "$OBJ"/pair_stage.o "$OBJ"/integrate.o "$OBJ"/slab.o "$OBJ"/multi.o
+"$NVCC" -shared -gencode arch=compute_100a,code=sm_100a -ccbin /usr/bin/g++ -o "$OUT" "$OBJ"/api.o "$OBJ"/scan_sort.o "$OBJ"/neighbor.o "$OBJ"/pair.o "$OBJ"/pair_mask.o "$OBJ"/pair_mask_wide.o "$OBJ"/pair_stage.o "$OBJ"/pair_split.o "$OBJ"/integrate.o "$OBJ"/slab.o "$OBJ"/multi.o
 echo "built $OUT"

@@ -285,6 +285,7 @@ size_t mask_bytes_per_slot(int R) {
 int launch_density_mask(const PairArgs& a, cudaStream_t st) {
     if (a.n == 0) return 0;
     if (a.walk_radius < 4) return launch_density_mask_wide(a, st);
+    if (a.lanes > 1) return launch_density_split(a, st);
     if (a.mode != 0) return launch_density_stage(a, st);
     const unsigned nb = (unsigned)((a.n + kThreads - 1) / kThreads);
     const bool slab = a.slab_axis >= 0;
@@ -307,6 +308,7 @@ int launch_density_mask(const PairArgs& a, cudaStream_t st) {
 int launch_force_mask(const PairArgs& a, cudaStream_t st) {
     if (a.n == 0) return 0;
     if (a.walk_radius < 4) return launch_force_mask_wide(a, st);
+    if (a.lanes > 1) return launch_force_split(a, st);
     if (a.mode == 1) return launch_force_stage(a, st);
     const unsigned nb = (unsigned)((a.n + kThreads - 1) / kThreads);
     const bool slab = a.slab_axis >= 0;

@@ -152,6 +152,7 @@ struct PairArgs {
     int walk_radius;
     int strict;
     int variant;
+    int lanes;                 // variant 2, R >= 4: lanes sharing one particle (1 = pair_mask.cu / pair_stage.cu; 2, 4, 8 = pair_split.cu)
     int kernel_type;           // kKernelCubic / kKernelWendlandC2 / kKernelGaussian (the latter two: tested-walk kernels only)
     int mode;                  // variant 2, R >= 4: 0 = pair_mask.cu, 1 = pair_stage.cu, 2 = staged density + per-lane force (SPHB_OPT_PAIR_MODE)
     // slab mode (slab_axis >= 0): density is evaluated for particles whose reference cell on the axis lies in
@@ -169,6 +170,8 @@ size_t mask_bytes_per_slot(int R);                  // bytes of mask storage per
 int stencil_reach_table(int R, signed char* out);   // host: copies the (2R+1)^2 column reaches, returns their number or -1
 int launch_density_mask(const PairArgs& a, cudaStream_t st);
 int launch_force_mask(const PairArgs& a, cudaStream_t st);
+int launch_density_split(const PairArgs& a, cudaStream_t st);       // R >= 4, a.lanes lanes per particle (pair_split.cu)
+int launch_force_split(const PairArgs& a, cudaStream_t st);
 int launch_density_stage(const PairArgs& a, cudaStream_t st);       // R >= 4, shared-memory staged (pair_stage.cu); -1: not configurable
 int launch_force_stage(const PairArgs& a, cudaStream_t st);
 int launch_density_mask_wide(const PairArgs& a, cudaStream_t st);   // R = 2, 3

@@ -360,6 +360,8 @@ void SPHEngine::push_params() const {
 void SPHEngine::push_to_device() const {
     if (!host_changed_) return;
     push_params();   // default-mass fallback of the ABI is not used: every record carries its mass
+    // device-side tuning only: small particle sets (the reference's own drivers) give each particle 8 or 4 lanes
+    DEV(set_option, SPHB_OPT_LANES_PER_PARTICLE, particles_.size() <= 16384 ? 8 : (particles_.size() <= 131072 ? 4 : 1));
     SPHB_CHECK(DEV(upload_strided, particles_.size(), particles_.data(), sizeof(Particle), offsetof(Particle, position),
                                    offsetof(Particle, velocity), offsetof(Particle, mass)));
     host_changed_ = false;

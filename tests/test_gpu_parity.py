@@ -538,6 +538,73 @@ def test_fast_mode_mask_overflow_falls_back(pkg, po, refine):
     ctx.close(); ora.close()
 
 
+@pytest.mark.parametrize("lanes", [2, 4, 8])
+@pytest.mark.parametrize("name", ["micro_pair", "micro_coincident", "micro_lattice27", "cloud600", "cloud600_truncated_support",
+                                  "dam_break_13k_tame"])
+def test_lanes_per_particle(pkg, name, lanes):
+    """SPHB_OPT_LANES_PER_PARTICLE (pair_split.cu, for small scenes): the column groups of a particle dealt to L lanes,
+    partial sums joined by shuffles.  Neighbour sets are those of the one-lane kernels (counts bit-exact against the
+    reference golden), fields inside the fast-mode gates against the reference and within summation-order noise of the
+    one-lane result; several steps stay inside the N-step gates."""
+    g = load_golden(name)
+    prm = params_from(g["params"])
+    n = g["pos"].shape[0]
+    L = float(max(prm["xmax"] - prm["xmin"], prm["ymax"] - prm["ymin"], prm["zmax"] - prm["zmin"]))
+    k0 = golden_steps(g)[0]
+    outs = {}
+    for ln in (1, lanes):
+        ctx = make_ctx(pkg, n, prm, strict=False, OPT_LANES_PER_PARTICLE=ln, OPT_PAIR_MODE=0)
+        assert ctx.get_option(pkg.capi.OPT_LANES_PER_PARTICLE) == ln
+        ctx.upload(g["pos"], g["vel"], g["mass"])
+        for k in range(k0 + 1):
+            ctx.step(float(g["dts"][k]))
+        outs[ln] = (ctx.download(), ctx.debug_dump(), ctx.stats()["max_neighbors"])
+        ctx.close()
+    got, dbg, mx = outs[lanes]
+    if k0 == 0:
+        assert_bits(dbg["nbr_count"], g["s0_counts"], f"{name} counts with {lanes} lanes per particle")
+    assert_bits(dbg["nbr_count"], outs[1][1]["nbr_count"], "counts vs one lane")
+    assert mx == outs[1][2]
+    check_fast(got, {f: g[f"s{k0}_{f}"] for f in ("rho", "P", "acc", "pos", "vel")}, L, f"{name} lanes={lanes}")
+    assert rel_err(got["rho"], outs[1][0]["rho"]) <= 2e-6
+    if n > 100:
+        assert not np.array_equal(got["acc"], outs[1][0]["acc"]), "the split kernels did not run (identical bits)"
+    amax = np.abs(outs[1][0]["acc"]).max()
+    if amax > 0:
+        assert np.abs(got["acc"].astype(np.float64) - outs[1][0]["acc"]).max() <= 2e-5 * amax
+
+
+@pytest.mark.parametrize("lanes", [4])
+def test_lanes_per_particle_overflow_and_steps(pkg, po, lanes):
+    """The mask-overflow fallback (collapsed cloud, > 2 000 neighbours) and ten consecutive steps with 4 lanes per particle."""
+    rng = np.random.default_rng(11)
+    prm = dict(pkg.DEFAULT_PARAMS)
+    prm.update(smoothing_length=0.05, neighbor_search_radius=0.1, gas_constant=1e-3, viscosity=1e-6, particle_mass=1e-4,
+               xmin=-1.0, xmax=1.0, ymin=-1.0, ymax=1.0, zmin=-1.0, zmax=1.0)
+    pos = np.concatenate([rng.uniform(-0.06, 0.06, size=(3000, 3)), rng.uniform(-0.9, 0.9, size=(3000, 3))]).astype(np.float32)
+    vel = rng.normal(0, 0.1, size=pos.shape).astype(np.float32)
+    mass = np.full(len(pos), prm["particle_mass"], np.float32)
+    ora = po.Engine("port", len(pos)); ora.initialize(prm); ora.add_particles(pos, vel, mass)
+    ctx = make_ctx(pkg, len(pos), prm, strict=False, OPT_LANES_PER_PARTICLE=lanes)
+    ctx.upload(pos, vel, mass)
+    ora.step(1e-4); ctx.step(1e-4)
+    assert_bits(ctx.debug_dump()["nbr_count"], ora.neighbor_counts(), "overflow counts")
+    check_fast(ctx.download(), ora.state(), 2.0, "overflow with 4 lanes per particle")
+    ctx.close(); ora.close()
+    from sph_b200 import scenes
+    pos, mass, prm, dt = scenes.dam_break_scene(0.02)
+    ora = po.Engine("port", len(pos)); ora.initialize(prm); ora.add_particles(pos, None, mass)
+    ctx = make_ctx(pkg, len(pos), prm, strict=False, OPT_LANES_PER_PARTICLE=lanes)
+    ctx.upload(pos, None, mass)
+    for _ in range(10):
+        ora.step(dt); ctx.step(dt)
+    want, fast = ora.state(), ctx.download()
+    assert rel_err(fast["rho"], want["rho"]) <= 10 * TOL_RHO
+    assert np.abs(fast["pos"].astype(np.float64) - want["pos"]).max() <= 10 * TOL_POS * 0.8
+    assert np.abs(fast["acc"].astype(np.float64) - want["acc"]).max() <= 10 * TOL_ACC * np.abs(want["acc"]).max()
+    ctx.close(); ora.close()
+
+
 def test_fast_mode_layout_major_axis(pkg):
     """SPHB_OPT_LAYOUT_MAJOR only permutes the device's cell order: neighbour sets, keys and the reference-order
     permutation are identical for every major axis, fields agree within the fast-mode gates, and the same axis twice

@@ -24,10 +24,11 @@ def device_lists():
     return lists
 
 
-def single_run(pkg, params, pos, vel, mass, dt, steps, strict, layout_major):
+def single_run(pkg, params, pos, vel, mass, dt, steps, strict, layout_major, lanes=1):
     capi = pkg.capi
     ctx = pkg.Context(len(pos), 0)
     ctx.set_option(capi.OPT_MATH_MODE, capi.MATH_STRICT if strict else capi.MATH_FAST)
+    ctx.set_option(capi.OPT_LANES_PER_PARTICLE, lanes)
     ctx.set_option(capi.OPT_LAYOUT_MAJOR, layout_major)
     ctx.set_params(params)
     ctx.upload(pos, vel, mass)
@@ -44,10 +45,11 @@ def single_run(pkg, params, pos, vel, mass, dt, steps, strict, layout_major):
     return out
 
 
-def multi_run(pkg, devices, params, pos, vel, mass, dt, steps, strict, axis=-1):
+def multi_run(pkg, devices, params, pos, vel, mass, dt, steps, strict, axis=-1, lanes=1):
     capi = pkg.capi
     m = pkg.MultiContext(len(pos), devices)
     m.set_option(capi.OPT_MATH_MODE, capi.MATH_STRICT if strict else capi.MATH_FAST)
+    m.set_option(capi.OPT_LANES_PER_PARTICLE, lanes)
     m.set_option(capi.OPT_MULTI_AXIS, axis)
     m.set_params(params)
     m.upload(pos, vel, mass)
@@ -272,3 +274,14 @@ def test_multi_rebalances_when_the_flow_piles_up(pkg):
     ctx.close()
     for f in ("pos", "vel", "rho", "P", "acc"):
         assert_bits(got[f], want[f], f"after re-cutting: {f}")
+
+
+def test_multi_with_lanes_per_particle(pkg):
+    """The small-scene kernels (4 lanes per particle) keep the slabs == single-context property: the association order of
+    a particle's sums depends on its column groups only, not on which device holds it."""
+    from sph_b200 import scenes
+    pos, mass, params, dt = scenes.dam_break_scene(0.02)
+    got = multi_run(pkg, [0, 0, 0], params, pos, None, mass, dt, 5, False, lanes=4)
+    want = single_run(pkg, params, pos, None, mass, dt, 5, False, got["layout"]["axis"], lanes=4)
+    for f in ("pos", "vel", "rho", "P", "acc"):
+        assert_bits(got[f], want[f], f)

@@ -7,7 +7,7 @@ SRC="$ROOT/sph-particle-simulator_b200/csrc"
 name=$1; shift 1
 mkdir -p "$ROOT/tune/obj"
 objs=(); pids=()
-for f in api scan_sort neighbor pair pair_mask pair_mask_wide pair_stage integrate slab multi; do
+for f in api scan_sort neighbor pair pair_mask pair_mask_wide pair_stage pair_split integrate slab multi; do
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-O2 -I"$ROOT/include" -I"$SRC" -ccbin /usr/bin/g++ \
        "$@" -Xptxas -v -c "$SRC/$f.cu" -o "$ROOT/tune/obj/${f}_$name.o" 2> "$ROOT/tune/obj/${f}_$name.log" &
   pids+=($!)
