@@ -399,6 +399,7 @@ int sphb_create(sphb_ctx** out, size_t capacity, int device) {
     c->device = device;
     c->capacity = capacity;
     if (const char* e = getenv("SPHB_PAIR_MODE")) { if (e[0] >= '0' && e[0] <= '2') c->pair_mode = e[0] - '0'; }   // A/B runs without touching the caller
+    if (const char* e = getenv("SPHB_LANES")) { if (e[0] == '1' || e[0] == '2' || e[0] == '4' || e[0] == '8') c->lanes = e[0] - '0'; }
     const size_t cap = capacity ? capacity : 1;
 #define CUC(call)                                                                                         \
     do {                                                                                                  \
