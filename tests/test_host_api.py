@@ -211,15 +211,22 @@ def test_headless_dam_break_example(tmp_path):
 
 
 @pytest.mark.gpu
-def test_headless_example_rows_match_the_reference(tmp_path, po):
-    """The first five CSV rows of the example (one device reduction per report) against what the reference program
+@pytest.mark.parametrize("devices", [None, "0,0"])
+def test_headless_example_rows_match_the_reference(tmp_path, po, devices):
+    """(devices = "0,0": the unchanged example program with SPHB_DEVICES exported — the engine owns two slabs.)
+    The first five CSV rows of the example (one device reduction per report) against what the reference program
     computes from full arrays (examples/dam_break.cpp:132-166): compute_conservation_errors, get_total_energy, the mean
     of the CAPACITY-long density buffer (quirk Q13) and max |v| — on the reference engine itself (strict build or the C
     port), same parameters, same 50 steps.  The scene explodes (reference defaults): rows agree while finite and turn
     non-finite together."""
     import subprocess
+    import os
+    env = dict(os.environ)
+    env.pop("SPHB_DEVICES", None)
+    if devices:
+        env["SPHB_DEVICES"] = devices
     out = subprocess.run([sys.executable, str(ROOT / "examples" / "dam_break_headless.py"), "10000", "0.05", str(tmp_path / "d.csv"), "--strict"],
-                         capture_output=True, text=True, timeout=300)
+                         capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
     rows = [r.split(",") for r in (tmp_path / "d.csv").read_text().splitlines()[1:]]
     assert len(rows) == 5
