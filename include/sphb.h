@@ -172,6 +172,13 @@ int sphb_upload_strided(sphb_ctx* ctx, size_t n, const void* base, size_t stride
  * acceleration belong to the last step: between an upload and the next step they read as zeros (the
  * reference would show its previous per-id buffers there). */
 int sphb_download(sphb_ctx* ctx, float* pos3, float* vel3, float* rho, float* pressure, float* acc3);
+/* The same download in two halves, for callers that stream: _begin un-permutes on the context's stream and starts the
+ * copies on a stream of the library's own, then returns; _end waits for them (a second _begin, or sphb_destroy, waits as
+ * well).  Whatever the caller enqueues in between — typically the NEXT sphb_upload, whose host-to-device copy runs on the
+ * other direction of the PCIe link — overlaps the transfer.  The arrays must stay valid (and should be pinned: pageable
+ * memory makes the copies synchronous) until _end.  No reference counterpart (its getters return host copies). */
+int sphb_download_begin(sphb_ctx* ctx, float* pos3, float* vel3, float* rho, float* pressure, float* acc3);
+int sphb_download_end(sphb_ctx* ctx);
 /* Write position/velocity/density/pressure back into an array-of-structs (byte offsets; pass
  * (size_t)-1 for a field to skip). */
 int sphb_download_strided(sphb_ctx* ctx, void* base, size_t stride, size_t off_pos, size_t off_vel,

@@ -49,7 +49,7 @@ MATH_FAST = 1
 ABI_SYMBOLS = (
     "sphb_create", "sphb_destroy", "sphb_last_error", "sphb_version", "sphb_set_option", "sphb_get_option",
     "sphb_set_stream", "sphb_synchronize", "sphb_set_params", "sphb_get_params", "sphb_upload",
-    "sphb_upload_strided", "sphb_download", "sphb_download_strided", "sphb_size", "sphb_step", "sphb_run_steps",
+    "sphb_upload_strided", "sphb_download", "sphb_download_begin", "sphb_download_end", "sphb_download_strided", "sphb_size", "sphb_step", "sphb_run_steps",
     "sphb_get_time", "sphb_set_time", "sphb_cfl_timestep", "sphb_get_stats", "sphb_reset_stats",
     "sphb_diagnostics", "sphb_set_colors", "sphb_export_instances", "sphb_debug_dump", "sphb_debug_stencil",
     "sphb_set_slab", "sphb_upload_ids", "sphb_slab_append", "sphb_slab_exchange_pack", "sphb_slab_exchange_count",
@@ -117,6 +117,8 @@ def load_library() -> C.CDLL:
     L.sphb_upload.argtypes = [vp, sz, vp, vp, vp]
     L.sphb_upload_strided.argtypes = [vp, sz, vp, sz, sz, sz, sz]
     L.sphb_download.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.sphb_download_begin.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.sphb_download_end.argtypes = [vp]
     L.sphb_download_strided.argtypes = [vp, vp, sz, sz, sz, sz, sz]
     L.sphb_size.argtypes = [vp, C.POINTER(sz)]
     L.sphb_step.argtypes = [vp, C.c_float]
@@ -274,6 +276,13 @@ class Context:
 
     def download_raw(self, pos_ptr=None, vel_ptr=None, rho_ptr=None, p_ptr=None, acc_ptr=None):
         self._ck(self.L.sphb_download(self.h, _ptr(pos_ptr), _ptr(vel_ptr), _ptr(rho_ptr), _ptr(p_ptr), _ptr(acc_ptr)))
+
+    def download_begin_raw(self, pos_ptr=None, vel_ptr=None, rho_ptr=None, p_ptr=None, acc_ptr=None):
+        """Starts the download into (pinned) host memory and returns; download_end() waits for it."""
+        self._ck(self.L.sphb_download_begin(self.h, _ptr(pos_ptr), _ptr(vel_ptr), _ptr(rho_ptr), _ptr(p_ptr), _ptr(acc_ptr)))
+
+    def download_end(self):
+        self._ck(self.L.sphb_download_end(self.h))
 
     def download_strided(self, base_ptr: int, stride: int, off_pos, off_vel, off_density, off_pressure):
         none = (1 << 64) - 1

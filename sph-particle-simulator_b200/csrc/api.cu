@@ -71,6 +71,20 @@ struct sphb_ctx {
     DeviceScalars* h_sc = nullptr;  // pinned mirror for read-back
     unsigned char* d_stage = nullptr;
     size_t stage_bytes = 0;
+    // sphb_upload: the host-to-device copies run on a stream of their own into a staging buffer of their own, so that they
+    // overlap whatever is still running on the context's stream (typically the previous step); only the pack kernel waits
+    float* d_in = nullptr;
+    size_t in_bytes = 0;
+    cudaStream_t in_stream = nullptr;
+    cudaEvent_t ev_in_done = nullptr, ev_in_free = nullptr;
+    bool in_used = false;
+    // sphb_download_begin / _end: un-permuted fields staged here and copied out on a stream of their own, so that the
+    // copy overlaps whatever the caller enqueues next (typically the next upload: PCIe is full duplex)
+    float* d_out = nullptr;
+    size_t out_bytes = 0;
+    cudaStream_t out_stream = nullptr;
+    cudaEvent_t ev_out_ready = nullptr, ev_out_done = nullptr;
+    bool out_pending = false;
     unsigned char* h_bounce = nullptr;  // pinned bounce buffer for the strided download
     size_t bounce_bytes = 0;
 
@@ -78,6 +92,7 @@ struct sphb_ctx {
     float box_min[3] = {0, 0, 0}, box_max[3] = {0, 0, 0};
     bool box_pending = false;  // box must be read back from the device (after an upload)
     int* d_box = nullptr;      // 6 ordered-int encoded floats
+    int* h_box = nullptr;      // pinned host copy, written by a kernel (fetch_box)
     bool stepped_since_upload = false;
     bool box_tracking = false;   // the last step's integrate kernel reduced the particle bounding box into d_box
 
@@ -185,9 +200,12 @@ float decode_ordered(int v) {
 
 int fetch_box(sphb_ctx* c) {
     if (!c->box_pending) return SPHB_OK;
-    int h[6];
-    CU(c, cudaMemcpyAsync(h, c->d_box, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    // written into pinned host memory by a kernel, not by a device-to-host copy: a copy would queue on the copy engine
+    // behind a read-back that is still in flight on another stream (sphb_download_begin) and stall the step behind it
+    if (!c->h_box) CU(c, cudaMallocHost(&c->h_box, 8 * sizeof(int)));
+    c->stats.kernel_launches += sphb::launch_box_to_host(c->d_box, c->h_box, c->stream);
     CU(c, cudaStreamSynchronize(c->stream));
+    const int* h = c->h_box;
     for (int a = 0; a < 3; ++a) {
         c->box_min[a] = decode_ordered(h[a]);
         c->box_max[a] = decode_ordered(h[3 + a]);
@@ -326,6 +344,14 @@ void free_all(sphb_ctx* c) {
     cudaSetDevice(c->device);
     for (auto& sg : c->graphs) if (sg.exec) { cudaGraphExecDestroy(sg.exec); sg.exec = nullptr; }
     if (c->capture_stream) { cudaStreamDestroy(c->capture_stream); c->capture_stream = nullptr; }
+    if (c->in_stream) { cudaStreamSynchronize(c->in_stream); cudaStreamDestroy(c->in_stream); c->in_stream = nullptr; }
+    if (c->ev_in_done) cudaEventDestroy(c->ev_in_done);
+    if (c->ev_in_free) cudaEventDestroy(c->ev_in_free);
+    cudaFree(c->d_in);
+    if (c->out_stream) { cudaStreamSynchronize(c->out_stream); cudaStreamDestroy(c->out_stream); c->out_stream = nullptr; }
+    if (c->ev_out_ready) cudaEventDestroy(c->ev_out_ready);
+    if (c->ev_out_done) cudaEventDestroy(c->ev_out_done);
+    cudaFree(c->d_out);
     for (int i = 0; i < 2; ++i) {
         cudaFree(c->posm[i]); cudaFree(c->velid[i]); cudaFree(c->refkeys[i]); cudaFree(c->dbg_keys[i]); cudaFree(c->dbg_vals[i]);
     }
@@ -335,6 +361,7 @@ void free_all(sphb_ctx* c) {
     cudaFree(c->cell_start);
     cudaFree(c->sc); cudaFree(c->d_stage); cudaFree(c->d_box); cudaFree(c->d_counts); cudaFree(c->sort_scratch);
     if (c->h_sc) cudaFreeHost(c->h_sc);
+    if (c->h_box) cudaFreeHost(c->h_box);
     if (c->h_bounce) cudaFreeHost(c->h_bounce);
     for (auto& set : c->ev_pool) for (auto& e : set.e) if (e) cudaEventDestroy(e);
     c->ev_pool.clear();
@@ -580,19 +607,37 @@ int sphb_upload(sphb_ctx* c, size_t n, const float* pos3, const float* vel3, con
     if (n > 0 && !pos3) return fail(c, SPHB_E_INVALID, "pos3 is NULL");
     CU(c, cudaSetDevice(c->device));
     if (n == 0) return after_upload(c, 0);
-    int rc = ensure_stage(c, n * 7 * sizeof(float));
-    if (rc) return rc;
-    float* d_pos = reinterpret_cast<float*>(c->d_stage);
+    // The copies do not touch the particle state, so they need not wait for the work that is still queued on the context's
+    // stream (the previous step, a read-back in flight): they run on a stream of their own into their own staging buffer,
+    // and only the pack kernel — which replaces the state — is ordered behind both.
+    if (!c->in_stream) {
+        CU(c, cudaStreamCreateWithFlags(&c->in_stream, cudaStreamNonBlocking));
+        CU(c, cudaEventCreateWithFlags(&c->ev_in_done, cudaEventDisableTiming));
+        CU(c, cudaEventCreateWithFlags(&c->ev_in_free, cudaEventDisableTiming));
+    }
+    const size_t need = n * 7 * sizeof(float);
+    if (need > c->in_bytes) {
+        cudaFree(c->d_in);   // (synchronises the device: no copy into the old buffer is in flight afterwards)
+        c->d_in = nullptr; c->in_bytes = 0;
+        CU(c, cudaMalloc(&c->d_in, need));
+        c->in_bytes = need;
+    }
+    float* d_pos = c->d_in;
     float* d_vel = d_pos + 3 * n;
     float* d_mass = d_vel + 3 * n;
-    CU(c, cudaMemcpyAsync(d_pos, pos3, n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    if (vel3) CU(c, cudaMemcpyAsync(d_vel, vel3, n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    if (mass) CU(c, cudaMemcpyAsync(d_mass, mass, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    rc = reset_box_and_speed(c);
+    if (c->in_used) CU(c, cudaStreamWaitEvent(c->in_stream, c->ev_in_free, 0));   // the previous upload's pack kernel has read the buffer
+    CU(c, cudaMemcpyAsync(d_pos, pos3, n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->in_stream));
+    if (vel3) CU(c, cudaMemcpyAsync(d_vel, vel3, n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->in_stream));
+    if (mass) CU(c, cudaMemcpyAsync(d_mass, mass, n * sizeof(float), cudaMemcpyHostToDevice, c->in_stream));
+    CU(c, cudaEventRecord(c->ev_in_done, c->in_stream));
+    CU(c, cudaStreamWaitEvent(c->stream, c->ev_in_done, 0));
+    int rc = reset_box_and_speed(c);
     if (rc) return rc;
     c->stats.kernel_launches += launch_pack_upload(n, d_pos, vel3 ? d_vel : nullptr, mass ? d_mass : nullptr,
                                                    c->prm.particle_mass, c->posm[0], c->velid[0], c->sc, c->stream);
     c->stats.kernel_launches += launch_bbox(n, c->posm[0], c->d_box, c->stream);
+    CU(c, cudaEventRecord(c->ev_in_free, c->stream));
+    c->in_used = true;
     CU(c, cudaGetLastError());
     return after_upload(c, n);
 }
@@ -652,6 +697,64 @@ int sphb_download(sphb_ctx* c, float* pos3, float* vel3, float* rho, float* pres
     if (rho) CU(c, cudaMemcpyAsync(rho, d_rho, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     if (pressure) CU(c, cudaMemcpyAsync(pressure, d_P, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
+    return SPHB_OK;
+}
+
+int sphb_download_end(sphb_ctx* c) {
+    if (!c) return SPHB_E_INVALID;
+    if (!c->out_pending) return SPHB_OK;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaEventSynchronize(c->ev_out_done));
+    c->out_pending = false;
+    return SPHB_OK;
+}
+
+int sphb_download_begin(sphb_ctx* c, float* pos3, float* vel3, float* rho, float* pressure, float* acc3) {
+    if (!c) return SPHB_E_INVALID;
+    if (c->slab_on) return fail(c, SPHB_E_INVALID, "slab mode: ids are global, use sphb_slab_download");
+    CU(c, cudaSetDevice(c->device));
+    int rc = sphb_download_end(c);   // one transfer in flight: its staging buffer (and the caller's arrays) are reused
+    if (rc) return rc;
+    const size_t n = c->n;
+    if (n == 0) return SPHB_OK;
+    if (!c->out_stream) {
+        CU(c, cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking));
+        CU(c, cudaEventCreateWithFlags(&c->ev_out_ready, cudaEventDisableTiming));
+        CU(c, cudaEventCreateWithFlags(&c->ev_out_done, cudaEventDisableTiming));
+    }
+    const size_t need = n * 11 * sizeof(float);
+    if (need > c->out_bytes) {
+        cudaFree(c->d_out);
+        c->d_out = nullptr; c->out_bytes = 0;
+        CU(c, cudaMalloc(&c->d_out, need));
+        c->out_bytes = need;
+    }
+    float* d_pos = c->d_out;
+    float* d_vel = d_pos + 3 * n;
+    float* d_acc = d_vel + 3 * n;
+    float* d_rho = d_acc + 3 * n;
+    float* d_P = d_rho + n;
+    if (!c->stepped_since_upload) {   // see sphb_download
+        if (rho) memset(rho, 0, n * sizeof(float));
+        if (pressure) memset(pressure, 0, n * sizeof(float));
+        if (acc3) memset(acc3, 0, n * 3 * sizeof(float));
+        rho = nullptr; pressure = nullptr; acc3 = nullptr;
+        if (!pos3 && !vel3) return SPHB_OK;
+    }
+    c->stats.kernel_launches += launch_unpermute(n, c->posm[c->cur], c->velid[c->cur], c->rho_p, c->acc, nullptr, nullptr,
+                                                 pos3 ? d_pos : nullptr, vel3 ? d_vel : nullptr, rho ? d_rho : nullptr,
+                                                 pressure ? d_P : nullptr, acc3 ? d_acc : nullptr, nullptr, nullptr, nullptr,
+                                                 c->stream);
+    CU(c, cudaGetLastError());
+    CU(c, cudaEventRecord(c->ev_out_ready, c->stream));
+    CU(c, cudaStreamWaitEvent(c->out_stream, c->ev_out_ready, 0));
+    if (pos3) CU(c, cudaMemcpyAsync(pos3, d_pos, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->out_stream));
+    if (vel3) CU(c, cudaMemcpyAsync(vel3, d_vel, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->out_stream));
+    if (acc3) CU(c, cudaMemcpyAsync(acc3, d_acc, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->out_stream));
+    if (rho) CU(c, cudaMemcpyAsync(rho, d_rho, n * sizeof(float), cudaMemcpyDeviceToHost, c->out_stream));
+    if (pressure) CU(c, cudaMemcpyAsync(pressure, d_P, n * sizeof(float), cudaMemcpyDeviceToHost, c->out_stream));
+    CU(c, cudaEventRecord(c->ev_out_done, c->out_stream));
+    c->out_pending = true;
     return SPHB_OK;
 }
 

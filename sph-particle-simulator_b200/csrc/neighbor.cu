@@ -365,6 +365,18 @@ int launch_bbox(size_t n, const float4* posm, int* d_box, cudaStream_t st) {
     return 1;
 }
 
+// Six words from device memory into PINNED HOST memory, written by a kernel: a read-back that does not pass through a
+// copy engine, so it never queues behind a bulk transfer of another stream (sphb_download_begin) on that engine.
+namespace {
+__global__ void k_box_to_host(const int* __restrict__ d_box, volatile int* h_box) {
+    if (threadIdx.x < 6) h_box[threadIdx.x] = d_box[threadIdx.x];
+}
+}  // namespace
+int launch_box_to_host(const int* d_box, int* h_box_pinned, cudaStream_t st) {
+    k_box_to_host<<<1, 32, 0, st>>>(d_box, h_box_pinned);
+    return 1;
+}
+
 int launch_unpack_strided(size_t n, const unsigned char* d_base, size_t stride, size_t off_pos, size_t off_vel, size_t off_mass,
                           float4* posm, float4* velid, DeviceScalars* sc, cudaStream_t st) {
     if (n == 0) return 0;

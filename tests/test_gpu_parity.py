@@ -212,6 +212,41 @@ def test_step_graphs_replay_identical_steps(pkg, strict):
     assert a[-1] == b[-1]
 
 
+def test_download_begin_end_overlaps_the_next_upload(pkg):
+    """sphb_download_begin / _end: the read-back of one step may still be in flight while the next upload and step are
+    enqueued; every read-back equals the synchronous download of the same state, and a second _begin (or destroy) waits."""
+    import torch
+    from sph_b200 import scenes
+    pos, mass, prm, dt = scenes.dam_break_scene(0.02)
+    n = len(pos)
+    h_pos = torch.from_numpy(pos.copy()).pin_memory()
+    h_vel = torch.zeros((n, 3), dtype=torch.float32).pin_memory()
+    h_mass = torch.from_numpy(mass.copy()).pin_memory()
+    outs = [[torch.empty((n, 3), dtype=torch.float32).pin_memory(), torch.empty((n, 3), dtype=torch.float32).pin_memory(),
+             torch.empty((n,), dtype=torch.float32).pin_memory()] for _ in range(2)]
+    ctx = make_ctx(pkg, n, prm, strict=False)
+    ref = make_ctx(pkg, n, prm, strict=False)
+    for k in range(4):
+        h_pos[:, 1] += 1e-4                                   # a different input every cycle
+        ctx.upload_raw(n, h_pos.data_ptr(), h_vel.data_ptr(), h_mass.data_ptr())
+        ctx.step(dt)
+        o = outs[k % 2]
+        ctx.download_begin_raw(o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), None, None)
+        ref.upload_raw(n, h_pos.data_ptr(), h_vel.data_ptr(), h_mass.data_ptr())   # meanwhile: other work
+        ref.step(dt)
+        want = ref.download()
+        ctx.download_end()
+        assert_bits(o[0].numpy(), want["pos"], f"cycle {k} pos")
+        assert_bits(o[1].numpy(), want["vel"], f"cycle {k} vel")
+        assert_bits(o[2].numpy(), want["rho"], f"cycle {k} rho")
+    ctx.download_begin_raw(outs[0][0].data_ptr(), None, None, None, None)
+    ctx.download_begin_raw(outs[1][0].data_ptr(), None, None, None, None)       # waits for the first
+    assert_bits(outs[0][0].numpy(), ref.download()["pos"], "back-to-back begins")
+    ctx.close()                                               # waits for the second
+    assert_bits(outs[1][0].numpy(), ref.download()["pos"], "destroy waits for the transfer")
+    ref.close()
+
+
 def test_ten_steps_vs_oracle(pkg, po):
     """N-step parity on the 13k tame dam break: strict stays bit-exact; fast stays inside 10x the
     single-step gates (10 steps 10x looser)."""
