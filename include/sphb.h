@@ -160,7 +160,12 @@ int sphb_get_params(const sphb_ctx* ctx, sphb_params* p);
 /* ---- particle state ---------------------------------------------------------------------------
  * sphb_upload replaces ParticleSystem::clear + add_particles as seen by the hot path (reference
  * particle.cpp:22-39): the device state becomes exactly these n particles, id = index.
- * vel3 == NULL → zero velocities; mass == NULL → params.particle_mass for every particle. */
+ * vel3 == NULL → zero velocities; mass == NULL → params.particle_mass for every particle.
+ * The call returns once the work is enqueued.  The host-to-device copies run on a stream of the library's own, so
+ * they overlap whatever is still queued on the context's stream (the previous step, a read-back in flight); the
+ * kernel that installs the new state is ordered behind both.  Pinned arrays must stay valid until the context's
+ * stream has passed that kernel (sphb_synchronize, or any later synchronising call); pageable arrays are consumed
+ * before the call returns. */
 int sphb_upload(sphb_ctx* ctx, size_t n, const float* pos3, const float* vel3, const float* mass);
 /* Strided variant for an array-of-structs such as the reference's 76-byte sph::Particle
  * (particle.h:17-49): byte offsets of position[3], velocity[3], mass inside each record. */
