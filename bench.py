@@ -321,32 +321,45 @@ class Run:
         """The same metric through the host-buffer API: every step uploads its inputs from pinned host memory (H2D), steps, and
         reads pos / vel / rho back into pinned host memory (D2H).  One GPU: the read-back is started with sphb_download_begin and
         completes while the NEXT step's upload runs on the other direction of the PCIe link (sphb_download_end before its
-        buffers are reused and once after the loop, inside the timed region); slabs: synchronous sphb_slab_download."""
+        buffers are reused and once after the loop, inside the timed region); slabs: the same with sphb_upload_ids and
+        sphb_slab_download_begin / _end per rank."""
         ctx = self.ctx
-        piped = self.world == 1
+        held = [0]
 
         def cycle():
             self.upload()
             self.step()
-            if piped:
+            if self.world == 1:
                 ctx.download_begin_raw(self.o_pos.data_ptr(), self.o_vel.data_ptr(), self.o_rho.data_ptr(), None, None)
+            else:   # the owned count is known on the device only: min(capacity, particles held incl. halo copies) entries move
+                held[0] = ctx.size
+                ctx.slab_download_begin_raw(self.o_cap, self.o_ids.data_ptr(), self.o_pos.data_ptr(), self.o_vel.data_ptr(),
+                                            self.o_rho.data_ptr(), None, None)
+
+        def finish(check=False):
+            if self.world == 1:
+                ctx.download_end()
             else:
-                self.download()                # synchronises
+                got = ctx.slab_download_end()
+                assert not check or got == self.owned_now()
 
         for _ in range(2):
             cycle()
-        if piped:
-            ctx.download_end()
+        finish(check=True)
         self.barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
             cycle()
-        if piped:
-            ctx.download_end()
+        finish()
         self.torch.cuda.synchronize(self.dev)
         secs = self.allmax(time.perf_counter() - t0)
-        per = self.n_local * (12 + 12 + 4 + (4 if self.world > 1 else 0))
-        return dict(value=self.n_total * steps / secs / 1e6, h2d=per, d2h=per, steps=steps, piped=piped)
+        h2d = self.n_local * (12 + 12 + 4 + (4 if self.world > 1 else 0))
+        d2h = h2d if self.world == 1 else min(held[0], self.o_cap) * 32
+        return dict(value=self.n_total * steps / secs / 1e6, h2d=h2d, d2h=d2h, steps=steps, piped=True)
+
+    def owned_now(self):
+        """Owned particles of this rank after the last exchange (slab runs)."""
+        return int(self.sr.store.ctx.slab_download(pos=False, vel=False, rho=False, pressure=False, acc=False)["ids"].shape[0])
 
     def neighbour_stats(self):
         """Mean accepted neighbours per particle (self included) of one more step, from the per-particle counts."""
@@ -586,9 +599,10 @@ def run_ours(args):
                 "steps": e2e["steps"],
                 "what": ("sphb_upload(pinned host pos,vel,mass) + sphb_step + sphb_download_begin(pinned host pos,vel,rho) per step; the "
                          "read-back of step k completes (sphb_download_end) while the upload of step k+1 runs on the other direction of "
-                         "the PCIe link; every byte moves inside the timed region" if e2e.get("piped") else
-                         "sphb_upload(host pos,vel,mass) + sphb_step + sphb_slab_download(host ids,pos,vel,rho) per step per rank, slab "
-                         "exchange included")},
+                         "the PCIe link; every byte moves inside the timed region" if world == 1 else
+                         "per rank and step: sphb_upload_ids(pinned host pos,vel,mass,ids of the rank's particles) + slab exchange + "
+                         "sphb_step + sphb_slab_download_begin(pinned host ids,pos,vel,rho); the read-back of step k completes while "
+                         "the upload of step k+1 runs; every byte moves inside the timed region")},
         "gpu_launches": m["launches"],
         "clocks": m["clocks"],
         "roofline": roofline,

@@ -275,6 +275,11 @@ int sphb_slab_exchange_split(sphb_ctx* ctx, const int32_t* cuts, int nranks, int
                              size_t cap_records);
 /* Append records: ghost = -1 keeps each record's own flag (what the exchange delivers); 0 / 1 force owned / ghost. */
 int sphb_slab_append(sphb_ctx* ctx, const void* d_in, size_t count, int ghost);
+/* Helper of the exchange driver: a small DEVICE buffer (the gathered table of group sizes) into PINNED host memory, written
+ * by a kernel on the context's stream instead of a device-to-host copy — a copy would queue on the copy engine behind a
+ * bulk read-back that is still in flight (sphb_slab_download_begin) and hold the step up behind it.  Enqueue only: the
+ * caller synchronises the stream before reading.  bytes: a multiple of 4, at most 1 MiB. */
+int sphb_read_small(sphb_ctx* ctx, const void* d_src, void* h_dst_pinned, size_t bytes);
 /* Owned particles of this context in arbitrary order: ids[k] with the matching fields (host pointers,
  * any field may be NULL); *count = number written (<= cap). */
 /* Adaptive timestep across slabs: compute_cfl_timestep (reference sph_engine.cpp:312-333) needs the global
@@ -285,6 +290,12 @@ int sphb_get_cfl_state(sphb_ctx* ctx, float* max_v2, float* a0_xyz, int* a0_fres
 int sphb_set_cfl_state(sphb_ctx* ctx, float max_v2, const float* a0_xyz);
 int sphb_slab_download(sphb_ctx* ctx, size_t cap, uint32_t* ids, float* pos3, float* vel3, float* rho, float* pressure,
                        float* acc3, size_t* count);
+/* The same in two halves (see sphb_download_begin): _begin enqueues the export and the copies — min(cap, particles held
+ * incl. halo copies) entries per field, because the number of OWNED particles is only known on the device at that point —
+ * and returns; _end waits and reports how many leading entries are owned particles. */
+int sphb_slab_download_begin(sphb_ctx* ctx, size_t cap, uint32_t* ids, float* pos3, float* vel3, float* rho, float* pressure,
+                             float* acc3);
+int sphb_slab_download_end(sphb_ctx* ctx, size_t* count);
 
 /* ---- several GPUs of one node behind ONE handle (csrc/multi.cu) -----------------------------------------
  * "Multi-GPU: sphb_create_multi(ctx**, capacity, ndev, const int* devs) with the same calls".

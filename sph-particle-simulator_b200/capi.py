@@ -54,7 +54,7 @@ ABI_SYMBOLS = (
     "sphb_diagnostics", "sphb_set_colors", "sphb_export_instances", "sphb_debug_dump", "sphb_debug_stencil",
     "sphb_set_slab", "sphb_upload_ids", "sphb_slab_append", "sphb_slab_exchange_pack", "sphb_slab_exchange_count",
     "sphb_slab_exchange_split", "sphb_get_cfl_state", "sphb_set_cfl_state",
-    "sphb_slab_download",
+    "sphb_slab_download", "sphb_slab_download_begin", "sphb_slab_download_end", "sphb_read_small",
     "sphb_create_multi", "sphb_destroy_multi", "sphb_multi_last_error", "sphb_multi_device_count", "sphb_multi_set_option",
     "sphb_multi_set_params", "sphb_multi_upload", "sphb_multi_upload_strided", "sphb_multi_step", "sphb_multi_run_steps",
     "sphb_multi_synchronize", "sphb_multi_size", "sphb_multi_download", "sphb_multi_download_strided", "sphb_multi_get_time",
@@ -142,6 +142,9 @@ def load_library() -> C.CDLL:
     L.sphb_slab_exchange_split.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, sz]
     L.sphb_slab_append.argtypes = [vp, vp, sz, C.c_int]
     L.sphb_slab_download.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, C.POINTER(sz)]
+    L.sphb_slab_download_begin.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp]
+    L.sphb_slab_download_end.argtypes = [vp, C.POINTER(sz)]
+    L.sphb_read_small.argtypes = [vp, vp, vp, sz]
     L.sphb_create_multi.argtypes = [C.POINTER(vp), sz, C.c_int, C.POINTER(C.c_int)]
     L.sphb_destroy_multi.argtypes = [vp]
     L.sphb_destroy_multi.restype = None
@@ -399,6 +402,20 @@ class Context:
         self._ck(self.L.sphb_slab_download(self.h, cap, _ptr(out["ids"]), _ptr(out.get("pos")), _ptr(out.get("vel")),
                                            _ptr(out.get("rho")), _ptr(out.get("P")), _ptr(out.get("acc")), C.byref(n)))
         return {k: v[: n.value] for k, v in out.items()}
+
+    def slab_download_begin_raw(self, cap: int, ids_ptr, pos_ptr=None, vel_ptr=None, rho_ptr=None, p_ptr=None, acc_ptr=None):
+        """Starts the read-back of the owned particles into (pinned) host memory; slab_download_end() waits, returns their number."""
+        self._ck(self.L.sphb_slab_download_begin(self.h, int(cap), _ptr(ids_ptr), _ptr(pos_ptr), _ptr(vel_ptr), _ptr(rho_ptr), _ptr(p_ptr),
+                                                 _ptr(acc_ptr)))
+
+    def read_small(self, d_src_ptr: int, h_dst_pinned_ptr: int, nbytes: int):
+        """Enqueue a kernel-written read-back of a small device buffer into pinned host memory (see sphb_read_small)."""
+        self._ck(self.L.sphb_read_small(self.h, C.c_void_p(d_src_ptr), C.c_void_p(h_dst_pinned_ptr), int(nbytes)))
+
+    def slab_download_end(self) -> int:
+        n = C.c_size_t()
+        self._ck(self.L.sphb_slab_download_end(self.h, C.byref(n)))
+        return n.value
 
     def get_cfl_state(self):
         """(max |v|^2 over owned particles, a0[3], a0_fresh) — see sphb_get_cfl_state."""

@@ -85,6 +85,7 @@ struct sphb_ctx {
     cudaStream_t out_stream = nullptr;
     cudaEvent_t ev_out_ready = nullptr, ev_out_done = nullptr;
     bool out_pending = false;
+    size_t out_cap = 0;        // sphb_slab_download_begin: capacity of the caller's arrays
     unsigned char* h_bounce = nullptr;  // pinned bounce buffer for the strided download
     size_t bounce_bytes = 0;
 
@@ -601,43 +602,59 @@ int launch_bbox(size_t n, const float4* posm, int* d_box, cudaStream_t st);
 
 extern "C" {
 
+// Staging of an upload: the host-to-device copies do not touch the particle state, so they need not wait for the work that is
+// still queued on the context's stream (the previous step, a read-back in flight): they run on a stream of their own
+// (c->in_stream) into their own staging buffer (c->d_in), and only the kernel that installs the new state — enqueued by the
+// caller on the context's stream after stage_in_commit — is ordered behind both.
+static int stage_in_begin(sphb_ctx* c, size_t bytes) {
+    if (!c->in_stream) {
+        CU(c, cudaStreamCreateWithFlags(&c->in_stream, cudaStreamNonBlocking));
+        CU(c, cudaEventCreateWithFlags(&c->ev_in_done, cudaEventDisableTiming));
+        CU(c, cudaEventCreateWithFlags(&c->ev_in_free, cudaEventDisableTiming));
+    }
+    if (bytes > c->in_bytes) {
+        cudaFree(c->d_in);   // (synchronises the device: no copy into the old buffer is in flight afterwards)
+        c->d_in = nullptr; c->in_bytes = 0;
+        CU(c, cudaMalloc(&c->d_in, bytes));
+        c->in_bytes = bytes;
+    }
+    if (c->in_used) CU(c, cudaStreamWaitEvent(c->in_stream, c->ev_in_free, 0));   // the previous upload's kernels have read the buffer
+    return SPHB_OK;
+}
+static int stage_in_commit(sphb_ctx* c) {    // after the copies were enqueued on c->in_stream
+    CU(c, cudaEventRecord(c->ev_in_done, c->in_stream));
+    CU(c, cudaStreamWaitEvent(c->stream, c->ev_in_done, 0));
+    return SPHB_OK;
+}
+static int stage_in_release(sphb_ctx* c) {   // after the consuming kernels were enqueued on c->stream
+    CU(c, cudaEventRecord(c->ev_in_free, c->stream));
+    c->in_used = true;
+    return SPHB_OK;
+}
+
 int sphb_upload(sphb_ctx* c, size_t n, const float* pos3, const float* vel3, const float* mass) {
     if (!c) return SPHB_E_INVALID;
     if (n > c->capacity) return fail(c, SPHB_E_CAPACITY, "upload of %zu particles exceeds capacity %zu", n, c->capacity);
     if (n > 0 && !pos3) return fail(c, SPHB_E_INVALID, "pos3 is NULL");
     CU(c, cudaSetDevice(c->device));
     if (n == 0) return after_upload(c, 0);
-    // The copies do not touch the particle state, so they need not wait for the work that is still queued on the context's
-    // stream (the previous step, a read-back in flight): they run on a stream of their own into their own staging buffer,
-    // and only the pack kernel — which replaces the state — is ordered behind both.
-    if (!c->in_stream) {
-        CU(c, cudaStreamCreateWithFlags(&c->in_stream, cudaStreamNonBlocking));
-        CU(c, cudaEventCreateWithFlags(&c->ev_in_done, cudaEventDisableTiming));
-        CU(c, cudaEventCreateWithFlags(&c->ev_in_free, cudaEventDisableTiming));
-    }
-    const size_t need = n * 7 * sizeof(float);
-    if (need > c->in_bytes) {
-        cudaFree(c->d_in);   // (synchronises the device: no copy into the old buffer is in flight afterwards)
-        c->d_in = nullptr; c->in_bytes = 0;
-        CU(c, cudaMalloc(&c->d_in, need));
-        c->in_bytes = need;
-    }
+    int rc = stage_in_begin(c, n * 7 * sizeof(float));
+    if (rc) return rc;
     float* d_pos = c->d_in;
     float* d_vel = d_pos + 3 * n;
     float* d_mass = d_vel + 3 * n;
-    if (c->in_used) CU(c, cudaStreamWaitEvent(c->in_stream, c->ev_in_free, 0));   // the previous upload's pack kernel has read the buffer
     CU(c, cudaMemcpyAsync(d_pos, pos3, n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->in_stream));
     if (vel3) CU(c, cudaMemcpyAsync(d_vel, vel3, n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->in_stream));
     if (mass) CU(c, cudaMemcpyAsync(d_mass, mass, n * sizeof(float), cudaMemcpyHostToDevice, c->in_stream));
-    CU(c, cudaEventRecord(c->ev_in_done, c->in_stream));
-    CU(c, cudaStreamWaitEvent(c->stream, c->ev_in_done, 0));
-    int rc = reset_box_and_speed(c);
+    rc = stage_in_commit(c);
+    if (rc) return rc;
+    rc = reset_box_and_speed(c);
     if (rc) return rc;
     c->stats.kernel_launches += launch_pack_upload(n, d_pos, vel3 ? d_vel : nullptr, mass ? d_mass : nullptr,
                                                    c->prm.particle_mass, c->posm[0], c->velid[0], c->sc, c->stream);
     c->stats.kernel_launches += launch_bbox(n, c->posm[0], c->d_box, c->stream);
-    CU(c, cudaEventRecord(c->ev_in_free, c->stream));
-    c->in_used = true;
+    rc = stage_in_release(c);
+    if (rc) return rc;
     CU(c, cudaGetLastError());
     return after_upload(c, n);
 }
@@ -709,26 +726,33 @@ int sphb_download_end(sphb_ctx* c) {
     return SPHB_OK;
 }
 
-int sphb_download_begin(sphb_ctx* c, float* pos3, float* vel3, float* rho, float* pressure, float* acc3) {
-    if (!c) return SPHB_E_INVALID;
-    if (c->slab_on) return fail(c, SPHB_E_INVALID, "slab mode: ids are global, use sphb_slab_download");
-    CU(c, cudaSetDevice(c->device));
-    int rc = sphb_download_end(c);   // one transfer in flight: its staging buffer (and the caller's arrays) are reused
+// staging of an asynchronous read-back: waits for the previous one (one transfer in flight: its staging buffer and the
+// caller's arrays are reused), then makes sure the stream, the events and `bytes` of staging exist
+static int stage_out_begin(sphb_ctx* c, size_t bytes) {
+    int rc = sphb_download_end(c);
     if (rc) return rc;
-    const size_t n = c->n;
-    if (n == 0) return SPHB_OK;
     if (!c->out_stream) {
         CU(c, cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking));
         CU(c, cudaEventCreateWithFlags(&c->ev_out_ready, cudaEventDisableTiming));
         CU(c, cudaEventCreateWithFlags(&c->ev_out_done, cudaEventDisableTiming));
     }
-    const size_t need = n * 11 * sizeof(float);
-    if (need > c->out_bytes) {
+    if (bytes > c->out_bytes) {
         cudaFree(c->d_out);
         c->d_out = nullptr; c->out_bytes = 0;
-        CU(c, cudaMalloc(&c->d_out, need));
-        c->out_bytes = need;
+        CU(c, cudaMalloc(&c->d_out, bytes));
+        c->out_bytes = bytes;
     }
+    return SPHB_OK;
+}
+
+int sphb_download_begin(sphb_ctx* c, float* pos3, float* vel3, float* rho, float* pressure, float* acc3) {
+    if (!c) return SPHB_E_INVALID;
+    if (c->slab_on) return fail(c, SPHB_E_INVALID, "slab mode: ids are global, use sphb_slab_download");
+    CU(c, cudaSetDevice(c->device));
+    const size_t n = c->n;
+    int rc = stage_out_begin(c, n * 11 * sizeof(float));
+    if (rc) return rc;
+    if (n == 0) return SPHB_OK;
     float* d_pos = c->d_out;
     float* d_vel = d_pos + 3 * n;
     float* d_acc = d_vel + 3 * n;
@@ -1198,22 +1222,26 @@ int sphb_upload_ids(sphb_ctx* c, size_t n, const float* pos3, const float* vel3,
     if (n > 0 && (!pos3 || !ids)) return fail(c, SPHB_E_INVALID, "pos3 / ids is NULL");
     CU(c, cudaSetDevice(c->device));
     if (n == 0) return after_upload(c, 0);
-    int rc = ensure_stage(c, n * 8 * sizeof(float));
+    int rc = stage_in_begin(c, n * 8 * sizeof(float));
     if (rc) return rc;
-    float* d_pos = reinterpret_cast<float*>(c->d_stage);
+    float* d_pos = c->d_in;
     float* d_vel = d_pos + 3 * n;
     float* d_mass = d_vel + 3 * n;
     uint32_t* d_ids = reinterpret_cast<uint32_t*>(d_mass + n);
-    CU(c, cudaMemcpyAsync(d_pos, pos3, n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    if (vel3) CU(c, cudaMemcpyAsync(d_vel, vel3, n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    if (mass) CU(c, cudaMemcpyAsync(d_mass, mass, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaMemcpyAsync(d_ids, ids, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(d_pos, pos3, n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->in_stream));
+    if (vel3) CU(c, cudaMemcpyAsync(d_vel, vel3, n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->in_stream));
+    if (mass) CU(c, cudaMemcpyAsync(d_mass, mass, n * sizeof(float), cudaMemcpyHostToDevice, c->in_stream));
+    CU(c, cudaMemcpyAsync(d_ids, ids, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->in_stream));
+    rc = stage_in_commit(c);
+    if (rc) return rc;
     rc = reset_box_and_speed(c);
     if (rc) return rc;
     c->stats.kernel_launches += launch_pack_upload_ids(n, d_pos, vel3 ? d_vel : nullptr, mass ? d_mass : nullptr, d_ids,
                                                        c->prm.particle_mass, c->posm[0], c->velid[0], c->stream);
     c->stats.kernel_launches += launch_max_speed(n, c->velid[0], c->sc, c->stream);
     c->stats.kernel_launches += launch_bbox(n, c->posm[0], c->d_box, c->stream);
+    rc = stage_in_release(c);
+    if (rc) return rc;
     CU(c, cudaGetLastError());
     return after_upload(c, n);
 }
@@ -1345,6 +1373,69 @@ int sphb_slab_download(sphb_ctx* c, size_t cap, uint32_t* ids, float* pos3, floa
     return SPHB_OK;
 }
 
+
+// sphb_slab_download in two halves (see sphb_download_begin): the number of owned particles is only known on the device
+// when the copies are enqueued, so they move min(cap, particles held incl. halo copies) entries per field; _end waits and
+// reports how many of them are owned particles (the compacted front of every array).
+int sphb_slab_download_begin(sphb_ctx* c, size_t cap, uint32_t* ids, float* pos3, float* vel3, float* rho, float* pressure, float* acc3) {
+    if (!c || !ids) return SPHB_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    const size_t n = c->n;
+    int rc = stage_out_begin(c, n * 12 * sizeof(float));
+    if (rc) return rc;
+    if (!c->h_box) CU(c, cudaMallocHost(&c->h_box, 8 * sizeof(int)));
+    c->h_box[6] = 0;
+    c->out_cap = cap;
+    if (n == 0) return SPHB_OK;
+    float* d_pos = c->d_out;
+    float* d_vel = d_pos + 3 * n;
+    float* d_acc = d_vel + 3 * n;
+    float* d_rho = d_acc + 3 * n;
+    float* d_P = d_rho + n;
+    uint32_t* d_ids = reinterpret_cast<uint32_t*>(d_P + n);
+    CU(c, cudaMemsetAsync(c->d_counts, 0, sizeof(unsigned int), c->stream));
+    c->stats.kernel_launches += launch_slab_export(n, c->posm[c->cur], c->velid[c->cur], c->rho_p, c->acc, d_ids, pos3 ? d_pos : nullptr,
+                                                   vel3 ? d_vel : nullptr, rho ? d_rho : nullptr, pressure ? d_P : nullptr,
+                                                   acc3 ? d_acc : nullptr, c->d_counts, c->stream);
+    // the owned count goes to pinned host memory by a kernel (word 6 of the read-back block; no copy engine involved)
+    c->stats.kernel_launches += sphb::launch_word_to_host(reinterpret_cast<const int*>(c->d_counts), c->h_box + 6, c->stream);
+    CU(c, cudaGetLastError());
+    CU(c, cudaEventRecord(c->ev_out_ready, c->stream));
+    CU(c, cudaStreamWaitEvent(c->out_stream, c->ev_out_ready, 0));
+    const size_t m = n < cap ? n : cap;
+    CU(c, cudaMemcpyAsync(ids, d_ids, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->out_stream));
+    if (pos3) CU(c, cudaMemcpyAsync(pos3, d_pos, m * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->out_stream));
+    if (vel3) CU(c, cudaMemcpyAsync(vel3, d_vel, m * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->out_stream));
+    if (acc3) CU(c, cudaMemcpyAsync(acc3, d_acc, m * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->out_stream));
+    if (rho) CU(c, cudaMemcpyAsync(rho, d_rho, m * sizeof(float), cudaMemcpyDeviceToHost, c->out_stream));
+    if (pressure) CU(c, cudaMemcpyAsync(pressure, d_P, m * sizeof(float), cudaMemcpyDeviceToHost, c->out_stream));
+    CU(c, cudaEventRecord(c->ev_out_done, c->out_stream));
+    c->out_pending = true;
+    return SPHB_OK;
+}
+
+int sphb_slab_download_end(sphb_ctx* c, size_t* count) {
+    if (!c || !count) return SPHB_E_INVALID;
+    int rc = sphb_download_end(c);
+    if (rc) return rc;
+    const size_t h = c->h_box ? (size_t)(unsigned int)c->h_box[6] : 0;
+    *count = h;
+    if (h > c->out_cap) return fail(c, SPHB_E_CAPACITY, "%zu owned particles exceed the output capacity %zu", h, c->out_cap);
+    return SPHB_OK;
+}
+
+// A small device buffer (the gathered table of exchange group sizes) into PINNED host memory by a kernel on the context's
+// stream — not by a device-to-host copy, which would queue on the copy engine behind a bulk read-back still in flight
+// (sphb_slab_download_begin) and stall the step behind it.  Enqueue only: the caller synchronises the stream.
+int sphb_read_small(sphb_ctx* c, const void* d_src, void* h_dst_pinned, size_t bytes) {
+    if (!c || !d_src || !h_dst_pinned) return SPHB_E_INVALID;
+    if (bytes % 4 || bytes > (1u << 20)) return fail(c, SPHB_E_INVALID, "sphb_read_small: %zu bytes (a multiple of 4, at most 1 MiB)", bytes);
+    CU(c, cudaSetDevice(c->device));
+    c->stats.kernel_launches += sphb::launch_words_to_host(static_cast<const uint32_t*>(d_src), static_cast<uint32_t*>(h_dst_pinned),
+                                                           (unsigned)(bytes / 4), c->stream);
+    CU(c, cudaGetLastError());
+    return SPHB_OK;
+}
 
 int sphb_get_cfl_state(sphb_ctx* c, float* max_v2, float* a0_xyz, int* a0_fresh) {
     if (!c) return SPHB_E_INVALID;

@@ -376,6 +376,23 @@ int launch_box_to_host(const int* d_box, int* h_box_pinned, cudaStream_t st) {
     k_box_to_host<<<1, 32, 0, st>>>(d_box, h_box_pinned);
     return 1;
 }
+namespace {
+__global__ void k_word_to_host(const int* __restrict__ d_word, volatile int* h_word) { *h_word = *d_word; }
+}  // namespace
+int launch_word_to_host(const int* d_word, int* h_word_pinned, cudaStream_t st) {
+    k_word_to_host<<<1, 1, 0, st>>>(d_word, h_word_pinned);
+    return 1;
+}
+namespace {
+__global__ void k_words_to_host(const uint32_t* __restrict__ d_src, volatile uint32_t* h_dst, unsigned nwords) {
+    for (unsigned k = threadIdx.x; k < nwords; k += blockDim.x) h_dst[k] = d_src[k];
+}
+}  // namespace
+int launch_words_to_host(const uint32_t* d_src, uint32_t* h_dst_pinned, unsigned nwords, cudaStream_t st) {
+    if (nwords == 0) return 0;
+    k_words_to_host<<<1, 256, 0, st>>>(d_src, h_dst_pinned, nwords);
+    return 1;
+}
 
 int launch_unpack_strided(size_t n, const unsigned char* d_base, size_t stride, size_t off_pos, size_t off_vel, size_t off_mass,
                           float4* posm, float4* velid, DeviceScalars* sc, cudaStream_t st) {

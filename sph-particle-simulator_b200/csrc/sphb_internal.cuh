@@ -178,6 +178,8 @@ int launch_density_mask_wide(const PairArgs& a, cudaStream_t st);   // R = 2, 3
 int launch_force_mask_wide(const PairArgs& a, cudaStream_t st);
 
 int launch_box_to_host(const int* d_box, int* h_box_pinned, cudaStream_t st);   // kernel-written read-back (no copy engine)
+int launch_word_to_host(const int* d_word, int* h_word_pinned, cudaStream_t st);
+int launch_words_to_host(const uint32_t* d_src, uint32_t* h_dst_pinned, unsigned nwords, cudaStream_t st);
 int launch_cfl_probe(DeviceScalars* sc, IntegrateConsts ic, cudaStream_t st);   // sphb_cfl_timestep: sc->dt = the CFL rule, nothing consumed
 int launch_integrate(size_t n, float4* posm, float4* velid, const float4* acc, IntegrateConsts ic, DeviceScalars* sc,
                      int* d_box_or_null, cudaStream_t st);

@@ -243,7 +243,10 @@ def step_distributed(r: SlabRank, dt: float, group=None):
         # after it (record split, all_to_all, append, the local step) is enqueued without further waiting
         r.store.exchange_count(r.cuts, me, r.d_counts)
         dist.all_gather_into_tensor(r.d_table.view(-1), r.d_counts, group=group)
-        r.h_table.copy_(r.d_table, non_blocking=True)
+        if dev.type == "cuda":    # kernel-written read-back: a copy would queue behind a bulk read-back in flight on the copy engine
+            r.store.ctx.read_small(r.d_table.data_ptr(), r.h_table.data_ptr(), r.d_table.numel() * r.d_table.element_size())
+        else:
+            r.h_table.copy_(r.d_table, non_blocking=True)
         if dev.type == "cuda":
             torch.cuda.current_stream(dev).synchronize()
         table = r.h_table.numpy().astype(np.int64)

@@ -237,3 +237,43 @@ def test_cfl_limited_adaptive_timestep_across_slabs(pkg, po, name):
     for r in ranks:
         assert np.float32(r.store.ctx.get_time()[0]) == np.float32(case["times"][-1])
         r.store.close()
+
+
+def test_slab_download_begin_end(pkg):
+    """sphb_slab_download_begin / _end (the read-back that overlaps the next upload): same owned set and fields as the
+    synchronous sphb_slab_download, count reported by _end; an output capacity below the owned count is an error."""
+    import torch
+    from sph_b200 import scenes, slab
+    pos, mass, params, dt = scenes.dam_break_scene(0.02)
+    n = len(pos)
+    nsr = float(params["neighbor_search_radius"])
+    cuts = slab.plan_cuts(slab.axis_cells(pos, 2, nsr), 2, 2)
+    box_min = np.minimum(pos.min(0), [params["xmin"], params["ymin"], params["zmin"]])
+    box_max = np.maximum(pos.max(0), [params["xmax"], params["ymax"], params["zmax"]])
+    ranks = []
+    for d in range(2):
+        store = slab.GpuStore(pkg, n, 0, params, strict=False)
+        ranks.append(slab.SlabRank(store, d, cuts, 2, 2, n, box_min, box_max, 3 * n))
+        ranks[-1].load_initial(pos, None, mass, nsr)
+    for _ in range(3):
+        slab.step_local(ranks, dt)
+    for r in ranks:
+        ctx = r.store.ctx
+        want = ctx.slab_download()
+        cap = ctx.size
+        ids = torch.empty((cap,), dtype=torch.int32).pin_memory()
+        p = torch.empty((cap, 3), dtype=torch.float32).pin_memory()
+        v = torch.empty((cap, 3), dtype=torch.float32).pin_memory()
+        rho = torch.empty((cap,), dtype=torch.float32).pin_memory()
+        ctx.slab_download_begin_raw(cap, ids.data_ptr(), p.data_ptr(), v.data_ptr(), rho.data_ptr(), None, None)
+        k = ctx.slab_download_end()
+        assert k == len(want["ids"]) and 0 < k < cap                       # the slab also holds halo copies
+        order_a, order_b = np.argsort(ids.numpy()[:k].view(np.uint32)), np.argsort(want["ids"])
+        assert_bits(ids.numpy()[:k].view(np.uint32)[order_a], want["ids"][order_b], "ids")
+        assert_bits(p.numpy()[:k][order_a], want["pos"][order_b], "pos")
+        assert_bits(v.numpy()[:k][order_a], want["vel"][order_b], "vel")
+        assert_bits(rho.numpy()[:k][order_a], want["rho"][order_b], "rho")
+        ctx.slab_download_begin_raw(k - 1, ids.data_ptr(), None, None, None, None, None)
+        with pytest.raises(pkg.SphbError):
+            ctx.slab_download_end()
+        r.store.close()
