@@ -277,3 +277,21 @@ def test_slab_download_begin_end(pkg):
         with pytest.raises(pkg.SphbError):
             ctx.slab_download_end()
         r.store.close()
+
+
+def test_read_small_kernel_written_readback(pkg):
+    """sphb_read_small: the exchange driver's read-back of the gathered group-size table — a kernel writes it into pinned
+    host memory (a device-to-host copy would queue on the copy engine behind a bulk read-back in flight)."""
+    import torch
+    ctx = pkg.Context(16, 0)
+    d = torch.arange(1, 129, dtype=torch.int32, device="cuda:0") * 7
+    h = torch.zeros(128, dtype=torch.int32).pin_memory()
+    torch.cuda.synchronize()
+    ctx.read_small(d.data_ptr(), h.data_ptr(), 128 * 4)
+    ctx.synchronize()
+    assert torch.equal(h, d.cpu())
+    with pytest.raises(pkg.SphbError):
+        ctx.read_small(d.data_ptr(), h.data_ptr(), 6)            # not a multiple of 4
+    with pytest.raises(pkg.SphbError):
+        ctx.read_small(d.data_ptr(), h.data_ptr(), 4 << 20)      # not small
+    ctx.close()
