@@ -20,10 +20,76 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "sphb_internal.cuh"
+
+// One worker thread per device: the phases of a step (count, split + copies, append + local step) are enqueued on all
+// devices at once.  A single host thread needs ~40 us per device to enqueue a local step; with 8 devices and 2 ms steps
+// (strong scaling) the last device would start 0.3 ms late every step.
+struct DeviceWorkers {
+    std::vector<std::thread> threads;
+    std::mutex mu;
+    std::condition_variable cv_go, cv_done;
+    std::function<int(int)> job;
+    std::vector<int> rc;
+    uint64_t generation = 0;
+    int pending = 0;
+    bool stop = false;
+
+    void start(int n) {
+        rc.assign((size_t)n, 0);
+        for (int d = 0; d < n; ++d) threads.emplace_back([this, d] { loop(d); });
+    }
+    void loop(int d) {
+        uint64_t seen = 0;
+        for (;;) {
+            std::function<int(int)> fn;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_go.wait(lk, [&] { return stop || generation != seen; });
+                if (stop) return;
+                seen = generation;
+                fn = job;
+            }
+            const int r = fn(d);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                rc[(size_t)d] = r;
+                if (--pending == 0) cv_done.notify_one();
+            }
+        }
+    }
+    // runs fn(d) for every device concurrently and waits; returns the first non-zero result
+    int run(const std::function<int(int)>& fn) {
+        if (threads.empty()) return 0;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            job = fn;
+            pending = (int)threads.size();
+            ++generation;
+        }
+        cv_go.notify_all();
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return pending == 0; });
+        for (int r : rc) if (r) return r;
+        return 0;
+    }
+    void shutdown() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv_go.notify_all();
+        for (auto& t : threads) t.join();
+        threads.clear();
+    }
+};
 
 struct sphb_multi {
     int ndev = 0;
@@ -50,6 +116,8 @@ struct sphb_multi {
     uint64_t rebalances = 0;
     uint64_t rebalance_min = 32768;           // ... and at least this many particles above it (SPHB_OPT_MULTI_REBALANCE_MIN)
     std::string err;
+    std::vector<std::string> err_dev;         // per device: message of a failure inside a worker
+    DeviceWorkers workers;
 };
 
 namespace {
@@ -251,12 +319,15 @@ int sphb_create_multi(sphb_multi** out, size_t capacity, int ndev, const int* de
         }
     }
     if (cudaMallocHost(&m->h_table, (size_t)ndev * 2 * ndev * sizeof(uint32_t)) != cudaSuccess) return bail(SPHB_E_CUDA, "pinned count table");
+    m->err_dev.assign((size_t)ndev, std::string());
+    if (ndev > 1) m->workers.start(ndev);
     *out = m;
     return SPHB_OK;
 }
 
 void sphb_destroy_multi(sphb_multi* m) {
     if (!m) return;
+    m->workers.shutdown();
     for (int d = 0; d < m->ndev; ++d) { cudaSetDevice(m->devs[d]); if (m->streams[d]) cudaStreamSynchronize(m->streams[d]); }
     release(m);
     delete m;
@@ -372,15 +443,39 @@ int sphb_multi_step(sphb_multi* m, float dt) {
         if (rc != SPHB_OK) return rc;
     }
     const int32_t* cuts = m->cuts.data();
-    // count: enqueue on every device, then ONE host wait for all of them
-    for (int d = 0; d < G; ++d) {
-        MCTX(m, d, sphb_slab_exchange_count(m->ctx[d], cuts, G, d, m->d_counts[d]));
-        MCU(m, cudaSetDevice(m->devs[d]));
-        MCU(m, cudaMemcpyAsync(m->h_table + (size_t)d * 2 * G, m->d_counts[d], 2 * G * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->streams[d]));
-    }
-    for (int d = 0; d < G; ++d) { MCU(m, cudaSetDevice(m->devs[d])); MCU(m, cudaStreamSynchronize(m->streams[d])); }
-    // split: records grouped by destination in send[d]; block r = [owned by r (none for r = d)][ghosts for r]
-    std::vector<size_t> soff((size_t)G * (G + 1), 0), rin((size_t)G, 0);
+    // what a worker reports: the context's own message, or the CUDA error of a call it made for its device
+    auto ctx_fail = [m](int d, int rc) {
+        const char* e = sphb_last_error(m->ctx[(size_t)d]);
+        m->err_dev[(size_t)d] = std::string("device ") + std::to_string(m->devs[(size_t)d]) + ": " + (e ? e : "error");
+        return rc;
+    };
+    auto cuda_fail = [m](int d, const char* what, cudaError_t e) {
+        m->err_dev[(size_t)d] = std::string("device ") + std::to_string(m->devs[(size_t)d]) + ": " + what + ": " + cudaGetErrorString(e);
+        return (int)SPHB_E_CUDA;
+    };
+    auto phase = [m](const std::function<int(int)>& fn) {
+        const int rc = m->workers.run(fn);
+        if (rc != SPHB_OK)
+            for (const std::string& e : m->err_dev) if (!e.empty()) { m->err = e; break; }
+        for (std::string& e : m->err_dev) e.clear();
+        return rc;
+    };
+#define WCTX(d, call) do { const int rc_ = (call); if (rc_ != SPHB_OK) return ctx_fail(d, rc_); } while (0)
+#define WCU(d, call) do { const cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(d, #call, e_); } while (0)
+
+    // count: every device counts and copies its row of group sizes out — the step's ONE host wait, taken on all devices at once
+    int rc = phase([&](int d) -> int {
+        WCU(d, cudaSetDevice(m->devs[(size_t)d]));
+        WCTX(d, sphb_slab_exchange_count(m->ctx[(size_t)d], cuts, G, d, m->d_counts[(size_t)d]));
+        WCU(d, cudaMemcpyAsync(m->h_table + (size_t)d * 2 * G, m->d_counts[(size_t)d], 2 * G * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                               m->streams[(size_t)d]));
+        WCU(d, cudaStreamSynchronize(m->streams[(size_t)d]));
+        return SPHB_OK;
+    });
+    if (rc != SPHB_OK) return rc;
+    // layout of the exchange: send[d] holds, for r = 0..G-1, [owned by r (none for r = d)][ghosts for r]; in recv[dst] the block
+    // of every source lands behind the previous sources' blocks
+    std::vector<size_t> soff((size_t)G * (G + 1), 0), roff((size_t)G * G, 0), rin((size_t)G, 0);
     for (int d = 0; d < G; ++d) {
         const uint32_t* row = m->h_table + (size_t)d * 2 * G;
         size_t off = 0;
@@ -390,10 +485,7 @@ int sphb_multi_step(sphb_multi* m, float dt) {
         }
         soff[(size_t)d * (G + 1) + G] = off;
         if (off > m->xcap) return mfail(m, SPHB_E_CAPACITY, "device %d sends %zu records, more than the exchange buffer (%zu)", m->devs[d], off, m->xcap);
-        MCTX(m, d, sphb_slab_exchange_split(m->ctx[d], cuts, G, d, row, m->send[d], m->xcap));
     }
-    // copy: source-major, each destination's block of every source lands behind the previous sources' blocks
-    std::vector<size_t> roff((size_t)G * G, 0);
     for (int dst = 0; dst < G; ++dst) {
         size_t off = 0;
         for (int src = 0; src < G; ++src) {
@@ -416,39 +508,64 @@ int sphb_multi_step(sphb_multi* m, float dt) {
         const uint64_t even = m->n_total / (uint64_t)std::max(1, m->active);
         if (most * 2 > even * 3 && most > even + m->rebalance_min) m->want_rebalance = true;
     }
-    for (int src = 0; src < G; ++src) {
-        MCU(m, cudaSetDevice(m->devs[src]));
+    // split + copy: every source groups its records by destination and pushes each block to its destination's receive buffer
+    rc = phase([&](int src) -> int {
+        WCU(src, cudaSetDevice(m->devs[(size_t)src]));
+        WCTX(src, sphb_slab_exchange_split(m->ctx[(size_t)src], cuts, G, src, m->h_table + (size_t)src * 2 * G, m->send[(size_t)src], m->xcap));
         for (int dst = 0; dst < G; ++dst) {
             const size_t cnt = soff[(size_t)src * (G + 1) + dst + 1] - soff[(size_t)src * (G + 1) + dst];
             if (!cnt) continue;
             // recv[dst] may still be read by dst's append of the previous step
-            MCU(m, cudaStreamWaitEvent(m->streams[src], m->ev_appended[dst], 0));
-            const float4* from = m->send[src] + 2 * soff[(size_t)src * (G + 1) + dst];
-            float4* to = m->recv[dst] + 2 * roff[(size_t)src * G + dst];
-            if (m->devs[src] == m->devs[dst]) MCU(m, cudaMemcpyAsync(to, from, cnt * 2 * sizeof(float4), cudaMemcpyDeviceToDevice, m->streams[src]));
-            else MCU(m, cudaMemcpyPeerAsync(to, m->devs[dst], from, m->devs[src], cnt * 2 * sizeof(float4), m->streams[src]));
+            WCU(src, cudaStreamWaitEvent(m->streams[(size_t)src], m->ev_appended[(size_t)dst], 0));
+            const float4* from = m->send[(size_t)src] + 2 * soff[(size_t)src * (G + 1) + dst];
+            float4* to = m->recv[(size_t)dst] + 2 * roff[(size_t)src * G + dst];
+            if (m->devs[(size_t)src] == m->devs[(size_t)dst])
+                WCU(src, cudaMemcpyAsync(to, from, cnt * 2 * sizeof(float4), cudaMemcpyDeviceToDevice, m->streams[(size_t)src]));
+            else
+                WCU(src, cudaMemcpyPeerAsync(to, m->devs[(size_t)dst], from, m->devs[(size_t)src], cnt * 2 * sizeof(float4), m->streams[(size_t)src]));
         }
-        MCU(m, cudaEventRecord(m->ev_sent[src], m->streams[src]));
-    }
-    // append what arrived (after every source's copies), then the local step
-    for (int dst = 0; dst < G; ++dst) {
-        MCU(m, cudaSetDevice(m->devs[dst]));
-        for (int src = 0; src < G; ++src) MCU(m, cudaStreamWaitEvent(m->streams[dst], m->ev_sent[src], 0));
-        MCTX(m, dst, sphb_slab_append(m->ctx[dst], m->recv[dst], rin[(size_t)dst], -1));
-        MCU(m, cudaEventRecord(m->ev_appended[dst], m->streams[dst]));
-    }
-    if (dt <= 0.0f) {   // adaptive: global max |v|^2, the acceleration of particle 0 from the device that advanced it
+        WCU(src, cudaEventRecord(m->ev_sent[(size_t)src], m->streams[(size_t)src]));
+        return SPHB_OK;
+    });
+    if (rc != SPHB_OK) return rc;
+    // append what arrived (after every source's copies: their records are enqueued, the phase above has returned)
+    const bool adaptive = dt <= 0.0f;
+    std::vector<float> v2s((size_t)G, 0.0f), a0s((size_t)3 * G, 0.0f);
+    std::vector<int> fresh((size_t)G, 0);
+    auto append = [&](int dst) -> int {
+        WCU(dst, cudaSetDevice(m->devs[(size_t)dst]));
+        for (int src = 0; src < G; ++src) WCU(dst, cudaStreamWaitEvent(m->streams[(size_t)dst], m->ev_sent[(size_t)src], 0));
+        WCTX(dst, sphb_slab_append(m->ctx[(size_t)dst], m->recv[(size_t)dst], rin[(size_t)dst], -1));
+        WCU(dst, cudaEventRecord(m->ev_appended[(size_t)dst], m->streams[(size_t)dst]));
+        return SPHB_OK;
+    };
+    if (adaptive) {   // global max |v|^2, the acceleration of particle 0 from the device that advanced it: one more rendezvous
+        rc = phase([&](int d) -> int {
+            const int r = append(d);
+            if (r != SPHB_OK) return r;
+            WCTX(d, sphb_get_cfl_state(m->ctx[(size_t)d], &v2s[(size_t)d], &a0s[(size_t)3 * d], &fresh[(size_t)d]));
+            return SPHB_OK;
+        });
+        if (rc != SPHB_OK) return rc;
         float v2max = 0.0f;
         for (int d = 0; d < G; ++d) {
-            float v2 = 0.0f, a0[3] = {0.0f, 0.0f, 0.0f};
-            int fresh = 0;
-            MCTX(m, d, sphb_get_cfl_state(m->ctx[d], &v2, a0, &fresh));
-            if (v2 > v2max) v2max = v2;
-            if (fresh) { m->a0[0] = a0[0]; m->a0[1] = a0[1]; m->a0[2] = a0[2]; }
+            if (v2s[(size_t)d] > v2max) v2max = v2s[(size_t)d];
+            if (fresh[(size_t)d]) { m->a0[0] = a0s[(size_t)3 * d]; m->a0[1] = a0s[(size_t)3 * d + 1]; m->a0[2] = a0s[(size_t)3 * d + 2]; }
         }
         dt = cfl_timestep(m->prm, v2max, m->a0);
     }
-    for (int d = 0; d < G; ++d) MCTX(m, d, sphb_step(m->ctx[d], dt));
+    // ... then the local step
+    rc = phase([&](int d) -> int {
+        if (!adaptive) {
+            const int r = append(d);
+            if (r != SPHB_OK) return r;
+        }
+        WCTX(d, sphb_step(m->ctx[(size_t)d], dt));
+        return SPHB_OK;
+    });
+    if (rc != SPHB_OK) return rc;
+#undef WCTX
+#undef WCU
     m->step_count++;
     return SPHB_OK;
 }
