@@ -104,7 +104,7 @@ struct sphb_multi {
     std::vector<int32_t> cuts;
     int axis = -1;                            // -1: the longest axis of the uploaded particles' bounding box
     int slab_axis = -1;                       // the axis the current cuts are on
-    int layers = 2;                           // halo layers per face (SPHB_OPT_MULTI_HALO_LAYERS)
+    int layers = 2;                           // halo layers per face: 2 = the minimum (SPHB_OPT_MULTI_HALO_LAYERS: wider halos for diagnosis)
     int active = 0;                           // slabs that own cells (the last `active` devices; the others own an empty range)
     sphb_params prm{};
     bool have_params = false, planned = false;
@@ -122,7 +122,6 @@ struct sphb_multi {
 
 namespace {
 
-constexpr int kLayers = 2;   // halo layers per face (SPHB_OPT_MULTI_HALO_LAYERS overrides: wider halos for diagnosis)
 
 int mfail(sphb_multi* m, int code, const char* fmt, ...) {
     char buf[512];
